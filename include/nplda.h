@@ -1,0 +1,184 @@
+/*
+ * nplda.h -- C ABI of libnplda.so: B200 (sm_100a) kernels for the pairwise
+ * trial-scoring hot path of iiscleap/NeuralPlda.
+ *
+ * The reference has no FFI: the path sits behind a Python torch.nn.Module API
+ * (/root/reference/utils/models.py).  Each entry point below names the
+ * reference interface it replaces; neuralplda_b200/models.py binds them with
+ * ctypes and keeps the reference's class / method signatures.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current device unless its name
+ *    ends in _host; fp32 tensors are contiguous row-major; the caller owns all
+ *    buffers (PyTorch allocations); the library keeps no global mutable state
+ *    and allocates nothing that outlives a call except explicit workspaces
+ *    the caller passes in.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
+ *    and nothing synchronises unless stated.
+ *  - return value: 0 = OK; > 0 = a cudaError_t; < 0 = NPLDA_ERR_*.
+ *    nplda_error_string() renders either.  Nothing throws or exits.
+ *  - there is no CPU fallback anywhere in this library.
+ */
+#ifndef NPLDA_H_
+#define NPLDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPLDA_OK 0
+#define NPLDA_ERR_BAD_ARG (-1)        /* null pointer, negative size, misaligned buffer     */
+#define NPLDA_ERR_UNSUPPORTED_DIM (-2) /* layer widths beyond what the kernels are built for */
+#define NPLDA_ERR_WORKSPACE (-3)      /* workspace too small                                 */
+#define NPLDA_ERR_NO_DEVICE (-4)      /* no sm_100 device / kernel image not loadable        */
+
+/* kernel selection for the score kernels */
+#define NPLDA_IMPL_AUTO 0   /* tcgen05 path when the shape allows, else SIMT */
+#define NPLDA_IMPL_SIMT 1   /* fp32 FFMA2 register-tiled kernel (any supported shape) */
+#define NPLDA_IMPL_TC 2     /* tcgen05 split-bf16 tensor-core kernel (error if shape unsupported) */
+
+/* loss ids, matching the reference's case-sensitive `lossfn` strings (models.py:395-399) */
+#define NPLDA_LOSS_SOFTCDET 0      /* 'SoftCdet'      */
+#define NPLDA_LOSS_CROSSENTROPY 1  /* 'crossentropy'  */
+
+#define NPLDA_MAX_BETAS 8
+
+int nplda_version(void);
+const char *nplda_error_string(int code);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t nplda_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Packed weights.  The score kernels consume the affine layers transposed
+ * (k-major), zero-padded and, for the tensor-core path, split into bf16 hi/lo
+ * images in the tcgen05 shared-memory layout.  Packing is one small kernel; it
+ * must be re-run whenever the parameters change (every optimiser step).
+ * nplda_pack_bytes() gives the workspace size for given dims.
+ * ------------------------------------------------------------------------- */
+int64_t nplda_pack_bytes(int d_in, int d1, int d2);
+
+/* NeuralPlda parameters (models.py:349-363): W1 [d1,d_in], b1 [d1], W2 [d2,d1],
+ * b2 [d2], P_sqrt [d2], Q [d2]. */
+int nplda_pack_weights(const float *W1, const float *b1, const float *W2, const float *b2,
+                       const float *p_sqrt, const float *q, int d_in, int d1, int d2,
+                       void *pack, int64_t pack_bytes, void *stream);
+
+/* DPlda parameters (models.py:464-476): W1 [d1,d_in], b1 [d1],
+ * logistic_regres.weight [2*d1*d1+d1], logistic_regres.bias [1]. */
+int dplda_pack_weights(const float *W1, const float *b1, const float *w_lr, const float *c_lr,
+                       int d_in, int d1, void *pack, int64_t pack_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K1: fused score forward.
+ * Replaces NeuralPlda.forward (models.py:378-382 = extract_plda_embeddings
+ * 366-370 twice + forward_from_plda_embeddings 372-376):
+ *   a = W1 x + b1 ; u = a / max(||a||, 1e-12) ; y = W2 u + b2
+ *   S = sum_k Q_k y1_k^2 + Q_k y2_k^2 + 2 P_sqrt_k^2 y1_k y2_k
+ * x1, x2: [n, d_in] fp32, 16-byte aligned rows when d_in % 4 == 0.
+ * scores: [n] fp32.  n == 0 is a no-op.
+ * ------------------------------------------------------------------------- */
+int nplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2,
+                    const void *pack, float *scores, int impl, void *stream);
+
+/* Replaces DPlda.forward (models.py:491-495; closed form of 483-489):
+ *   u = normalize(W1 x + b1)
+ *   S = u1^T(Wb+Wb^T)u2 + u1^T Ww u1 + u2^T Ww u2 + ws.(u1+u2) + c          */
+int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,
+                    const void *pack, float *scores, int impl, void *stream);
+
+/* Same scores with the pair gather fused in: row i scores table[idx1[i]] vs
+ * table[idx2[i]].  Replaces load_xvec_trials_from_numbatch
+ * (sv_trials_loaders.py:418-426) + forward.  table: [n_rows, d_in] fp32;
+ * idx1, idx2: [n] int64 in [0, n_rows).  Out-of-range indices are an error
+ * reported through *bad_index_flag (device int32, set non-zero), never a fault. */
+int nplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *idx1,
+                            const int64_t *idx2, int64_t n, int d_in, int d1, int d2,
+                            const void *pack, float *scores, int32_t *bad_index_flag, int impl,
+                            void *stream);
+int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *idx1,
+                            const int64_t *idx2, int64_t n, int d_in, int d1, const void *pack,
+                            float *scores, int32_t *bad_index_flag, int impl, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K2: loss / detection-cost accumulators.
+ * One pass over (scores, labels) producing the raw fp64 sums every loss of the
+ * reference is built from.  acc layout (4*K + 4 doubles), ADDED INTO (the
+ * caller zeroes it; per-GPU shards are all-reduced as raw sums before
+ * nplda_loss_finalize):
+ *   for k < K:  acc[4k+0] = sum_i t_i     * sigmoid(alpha (th_k - s_i))   soft miss
+ *               acc[4k+1] = sum_i (1-t_i) * sigmoid(alpha (s_i - th_k))   soft false alarm
+ *               acc[4k+2] = sum_i t_i     * [s_i < th_k]                  hard miss   (cdet)
+ *               acc[4k+3] = sum_i (1-t_i) * [s_i > th_k]                  hard false alarm
+ *   acc[4K+0] = sum t, acc[4K+1] = sum (1-t),
+ *   acc[4K+2] = sum_i BCE(sigmoid(s_i - th_xent), t_i)  (log clamped at -100)
+ *   acc[4K+3] = n
+ * thresholds: [K] fp32 device; th_xent: [1] fp32 device or NULL (= 0, DPlda).
+ * Replaces the reductions inside softcdet (models.py:384-388), crossentropy
+ * (390-393 / 503-506) and cdet (401-404).
+ * ------------------------------------------------------------------------- */
+int nplda_loss_accum(const float *scores, const float *labels, int64_t n, const float *thresholds,
+                     int K, float alpha, const float *th_xent, double *acc, void *stream);
+
+/* out[0] = softcdet, out[1] = crossentropy, out[2] = cdet (hard), all fp32,
+ * computed on the device from (all-reduced) acc; betas_host: [K] doubles. */
+int nplda_loss_finalize(const double *acc, const double *betas_host, int K, float *out,
+                        void *stream);
+
+/* dL/ds_i for loss_id, scaled by *grad_out (device fp32 scalar; NULL = 1), plus
+ * the threshold gradients: dth[k] for SoftCdet (k < K), dth[K] for threshold_Xent.
+ * dth is ADDED INTO (caller zeroes; all-reduce for multi-GPU).  acc must hold
+ * the global label sums (after the all-reduce). */
+int nplda_loss_bwd(const float *scores, const float *labels, int64_t n, const float *thresholds,
+                   const double *betas_host, int K, float alpha, const float *th_xent,
+                   const double *acc, int loss_id, const float *grad_out, float *dscores,
+                   double *dth, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K3: score backward.  Recomputes the activations from x (nothing is saved by
+ * the forward), and ADDS parameter gradients into fp32 buffers shaped like the
+ * parameters (caller zeroes; all-reduce for multi-GPU).  Any gradient pointer
+ * may be NULL to skip it.  workspace: nplda_bwd_workspace_bytes(n, ...) bytes.
+ * Replaces autograd through models.py:366-376 / 478-489.
+ * ------------------------------------------------------------------------- */
+int64_t nplda_bwd_workspace_bytes(int64_t n, int d_in, int d1, int d2);
+int nplda_score_bwd(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2,
+                    const float *W1, const float *b1, const float *W2, const float *b2,
+                    const float *p_sqrt, const float *q, const float *dscores, float *dW1,
+                    float *db1, float *dW2, float *db2, float *dp_sqrt, float *dq, float *dx1,
+                    float *dx2, void *workspace, int64_t workspace_bytes, void *stream);
+int dplda_score_bwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,
+                    const float *W1, const float *b1, const float *w_lr, const float *dscores,
+                    float *dW1, float *db1, float *dw_lr, float *dc_lr, float *dx1, float *dx2,
+                    void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * minC threshold sweep.  Replaces the O(N_t * N) Python loop of
+ * NeuralPlda.minc (models.py:406-421) given the two score populations already
+ * sorted ascending: for every target score s_j, pmiss_j = (count(tgt < s_j) - 1)
+ * or 1 when the count is 0, pfa_j = (count(non >= s_j) - 1) or 1 when 0, both in
+ * fp32 divided by n_t / n_n as fp32, cdet = pmiss + beta_k * pfa, first argmin.
+ * out_min: [K] fp32, out_arg: [K] int64 (index into tgt_sorted).
+ * ------------------------------------------------------------------------- */
+int nplda_minc_sweep(const float *tgt_sorted, int64_t n_t, const float *non_sorted, int64_t n_n,
+                     float sum_t, float sum_n, const double *betas_host, int K, float *out_min,
+                     int64_t *out_arg, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Host-buffer entry (what a non-PyTorch caller binds, and what bench.py's e2e
+ * leg times): x1_host/x2_host are host buffers (pinned for full speed), scores
+ * come back in scores_host.  Copies are chunked and overlapped with the score
+ * kernel on internal streams; the call returns after the last D2H completes.
+ * pack is a device pointer from nplda_pack_weights.  dev_scratch: device buffer
+ * of nplda_host_scratch_bytes(chunk_pairs, d_in) bytes.
+ * ------------------------------------------------------------------------- */
+int64_t nplda_host_scratch_bytes(int64_t chunk_pairs, int d_in);
+int nplda_score_fwd_host(const float *x1_host, const float *x2_host, int64_t n, int d_in, int d1,
+                         int d2, const void *pack, float *scores_host, int64_t chunk_pairs,
+                         void *dev_scratch, int64_t dev_scratch_bytes, int is_dplda, int impl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPLDA_H_ */

@@ -1,0 +1,121 @@
+"""ctypes binding of libnplda.so (the C ABI declared in include/nplda.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` /
+``make -C neuralplda_b200/csrc`` and loaded lazily on first use.  There is no
+fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnplda.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+LOSS_SOFTCDET, LOSS_CROSSENTROPY = 0, 1
+MAX_BETAS = 8
+
+_lib = None
+_lock = threading.Lock()
+
+c_f32p = ctypes.c_void_p   # device pointers travel as integers
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); one entry per symbol declared in include/nplda.h
+SIGNATURES = {
+    "nplda_version": (c_int, []),
+    "nplda_error_string": (ctypes.c_char_p, [c_int]),
+    "nplda_launch_count": (c_i64, []),
+    "nplda_pack_bytes": (c_i64, [c_int, c_int, c_int]),
+    "nplda_pack_weights": (c_int, [c_vp] * 6 + [c_int] * 3 + [c_vp, c_i64, c_vp]),
+    "dplda_pack_weights": (c_int, [c_vp] * 4 + [c_int] * 2 + [c_vp, c_i64, c_vp]),
+    "nplda_score_fwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "dplda_score_fwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "nplda_score_fwd_indexed": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp,
+                                        c_vp, c_int, c_vp]),
+    "dplda_score_fwd_indexed": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
+                                        c_int, c_vp]),
+    "nplda_loss_accum": (c_int, [c_vp, c_vp, c_i64, c_vp, c_int, ctypes.c_float, c_vp, c_vp, c_vp]),
+    "nplda_loss_finalize": (c_int, [c_vp, ctypes.POINTER(ctypes.c_double), c_int, c_vp, c_vp]),
+    "nplda_loss_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, ctypes.POINTER(ctypes.c_double), c_int,
+                               ctypes.c_float, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "nplda_bwd_workspace_bytes": (c_i64, [c_i64, c_int, c_int, c_int]),
+    "nplda_score_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int] + [c_vp] * 6 + [c_vp] + [c_vp] * 8
+                        + [c_vp, c_i64, c_vp]),
+    "dplda_score_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int] + [c_vp] * 3 + [c_vp] + [c_vp] * 6
+                        + [c_vp, c_i64, c_vp]),
+    "nplda_minc_sweep": (c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
+                                 ctypes.POINTER(ctypes.c_double), c_int, c_vp, c_vp, c_vp]),
+    "nplda_host_scratch_bytes": (c_i64, [c_i64, c_int]),
+    "nplda_score_fwd_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_i64,
+                                     c_int, c_int]),
+}
+
+
+def build(verbose=False):
+    """Compile libnplda.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libnplda.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library, with argtypes set.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU or PyTorch fallback for the scoring path)")
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = L
+    return _lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = lib().nplda_error_string(int(code)).decode()
+        raise RuntimeError(f"libnplda {what} failed ({code}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("neuralplda_b200 scores on the GPU only: got a tensor on "
+                               f"'{t.device}' (there is no CPU fallback; move the module and inputs to cuda)")
+
+
+def launch_count():
+    return int(lib().nplda_launch_count())
+
+
+def betas_array(betas):
+    arr = (ctypes.c_double * max(1, len(betas)))(*[float(b) for b in betas])
+    return arr

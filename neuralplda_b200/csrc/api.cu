@@ -1,0 +1,165 @@
+// C-ABI entry points that are not tied to one kernel file: bookkeeping, the
+// score-forward dispatch (SIMT vs tcgen05) and the host-buffer entry.
+#include <atomic>
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace nplda {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev] = v;
+    }
+    return cached[dev];
+}
+
+int score_simt(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2,
+               int64_t n_rows, int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack,
+               float *scores, cudaStream_t st);   // score_simt.cu
+bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed);   // score_tc.cu
+int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2,
+             int64_t n_rows, int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack,
+             float *scores, cudaStream_t st);   // score_tc.cu
+
+static int score_dispatch(bool dplda, const float *x1, const float *x2, const int64_t *i1,
+                          const int64_t *i2, int64_t n_rows, int32_t *bad_flag, int64_t n, int d_in,
+                          int d1, int d2, const void *pack, float *scores, int impl, void *stream) {
+    const bool indexed = i1 != nullptr || i2 != nullptr;
+    if (n < 0 || !pack || (n > 0 && (!x1 || !scores))) return NPLDA_ERR_BAD_ARG;
+    if (indexed && (!i1 || !i2 || !bad_flag || n_rows <= 0)) return NPLDA_ERR_BAD_ARG;
+    if (!indexed && n > 0 && !x2) return NPLDA_ERR_BAD_ARG;
+    if (impl != NPLDA_IMPL_AUTO && impl != NPLDA_IMPL_SIMT && impl != NPLDA_IMPL_TC) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n == 0) return NPLDA_OK;
+    PackLayout L = make_pack_layout(d_in, d1, d2);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (((uintptr_t)x1 & 15) == 0) && (indexed || ((uintptr_t)x2 & 15) == 0);
+    const bool tc_ok = tc_shape_ok(dplda, L, indexed) && aligned;
+    if (impl == NPLDA_IMPL_TC && !tc_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (impl == NPLDA_IMPL_TC || (impl == NPLDA_IMPL_AUTO && tc_ok))
+        return score_tc(dplda, x1, x2, i1, i2, n_rows, bad_flag, n, L, (const char *)pack, scores, st);
+    return score_simt(dplda, x1, x2, i1, i2, n_rows, bad_flag, n, L, (const char *)pack, scores, st);
+}
+
+}  // namespace nplda
+
+using namespace nplda;
+
+extern "C" int nplda_version(void) { return 100; }
+
+extern "C" int64_t nplda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" const char *nplda_error_string(int code) {
+    switch (code) {
+        case NPLDA_OK: return "ok";
+        case NPLDA_ERR_BAD_ARG: return "nplda: bad argument (null pointer, negative size or misaligned buffer)";
+        case NPLDA_ERR_UNSUPPORTED_DIM: return "nplda: unsupported layer dimensions for this kernel";
+        case NPLDA_ERR_WORKSPACE: return "nplda: workspace too small";
+        case NPLDA_ERR_NO_DEVICE: return "nplda: no usable sm_100 device";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "nplda: unknown error";
+}
+
+extern "C" int nplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2,
+                               const void *pack, float *scores, int impl, void *stream) {
+    return score_dispatch(false, x1, x2, nullptr, nullptr, 0, nullptr, n, d_in, d1, d2, pack, scores, impl, stream);
+}
+
+extern "C" int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,
+                               const void *pack, float *scores, int impl, void *stream) {
+    return score_dispatch(true, x1, x2, nullptr, nullptr, 0, nullptr, n, d_in, d1, d1, pack, scores, impl, stream);
+}
+
+extern "C" int nplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *idx1,
+                                       const int64_t *idx2, int64_t n, int d_in, int d1, int d2,
+                                       const void *pack, float *scores, int32_t *bad_index_flag,
+                                       int impl, void *stream) {
+    if (!idx1 || !idx2) return n == 0 ? NPLDA_OK : NPLDA_ERR_BAD_ARG;
+    return score_dispatch(false, table, table, idx1, idx2, n_rows, bad_index_flag, n, d_in, d1, d2, pack, scores, impl, stream);
+}
+
+extern "C" int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *idx1,
+                                       const int64_t *idx2, int64_t n, int d_in, int d1,
+                                       const void *pack, float *scores, int32_t *bad_index_flag,
+                                       int impl, void *stream) {
+    if (!idx1 || !idx2) return n == 0 ? NPLDA_OK : NPLDA_ERR_BAD_ARG;
+    return score_dispatch(true, table, table, idx1, idx2, n_rows, bad_index_flag, n, d_in, d1, d1, pack, scores, impl, stream);
+}
+
+// ---- host-buffer entry -----------------------------------------------------------
+// Two-deep pipeline: while chunk c is scored on stream `comp`, chunk c+1 is in
+// flight host->device on stream `copy`.  Device scratch holds two chunks of
+// both sides plus two score buffers.
+extern "C" int64_t nplda_host_scratch_bytes(int64_t chunk_pairs, int d_in) {
+    if (chunk_pairs <= 0 || d_in <= 0) return NPLDA_ERR_BAD_ARG;
+    int64_t side = (chunk_pairs * d_in * 4 + 255) / 256 * 256;
+    int64_t sc = (chunk_pairs * 4 + 255) / 256 * 256;
+    return 2 * (2 * side + sc);
+}
+
+extern "C" int nplda_score_fwd_host(const float *x1_host, const float *x2_host, int64_t n, int d_in,
+                                    int d1, int d2, const void *pack, float *scores_host,
+                                    int64_t chunk_pairs, void *dev_scratch, int64_t dev_scratch_bytes,
+                                    int is_dplda, int impl) {
+    if (n < 0 || chunk_pairs <= 0 || !pack || !dev_scratch) return NPLDA_ERR_BAD_ARG;
+    if (n > 0 && (!x1_host || !x2_host || !scores_host)) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (dev_scratch_bytes < nplda_host_scratch_bytes(chunk_pairs, d_in)) return NPLDA_ERR_WORKSPACE;
+    if (n == 0) return NPLDA_OK;
+    const int64_t side = (chunk_pairs * d_in * 4 + 255) / 256 * 256;
+    const int64_t sc = (chunk_pairs * 4 + 255) / 256 * 256;
+    char *base = (char *)dev_scratch;
+    float *dx1[2], *dx2[2], *ds[2];
+    for (int b = 0; b < 2; ++b) {
+        char *p = base + b * (2 * side + sc);
+        dx1[b] = (float *)p; dx2[b] = (float *)(p + side); ds[b] = (float *)(p + 2 * side);
+    }
+    cudaStream_t copy = nullptr, comp = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    int rc = NPLDA_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == NPLDA_OK) rc = (int)e; return e != cudaSuccess; };
+    if (fail(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking)) ||
+        fail(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking))) goto done;
+    for (int b = 0; b < 2; ++b)
+        if (fail(cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming)) ||
+            fail(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming))) goto done;
+    {
+        const int64_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;
+        for (int64_t c = 0; c < nchunks && rc == NPLDA_OK; ++c) {
+            const int b = (int)(c & 1);
+            const int64_t p0 = c * chunk_pairs, m = std::min(chunk_pairs, n - p0);
+            if (c >= 2 && fail(cudaStreamWaitEvent(copy, freed[b], 0))) break;   // buffer b drained
+            if (fail(cudaMemcpyAsync(dx1[b], x1_host + p0 * d_in, (size_t)m * d_in * 4, cudaMemcpyHostToDevice, copy)) ||
+                fail(cudaMemcpyAsync(dx2[b], x2_host + p0 * d_in, (size_t)m * d_in * 4, cudaMemcpyHostToDevice, copy)) ||
+                fail(cudaEventRecord(ready[b], copy)) || fail(cudaStreamWaitEvent(comp, ready[b], 0)))
+                break;
+            int r = score_dispatch(is_dplda != 0, dx1[b], dx2[b], nullptr, nullptr, 0, nullptr, m, d_in, d1,
+                                   d2, pack, ds[b], impl, comp);
+            if (r != NPLDA_OK) { rc = r; break; }
+            if (fail(cudaMemcpyAsync(scores_host + p0, ds[b], (size_t)m * 4, cudaMemcpyDeviceToHost, comp)) ||
+                fail(cudaEventRecord(freed[b], comp)))
+                break;
+        }
+        fail(cudaStreamSynchronize(copy));
+        fail(cudaStreamSynchronize(comp));
+    }
+done:
+    for (int b = 0; b < 2; ++b) {
+        if (ready[b]) cudaEventDestroy(ready[b]);
+        if (freed[b]) cudaEventDestroy(freed[b]);
+    }
+    if (copy) cudaStreamDestroy(copy);
+    if (comp) cudaStreamDestroy(comp);
+    return rc;
+}

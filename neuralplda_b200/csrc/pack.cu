@@ -1,0 +1,102 @@
+// Weight packing: transposed (k-major), zero-padded fp32 images for the SIMT
+// kernels, plus the bf16 hi/lo tcgen05 images (score_tc.cu) in the same buffer.
+#include "common.cuh"
+
+namespace nplda {
+
+int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float *b2,
+                  const float *p_sqrt, const float *q, const PackLayout &L, char *pack,
+                  cudaStream_t st);   // score_tc.cu
+int tc_pack_dplda(const float *W1, const float *b1, const float *w_lr, const float *c_lr,
+                  const PackLayout &L, char *pack, cudaStream_t st);   // score_tc.cu
+
+// out[k][n] = W[n][k] for n < N, k < K, else 0.   out is [Kp][NP].
+__device__ __forceinline__ void put_wt(float *out, const float *W, int N, int K, int ldw, int64_t e) {
+    int k = (int)(e / NP), n = (int)(e % NP);
+    out[e] = (n < N && k < K) ? W[(int64_t)n * ldw + k] : 0.f;
+}
+__device__ __forceinline__ void put_vec(float *out, const float *v, int N, int n, bool square) {
+    float x = (v != nullptr && n < N) ? v[n] : 0.f;
+    out[n] = square ? x * x : x;
+}
+
+__global__ void pack_nplda_kernel(const float *__restrict__ W1, const float *__restrict__ b1,
+                                  const float *__restrict__ W2, const float *__restrict__ b2,
+                                  const float *__restrict__ p_sqrt, const float *__restrict__ q,
+                                  PackLayout L, char *pack) {
+    const int64_t n1 = (int64_t)L.k1p * NP, n2 = (int64_t)L.k2p * NP;
+    const int64_t total = n1 + n2 + 4 * NP;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        if (e < n1) {
+            put_wt((float *)(pack + L.w1t), W1, L.d1, L.d_in, L.d_in, e);
+        } else if (e < n1 + n2) {
+            put_wt((float *)(pack + L.w2t), W2, L.d2, L.d1, L.d1, e - n1);
+        } else {
+            int r = (int)(e - n1 - n2), which = r / NP, n = r % NP;
+            if (which == 0) put_vec((float *)(pack + L.b1), b1, L.d1, n, false);
+            if (which == 1) put_vec((float *)(pack + L.b2), b2, L.d2, n, false);
+            if (which == 2) put_vec((float *)(pack + L.p), p_sqrt, L.d2, n, true);   // P = P_sqrt^2 (models.py:373)
+            if (which == 3) put_vec((float *)(pack + L.q), q, L.d2, n, false);
+        }
+    }
+}
+
+// logistic_regres.weight = [ vec(Wb) | vec(Ww) | ws ]  (cat order of models.py:487)
+__global__ void pack_dplda_kernel(const float *__restrict__ W1, const float *__restrict__ b1,
+                                  const float *__restrict__ w_lr, const float *__restrict__ c_lr,
+                                  PackLayout L, char *pack) {
+    const int Ld = L.d1;
+    const int64_t n1 = (int64_t)L.k1p * NP, n2 = (int64_t)L.k2p * NP;
+    const int64_t total = n1 + 2 * n2 + 2 * NP + 1;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        if (e < n1) {
+            put_wt((float *)(pack + L.w1t), W1, L.d1, L.d_in, L.d_in, e);
+        } else if (e < n1 + n2) {
+            put_wt((float *)(pack + L.w2t), w_lr + (int64_t)Ld * Ld, Ld, Ld, Ld, e - n1);        // Ww
+        } else if (e < n1 + 2 * n2) {
+            put_wt((float *)(pack + L.w3t), w_lr, Ld, Ld, Ld, e - n1 - n2);                      // Wb
+        } else {
+            int r = (int)(e - n1 - 2 * n2);
+            if (r < NP) put_vec((float *)(pack + L.b1), b1, L.d1, r, false);
+            else if (r < 2 * NP) put_vec((float *)(pack + L.b2), w_lr + 2 * (int64_t)Ld * Ld, Ld, r - NP, false);
+            else ((float *)(pack + L.c))[0] = c_lr ? c_lr[0] : 0.f;
+        }
+    }
+}
+
+}  // namespace nplda
+
+using namespace nplda;
+
+extern "C" int64_t nplda_pack_bytes(int d_in, int d1, int d2) {
+    if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    return make_pack_layout(d_in, d1, d2).total;
+}
+
+extern "C" int nplda_pack_weights(const float *W1, const float *b1, const float *W2, const float *b2,
+                                  const float *p_sqrt, const float *q, int d_in, int d1, int d2,
+                                  void *pack, int64_t pack_bytes, void *stream) {
+    if (!W1 || !b1 || !W2 || !b2 || !p_sqrt || !q || !pack) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    PackLayout L = make_pack_layout(d_in, d1, d2);
+    if (pack_bytes < L.total) return NPLDA_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    pack_nplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack);
+    NPLDA_LAUNCH_CHECK();
+    return tc_pack_nplda(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack, st);
+}
+
+extern "C" int dplda_pack_weights(const float *W1, const float *b1, const float *w_lr,
+                                  const float *c_lr, int d_in, int d1, void *pack,
+                                  int64_t pack_bytes, void *stream) {
+    if (!W1 || !b1 || !w_lr || !pack) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    PackLayout L = make_pack_layout(d_in, d1, d1);
+    if (pack_bytes < L.total) return NPLDA_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    pack_dplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, w_lr, c_lr, L, (char *)pack);
+    NPLDA_LAUNCH_CHECK();
+    return tc_pack_dplda(W1, b1, w_lr, c_lr, L, (char *)pack, st);
+}

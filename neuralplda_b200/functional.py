@@ -1,0 +1,264 @@
+"""Autograd bindings of the C-ABI kernels (include/nplda.h).
+
+PyTorch is plumbing here: it owns the device buffers and the autograd tape;
+every arithmetic step of the hot path runs in libnplda.so.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+
+
+def _f32c(t):
+    """fp32 contiguous view/copy on the same device (the reference casts with .float())."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class PackedWeights:
+    """Device workspace holding the packed weights of one module, re-packed only
+    when a parameter changed (tracked through tensor._version / data_ptr)."""
+
+    def __init__(self):
+        self.buf = None
+        self.key = None
+
+    def get(self, kind, params, d_in, d1, d2):
+        key = (kind, d_in, d1, d2) + tuple((p.data_ptr(), p._version, p.device) for p in params)
+        if key != self.key:
+            dev = params[0].device
+            nbytes = lib().nplda_pack_bytes(d_in, d1, d2)
+            if nbytes < 0:
+                check(nbytes, "nplda_pack_bytes")
+            if self.buf is None or self.buf.numel() < nbytes or self.buf.device != dev:
+                self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ps = [_f32c(p.detach()) for p in params]
+            with torch.cuda.device(dev):
+                if kind == "nplda":
+                    rc = lib().nplda_pack_weights(*[ptr(p) for p in ps], d_in, d1, d2, ptr(self.buf),
+                                                  self.buf.numel(), stream_ptr())
+                else:
+                    rc = lib().dplda_pack_weights(*[ptr(p) for p in ps], d_in, d1, ptr(self.buf),
+                                                  self.buf.numel(), stream_ptr())
+            check(rc, "pack_weights")
+            self.key = key
+        return self.buf
+
+
+def _check_pair_inputs(x1, x2, d_in):
+    require_cuda(x1, x2)
+    if x1.dim() != 2 or x2.dim() != 2 or x1.shape != x2.shape:
+        raise RuntimeError(f"expected two [N, {d_in}] tensors, got {tuple(x1.shape)} and {tuple(x2.shape)}")
+    if x1.shape[1] != d_in:
+        # same failure class as the reference's addmm shape error
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x1.shape[0]}x{x1.shape[1]} and "
+                           f"{d_in}x...)")
+
+
+class NpldaScoreFn(torch.autograd.Function):
+    """S = NeuralPlda.forward(x1, x2)  (reference utils/models.py:378-382)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, W1, b1, W2, b2, P_sqrt, Q, packed, impl):
+        d1, d_in = W1.shape
+        d2 = W2.shape[0]
+        _check_pair_inputs(x1, x2, d_in)
+        x1c, x2c = _f32c(x1), _f32c(x2)
+        n = x1c.shape[0]
+        pack = packed.get("nplda", (W1, b1, W2, b2, P_sqrt, Q), d_in, d1, d2)
+        scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
+        with torch.cuda.device(x1c.device):
+            check(lib().nplda_score_fwd(ptr(x1c), ptr(x2c), n, d_in, d1, d2, ptr(pack), ptr(scores), impl,
+                                        stream_ptr()), "nplda_score_fwd")
+        ctx.save_for_backward(x1c, x2c, W1, b1, W2, b2, P_sqrt, Q)
+        return scores
+
+    @staticmethod
+    def backward(ctx, ds):
+        x1, x2, W1, b1, W2, b2, P_sqrt, Q = ctx.saved_tensors
+        d1, d_in = W1.shape
+        d2 = W2.shape[0]
+        n = x1.shape[0]
+        dev = x1.device
+        ds = _f32c(ds)
+        need = ctx.needs_input_grad
+        params = [_f32c(p.detach()) for p in (W1, b1, W2, b2, P_sqrt, Q)]
+        grads = [torch.zeros_like(p) if need[2 + i] else None for i, p in enumerate(params)]
+        dx1 = torch.zeros_like(x1) if need[0] else None
+        dx2 = torch.zeros_like(x2) if need[1] else None
+        if n > 0:
+            with torch.cuda.device(dev):
+                wsb = lib().nplda_bwd_workspace_bytes(n, d_in, d1, d2)
+                if wsb < 0:
+                    check(wsb, "nplda_bwd_workspace_bytes")
+                ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=dev)
+                check(lib().nplda_score_bwd(ptr(x1), ptr(x2), n, d_in, d1, d2, *[ptr(p) for p in params],
+                                            ptr(ds), *[ptr(g) for g in grads], ptr(dx1), ptr(dx2), ptr(ws),
+                                            ws.numel(), stream_ptr()), "nplda_score_bwd")
+        return (dx1, dx2, *grads, None, None)
+
+
+class DpldaScoreFn(torch.autograd.Function):
+    """S = DPlda.forward(x1, x2)  (reference utils/models.py:491-495)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, W1, b1, w_lr, c_lr, packed, impl):
+        d1, d_in = W1.shape
+        _check_pair_inputs(x1, x2, d_in)
+        if w_lr.numel() != 2 * d1 * d1 + d1:
+            raise RuntimeError("logistic_regres.weight has the wrong size for layer1_LDA_dim")
+        x1c, x2c = _f32c(x1), _f32c(x2)
+        n = x1c.shape[0]
+        pack = packed.get("dplda", (W1, b1, w_lr, c_lr), d_in, d1, d1)
+        scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
+        with torch.cuda.device(x1c.device):
+            check(lib().dplda_score_fwd(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), impl,
+                                        stream_ptr()), "dplda_score_fwd")
+        ctx.save_for_backward(x1c, x2c, W1, b1, w_lr)
+        return scores
+
+    @staticmethod
+    def backward(ctx, ds):
+        x1, x2, W1, b1, w_lr = ctx.saved_tensors
+        d1, d_in = W1.shape
+        n = x1.shape[0]
+        dev = x1.device
+        ds = _f32c(ds)
+        need = ctx.needs_input_grad
+        W1c, b1c, wc = _f32c(W1.detach()), _f32c(b1.detach()), _f32c(w_lr.detach())
+        dW1 = torch.zeros_like(W1c) if need[2] else None
+        db1 = torch.zeros_like(b1c) if need[3] else None
+        dw = torch.zeros_like(wc) if need[4] else None
+        dc = torch.zeros(1, dtype=torch.float32, device=dev) if need[5] else None
+        dx1 = torch.zeros_like(x1) if need[0] else None
+        dx2 = torch.zeros_like(x2) if need[1] else None
+        if n > 0:
+            with torch.cuda.device(dev):
+                wsb = lib().nplda_bwd_workspace_bytes(n, d_in, d1, d1)
+                if wsb < 0:
+                    check(wsb, "nplda_bwd_workspace_bytes")
+                ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=dev)
+                check(lib().dplda_score_bwd(ptr(x1), ptr(x2), n, d_in, d1, ptr(W1c), ptr(b1c), ptr(wc), ptr(ds),
+                                            ptr(dW1), ptr(db1), ptr(dw), ptr(dc), ptr(dx1), ptr(dx2), ptr(ws),
+                                            ws.numel(), stream_ptr()), "dplda_score_bwd")
+        return (dx1, dx2, dW1, db1, dw, dc, None, None)
+
+
+def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO):
+    """Scores of trials (table[i1[k]], table[i2[k]]) with the gather fused into the
+    kernel (replaces sv_trials_loaders.load_xvec_trials_from_numbatch + forward)."""
+    require_cuda(table, i1, i2)
+    d_in, d1, d2 = dims
+    if table.dim() != 2 or table.shape[1] != d_in:
+        raise RuntimeError(f"table must be [rows, {d_in}]")
+    table = _f32c(table)
+    i1 = i1.to(torch.int64).contiguous()
+    i2 = i2.to(torch.int64).contiguous()
+    if i1.shape != i2.shape or i1.dim() != 1:
+        raise RuntimeError("index tensors must be 1-D and the same length")
+    n = i1.numel()
+    dev = table.device
+    pack = packed.get(kind, params, d_in, d1, d2)
+    scores = torch.empty(n, dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        if kind == "nplda":
+            rc = lib().nplda_score_fwd_indexed(ptr(table), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1, d2,
+                                               ptr(pack), ptr(scores), ptr(flag), impl, stream_ptr())
+        else:
+            rc = lib().dplda_score_fwd_indexed(ptr(table), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1,
+                                               ptr(pack), ptr(scores), ptr(flag), impl, stream_ptr())
+    check(rc, "score_fwd_indexed")
+    return scores, flag
+
+
+# ------------------------------------------------------------------------------
+# Losses
+# ------------------------------------------------------------------------------
+
+
+def loss_accumulators(scores, target, thresholds, alpha, th_xent, group=None):
+    """Raw fp64 sums (layout in include/nplda.h), all-reduced over `group` if given.
+
+    The per-GPU shards of a trial list must be combined as RAW SUMS before any
+    division: per-rank label counts differ.
+    """
+    require_cuda(scores, target)
+    s, t = _f32c(scores), _f32c(target)
+    if s.shape != t.shape:
+        raise RuntimeError("scores and targets must have the same shape")
+    K = 0 if thresholds is None else thresholds.numel()
+    acc = torch.zeros(4 * K + 4, dtype=torch.float64, device=s.device)
+    th = None if K == 0 else _f32c(thresholds.detach())
+    thx = None if th_xent is None else _f32c(th_xent.detach())
+    with torch.cuda.device(s.device):
+        check(lib().nplda_loss_accum(ptr(s), ptr(t), s.numel(), ptr(th), K, float(alpha), ptr(thx), ptr(acc),
+                                     stream_ptr()), "nplda_loss_accum")
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=None if group is True else group)
+    return acc
+
+
+def finalize(acc, betas):
+    out = torch.empty(4, dtype=torch.float32, device=acc.device)
+    K = len(betas)
+    with torch.cuda.device(acc.device):
+        check(lib().nplda_loss_finalize(ptr(acc), _lib.betas_array(betas), K, ptr(out), stream_ptr()),
+              "nplda_loss_finalize")
+    return out
+
+
+class LossFn(torch.autograd.Function):
+    """softcdet / crossentropy of the reference (models.py:384-393) on the GPU.
+
+    thresholds: [K] fp32 (the Th{beta} parameters concatenated), th_xent: [1] or None.
+    """
+
+    @staticmethod
+    def forward(ctx, scores, target, thresholds, th_xent, betas, alpha, loss_id, group):
+        acc = loss_accumulators(scores, target, thresholds, alpha, th_xent, group)
+        out = finalize(acc, betas)
+        ctx.save_for_backward(_f32c(scores), _f32c(target), thresholds, th_xent, acc)
+        ctx.betas, ctx.alpha, ctx.loss_id, ctx.group = list(betas), float(alpha), loss_id, group
+        return out[loss_id].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        s, t, thresholds, th_xent, acc = ctx.saved_tensors
+        K = len(ctx.betas)
+        dev = s.device
+        ds = torch.empty_like(s)
+        dth = torch.zeros(K + 1, dtype=torch.float64, device=dev)
+        g = _f32c(g).reshape(1)
+        th = None if thresholds is None else _f32c(thresholds.detach())
+        thx = None if th_xent is None else _f32c(th_xent.detach())
+        with torch.cuda.device(dev):
+            check(lib().nplda_loss_bwd(ptr(s), ptr(t), s.numel(), ptr(th), _lib.betas_array(ctx.betas), K,
+                                       ctx.alpha, ptr(thx), ptr(acc), ctx.loss_id, ptr(g), ptr(ds), ptr(dth),
+                                       stream_ptr()), "nplda_loss_bwd")
+        # Threshold gradients are sums over this rank's trials; under a process
+        # group the caller all-reduces parameter gradients (DDP-style), as for
+        # the other parameters.
+        dthr = dth[:K].float() if (thresholds is not None and ctx.needs_input_grad[2]) else None
+        dthx = dth[K:].float() if (th_xent is not None and ctx.needs_input_grad[3]) else None
+        return ds, None, dthr, dthx, None, None, None, None
+
+
+def minc_sweep(tgt_sorted, non_sorted, sum_t, sum_n, betas):
+    """(min cost [K] fp32, argmin index [K] int64 into tgt_sorted); models.py:406-421."""
+    require_cuda(tgt_sorted, non_sorted)
+    K = len(betas)
+    dev = tgt_sorted.device
+    out_min = torch.empty(K, dtype=torch.float32, device=dev)
+    out_arg = torch.empty(K, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().nplda_minc_sweep(ptr(tgt_sorted), tgt_sorted.numel(), ptr(non_sorted), non_sorted.numel(),
+                                     ctypes.c_float(sum_t), ctypes.c_float(sum_n), _lib.betas_array(betas), K,
+                                     ptr(out_min), ptr(out_arg), stream_ptr()), "nplda_minc_sweep")
+    return out_min, out_arg
