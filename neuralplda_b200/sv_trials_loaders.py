@@ -1,0 +1,149 @@
+"""Trial batching with a device-resident x-vector table.
+
+Same entry points, argument meaning and batch layout as the reference's
+utils/sv_trials_loaders.py:371-437: trial TSVs become DataLoaders of
+(int64 idx1[B], int64 idx2[B], float32 label[B]); per batch the two sides are
+returned as [B, D] fp32 tensors on `device`.  The reference does the gather
+with a Python loop over B dict lookups plus a host->device copy of 4 KB per
+trial every batch; here the whole x-vector dict is uploaded once and the gather
+is an index_select on the GPU (or is fused into the score kernel through
+NeuralPlda.forward_indexed).
+"""
+from __future__ import annotations
+
+import os
+import weakref
+
+import numpy as np
+import torch
+from torch.utils.data import TensorDataset, DataLoader, ConcatDataset, Subset
+
+
+class XvectorTable:
+    """utt_id -> row of a [n_utts, D] fp32 device tensor; rows follow list(mega_dict)
+    (the reference's num_to_id order, xvector_NeuralPlda_pytorch.py:118-119)."""
+
+    def __init__(self, mega_dict, device):
+        self.ids = list(mega_dict)
+        self.row_of = {u: i for i, u in enumerate(self.ids)}
+        host = torch.from_numpy(np.asarray([mega_dict[u] for u in self.ids])).float()
+        self.device = torch.device(device)
+        self.table = host.to(self.device)
+
+    def rows_for_ids(self, ids):
+        return torch.tensor([self.row_of[u] for u in ids], dtype=torch.int64)
+
+
+_tables = {}   # id(mega_dict) -> (weakref-ish guard, {device: XvectorTable})
+
+
+def get_table(mega_dict, device):
+    """One upload per (dict object, device); re-uploaded if the dict grew."""
+    device = torch.device(device)
+    key = id(mega_dict)
+    ent = _tables.get(key)
+    if ent is None or ent[0] != len(mega_dict):
+        ent = (len(mega_dict), {})
+        _tables[key] = ent
+    tab = ent[1].get(str(device))
+    if tab is None:
+        tab = XvectorTable(mega_dict, device)
+        ent[1][str(device)] = tab
+    return tab
+
+
+def _rows_from_nums(tab, num_to_id_dict, data):
+    nums = data.detach().to("cpu", torch.int64)
+    # fast path: num_to_id_dict enumerates list(mega_dict) as in the reference drivers
+    n = len(tab.ids)
+    ident = getattr(tab, "_ident", None)
+    if ident is None or ident[0] is not num_to_id_dict:
+        ok = len(num_to_id_dict) == n and all(num_to_id_dict.get(i) == u for i, u in enumerate(tab.ids))
+        remap = None if ok else {k: tab.row_of[v] for k, v in num_to_id_dict.items() if v in tab.row_of}
+        tab._ident = (num_to_id_dict, ok, remap)
+        ident = tab._ident
+    if ident[1]:
+        if nums.numel() and (int(nums.min()) < 0 or int(nums.max()) >= n):
+            raise KeyError(int(nums.max()))
+        return nums
+    return torch.tensor([ident[2][int(i)] for i in nums], dtype=torch.int64)
+
+
+def load_xvec_trials_from_numbatch(mega_dict, num_to_id_dict, data1, data2, device):
+    """sv_trials_loaders.py:418-426: (X1, X2) [B, D] fp32 on `device`."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("neuralplda_b200 keeps x-vectors on the GPU; got device '%s'" % device)
+    tab = get_table(mega_dict, device)
+    r1 = _rows_from_nums(tab, num_to_id_dict, data1).to(device, non_blocking=True)
+    r2 = _rows_from_nums(tab, num_to_id_dict, data2).to(device, non_blocking=True)
+    return tab.table.index_select(0, r1), tab.table.index_select(0, r2)
+
+
+def strip_id(s):
+    return os.path.splitext(os.path.basename(s))[0]
+
+
+def load_xvec_trials_from_idbatch(mega_dict, trials, device):
+    """sv_trials_loaders.py:429-437: ids are basename/splitext-stripped before lookup."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("neuralplda_b200 keeps x-vectors on the GPU; got device '%s'" % device)
+    tab = get_table(mega_dict, device)
+    trials = np.asarray(trials)
+    if trials.size == 0:
+        empty = tab.table.new_zeros((0, tab.table.shape[1]))
+        return empty, empty.clone()
+    r1 = tab.rows_for_ids([strip_id(d) for d in trials[:, 0]]).to(device, non_blocking=True)
+    r2 = tab.rows_for_ids([strip_id(d) for d in trials[:, 1]]).to(device, non_blocking=True)
+    return tab.table.index_select(0, r1), tab.table.index_select(0, r2)
+
+
+def _read_trials(f, id_to_num_dict, strip_ext_col2):
+    """Rows with unknown ids or unparsable labels are silently dropped, as the
+    reference's try/except does (sv_trials_loaders.py:379-383, 402-406)."""
+    t = np.genfromtxt(f, dtype='str')
+    if t.ndim == 1:
+        t = t.reshape(1, -1)
+    x1, x2, l = [], [], []
+    for tr in t:
+        try:
+            b_id = os.path.splitext(tr[1])[0] if strip_ext_col2 else tr[1]
+            a, b, c = id_to_num_dict[tr[0]], id_to_num_dict[b_id], float(tr[2])
+            x1.append(a); x2.append(b); l.append(c)
+        except Exception:
+            pass
+    return TensorDataset(torch.tensor(x1, dtype=torch.int64), torch.tensor(x2, dtype=torch.int64),
+                         torch.tensor(l, dtype=torch.float32))
+
+
+def combine_trials_and_get_loader(trials_key_files_list, id_to_num_dict, subsample_factors=None, batch_size=2048, subset=0):
+    """sv_trials_loaders.py:371-392."""
+    if subsample_factors is None:
+        subsample_factors = [1 for w in trials_key_files_list]
+    datasets = []
+    for f, sf in zip(trials_key_files_list, subsample_factors):
+        tdset = _read_trials(f, id_to_num_dict, strip_ext_col2=False)
+        inds = np.arange(len(tdset))[np.random.rand(len(tdset)) < sf]
+        datasets.append(Subset(tdset, inds))
+    combined_dataset = ConcatDataset(datasets)
+    if subset > 0:
+        inds = np.arange(len(combined_dataset))[np.random.rand(len(combined_dataset)) < subset]
+        combined_dataset = Subset(combined_dataset, inds)
+    return DataLoader(combined_dataset, batch_size=batch_size, shuffle=True)
+
+
+def get_trials_loaders_dict(trials_key_files_list, id_to_num_dict, subsample_factors=None, batch_size=2048, subset=0):
+    """sv_trials_loaders.py:394-415 (column 2 loses its extension; keyed by file basename)."""
+    trials_loaders_dict = {}
+    if subsample_factors is None:
+        subsample_factors = [1 for w in trials_key_files_list]
+    for f, sf in zip(trials_key_files_list, subsample_factors):
+        tdset = _read_trials(f, id_to_num_dict, strip_ext_col2=True)
+        inds = np.arange(len(tdset))[np.random.rand(len(tdset)) < sf]
+        dataset = Subset(tdset, inds)
+        if subset > 0:
+            inds = np.arange(len(dataset))[np.random.rand(len(dataset)) < subset]
+            dataset = Subset(dataset, inds)
+        trials_loaders_dict[os.path.splitext(os.path.basename(f))[0]] = DataLoader(dataset, batch_size=batch_size, shuffle=True)
+    return trials_loaders_dict

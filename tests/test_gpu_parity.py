@@ -1,0 +1,372 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the
+reference's golden outputs.  Run on the B200 box: pytest -m gpu."""
+import ctypes
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import neuralplda_b200 as npl
+from neuralplda_b200 import _lib, functional as F_
+from oracle import nplda_oracle as O
+from conftest import GOLDEN, NC, NCD, parity_ok
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_nplda(kp, impl=None, loss="SoftCdet"):
+    class C(NC):
+        pass
+    C.loss = loss
+    m = npl.NeuralPlda(C).to(DEV)
+    sd = m.state_dict()
+    sd["centering_and_LDA.weight"].copy_(kp["W1"]); sd["centering_and_LDA.bias"].copy_(kp["b1"])
+    sd["centering_and_wccn_plda.weight"].copy_(kp["W2"]); sd["centering_and_wccn_plda.bias"].copy_(kp["b2"])
+    sd["P_sqrt"].copy_(kp["P_sqrt"]); sd["Q"].copy_(kp["Q"])
+    if impl is not None:
+        m.impl = impl
+    return m
+
+
+def dplda_weights(ref_out):
+    g = torch.Generator().manual_seed(int(ref_out["c4_seed_w"]))
+    return (torch.rand(1, 57970, generator=g) - 0.5) * 0.2, torch.tensor([0.3])
+
+
+def make_dplda(kp, ref_out, impl=None):
+    m = npl.DPlda(NCD).to(DEV)
+    w, c = dplda_weights(ref_out)
+    sd = m.state_dict()
+    sd["centering_and_LDA.weight"].copy_(kp["W1"]); sd["centering_and_LDA.bias"].copy_(kp["b1"])
+    sd["logistic_regres.weight"].copy_(w); sd["logistic_regres.bias"].copy_(c)
+    if impl is not None:
+        m.impl = impl
+    return m
+
+
+IMPLS = [npl.IMPL_SIMT, npl.IMPL_AUTO]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_nplda_forward_golden_10k(ref_out, kaldi_params, cfg1, impl):
+    """BASELINE.json configs[0]: 10k pairs vs the reference's CPU forward, 1e-4 relative."""
+    x1, x2, _ = cfg1
+    m = make_nplda(kaldi_params, impl)
+    with torch.no_grad():
+        s = m(x1.to(DEV), x2.to(DEV))
+    ok, worst = parity_ok(s, torch.from_numpy(ref_out["c1_scores"]), rel=1e-4)
+    assert ok, f"worst normalised error {worst} (bound 1.0)"
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 127, 129, 1000, 4097])
+def test_nplda_forward_ragged_sizes(kaldi_params, cfg1, impl, n):
+    x1, x2, _ = cfg1
+    m = make_nplda(kaldi_params, impl)
+    kp = kaldi_params
+    ref = O.nplda_score(x1[:n], x2[:n], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    with torch.no_grad():
+        s = m(x1[:n].to(DEV), x2[:n].to(DEV))
+    assert s.shape == (n,)
+    ok, worst = parity_ok(s, ref, rel=1e-4)
+    assert ok or n < 8, worst          # rms of a handful of scores is not a meaningful scale
+    np.testing.assert_allclose(s.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-4)
+
+
+def test_empty_input(kaldi_params):
+    m = make_nplda(kaldi_params)
+    with torch.no_grad():
+        s = m(torch.zeros(0, 512, device=DEV), torch.zeros(0, 512, device=DEV))
+    assert s.shape == (0,)
+
+
+def test_cpu_tensors_raise(kaldi_params):
+    m = make_nplda(kaldi_params)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(4, 512), torch.zeros(4, 512))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(4, 100, device=DEV), torch.zeros(4, 100, device=DEV))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_default_init_and_random_params(ref_out, impl):
+    z = np.load(os.path.join(GOLDEN, "default_init_params.npz"))
+    m = npl.NeuralPlda(NC).to(DEV)
+    m.impl = impl
+    m.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files})
+    g0 = torch.Generator().manual_seed(0)
+    z1, z2 = torch.randn(256, 512, generator=g0), torch.randn(256, 512, generator=g0)
+    with torch.no_grad():
+        s = m(z1.to(DEV), z2.to(DEV))
+    ok, worst = parity_ok(s, torch.from_numpy(ref_out["c3_scores"]), rel=1e-4)
+    assert ok, worst
+
+
+@pytest.mark.parametrize("dims", [(512, 170, 170), (96, 40, 24), (257, 192, 192), (30, 7, 5), (64, 64, 100)])
+def test_other_dims_simt(dims):
+    d_in, d1, d2 = dims
+    class C(NC):
+        xvector_dim, layer1_LDA_dim, layer2_PLDA_spkfactor_dim = d_in, d1, d2
+    torch.manual_seed(3)
+    m = npl.NeuralPlda(C)
+    g = torch.Generator().manual_seed(9)
+    x1, x2 = torch.randn(300, d_in, generator=g), torch.randn(300, d_in, generator=g)
+    p = m.state_dict()
+    ref = O.nplda_score(x1, x2, p["centering_and_LDA.weight"], p["centering_and_LDA.bias"],
+                        p["centering_and_wccn_plda.weight"], p["centering_and_wccn_plda.bias"], p["P_sqrt"], p["Q"])
+    m = m.to(DEV)
+    with torch.no_grad():
+        s = m(x1.to(DEV), x2.to(DEV))
+    ok, worst = parity_ok(s, ref, rel=1e-4)
+    assert ok, worst
+
+
+def test_unsupported_dims_error():
+    class C(NC):
+        layer1_LDA_dim = 300
+    m = npl.NeuralPlda(C).to(DEV)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(4, 512, device=DEV), torch.zeros(4, 512, device=DEV))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_dplda_forward_golden(ref_out, kaldi_params, cfg1, impl):
+    x1, x2, _ = cfg1
+    m = make_dplda(kaldi_params, ref_out, impl)
+    ref = torch.from_numpy(ref_out["c4_scores"])
+    n = ref.numel()
+    with torch.no_grad():
+        s = m(x1[:n].to(DEV), x2[:n].to(DEV))
+    ok, worst = parity_ok(s, ref, rel=1e-4)
+    assert ok, worst
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_indexed_matches_materialised(kaldi_params, impl):
+    table, i1, i2, _ = O.synth_grid(37, 53, 11, seed=1003, mean=kaldi_params["mean"])
+    m = make_nplda(kaldi_params, impl)
+    t = table.to(DEV)
+    with torch.no_grad():
+        s_idx, flag = m.forward_indexed(t, i1.to(DEV), i2.to(DEV))
+        s_mat = m(t[i1.to(DEV)], t[i2.to(DEV)])
+    assert int(flag.item()) == 0
+    np.testing.assert_array_equal(s_idx.cpu().numpy(), s_mat.cpu().numpy())
+    bad = i1.clone(); bad[5] = 10 ** 6
+    with torch.no_grad():
+        _, flag = m.forward_indexed(t, bad.to(DEV), i2.to(DEV))
+    assert int(flag.item()) != 0
+
+
+def test_losses_match_reference(ref_out, kaldi_params, cfg1):
+    _, _, t = cfg1
+    s = torch.from_numpy(ref_out["c1_scores"]).to(DEV)
+    t = t.to(DEV)
+    m = make_nplda(kaldi_params)
+    assert m.softcdet(s, t).item() == pytest.approx(float(ref_out["c1_softcdet_th0"]), rel=1e-4)
+    assert m.cdet(s, t).item() == pytest.approx(float(ref_out["c1_cdet_th0"]), rel=1e-6)
+    assert m.crossentropy(s, t).item() == pytest.approx(float(ref_out["c1_bce_th0"]), rel=1e-4)
+    mc, th = m.minc(s[:2000], t[:2000], update_thresholds=True)
+    assert float(mc) == pytest.approx(float(ref_out["c1_minc2k"]), rel=1e-6)
+    np.testing.assert_array_equal(np.float32([float(th[b]) for b in NC.beta]), ref_out["c1_minc2k_th"].astype(np.float32))
+    np.testing.assert_array_equal(np.float32([m.Th99.item(), m.Th199.item()]), ref_out["c1_th_state"].astype(np.float32))
+    assert m.softcdet(s, t).item() == pytest.approx(float(ref_out["c1_softcdet_thminc"]), rel=1e-4)
+    assert m.cdet(s, t).item() == pytest.approx(float(ref_out["c1_cdet_thminc"]), rel=1e-6)
+    m.lossfn = "softCdet"          # the shipped voices_config.cfg spelling: loss() returns None (models.py:395-399)
+    assert m.loss(s, t) is None
+
+
+def test_accumulators_bitwise_layout(ref_out, cfg1):
+    _, _, t = cfg1
+    s = torch.from_numpy(ref_out["c1_scores"])
+    th = torch.tensor([0.1, -0.3])
+    acc = F_.loss_accumulators(s.to(DEV), t.to(DEV), th.to(DEV), 15.0, torch.tensor([0.25], device=DEV)).cpu()
+    ref = O.loss_accumulators(s, t, th.tolist(), NC.beta, 15.0, 0.25)
+    np.testing.assert_allclose(acc.numpy(), ref.numpy(), rtol=2e-6)
+    assert acc[4 * 2 + 0].item() == t.sum().item() and acc[4 * 2 + 3].item() == 10000.0
+    assert acc[2].item() == ((s < 0.1).float() * t).sum().item()          # hard counts are exact
+
+
+def test_minc_quirks_gpu(ref_out, kaldi_params):
+    m = make_nplda(kaldi_params)
+    toy_s = torch.tensor([.1, .5, .9, -.2, .3, .7, -1.], device=DEV)
+    toy_t = torch.tensor([1., 1., 1., 0., 0., 0., 0.], device=DEV)
+    mc, th = m.minc(toy_s, toy_t)
+    assert float(mc) == pytest.approx(float(ref_out["c5_minc"]), rel=1e-6)
+    assert [float(th[b]) for b in NC.beta] == pytest.approx(list(ref_out["c5_th"]))
+    g = torch.Generator().manual_seed(5)
+    qs = torch.round(torch.randn(400, generator=g) * 4) / 4
+    qt = (torch.rand(400, generator=g) < 0.3).float()
+    mc, th = m.minc(qs.to(DEV), qt.to(DEV))
+    assert float(mc) == pytest.approx(float(ref_out["c5b_minc"]), rel=1e-6)
+    assert [float(th[b]) for b in NC.beta] == pytest.approx(list(ref_out["c5b_th"]))
+    # large sweep against the O(N log N) oracle, exact
+    g = torch.Generator().manual_seed(11)
+    s = torch.randn(200000, generator=g)
+    t = (torch.rand(200000, generator=g) < 0.05).float()
+    s = s + 2.0 * t
+    mc, th = m.minc(s.to(DEV), t.to(DEV))
+    omc, oth = O.minc(s, t, NC.beta)
+    assert float(mc) == pytest.approx(float(omc), rel=1e-6)
+    assert [float(th[b]) for b in NC.beta] == [float(oth[b]) for b in NC.beta]
+
+
+def _check_grads(model, ref_out, prefix, names, rtol=2e-3):
+    got = dict(model.named_parameters())
+    for n in names:
+        sample = ref_out[f"{prefix}_grad_{n}_sample"]
+        p = got[n]
+        if sample.size == 0:
+            assert p.grad is None or float(p.grad.abs().sum()) == 0.0, n
+            continue
+        assert p.grad is not None, n
+        g = p.grad.reshape(-1).cpu()
+        norm = float(ref_out[f"{prefix}_grad_{n}_norm"])
+        assert float(g.double().norm()) == pytest.approx(norm, rel=rtol), n
+        scale = norm / np.sqrt(g.numel()) + 1e-30
+        np.testing.assert_allclose(g[::7].numpy(), sample, rtol=rtol, atol=rtol * scale, err_msg=n)
+
+
+@pytest.mark.parametrize("lossname", ["SoftCdet", "crossentropy"])
+def test_nplda_training_step_gradients(ref_out, kaldi_params, cfg1, lossname):
+    """forward + loss + backward at the voices batch size against the reference's autograd."""
+    x1, x2, t = cfg1
+    m = make_nplda(kaldi_params, loss=lossname)
+    with torch.no_grad():
+        m.Th99.fill_(float(ref_out["c1_th_state"][0])); m.Th199.fill_(float(ref_out["c1_th_state"][1]))
+        m.threshold_Xent.fill_(0.25)
+    out = m(x1[:2048].to(DEV), x2[:2048].to(DEV))
+    loss = m.loss(out, t[:2048].to(DEV))
+    assert loss.item() == pytest.approx(float(ref_out[f"c2_{lossname}_loss"]), rel=1e-4)
+    loss.backward()
+    _check_grads(m, ref_out, f"c2_{lossname}", [str(n) for n in ref_out["param_names"]])
+
+
+def test_dplda_training_step_gradients(ref_out, kaldi_params, cfg1):
+    x1, x2, t = cfg1
+    m = make_dplda(kaldi_params, ref_out)
+    out = m(x1[:256].to(DEV), x2[:256].to(DEV))
+    loss = m.loss(out, t[:256].to(DEV))
+    assert loss.item() == pytest.approx(float(ref_out["c4_train_loss"]), rel=1e-4)
+    loss.backward()
+    _check_grads(m, ref_out, "c4", [str(n) for n in ref_out["c4_param_names"]])
+
+
+def test_backward_linearity_large(kaldi_params, cfg1):
+    """Size-independent property at a multi-chunk size: grads are linear in dS."""
+    x1, x2, _ = cfg1
+    reps = 14                                  # 140k pairs > one backward chunk (131072)
+    X1 = x1.repeat(reps, 1).to(DEV); X2 = x2.repeat(reps, 1).to(DEV)
+    m = make_nplda(kaldi_params)
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(10000, generator=g).to(DEV)
+    m(X1, X2).mul(w.repeat(reps)).sum().backward()
+    big = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    m(X1[:10000], X2[:10000]).mul(w).sum().backward()
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        scale = float(p.grad.abs().max()) * reps + 1e-30
+        assert float((big[n] - reps * p.grad).abs().max()) <= 2e-3 * scale, n
+
+
+def test_optimizer_step_repacks_weights(kaldi_params, cfg1):
+    x1, x2, t = cfg1
+    m = make_nplda(kaldi_params, loss="crossentropy")
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)
+    a, b, tt = x1[:512].to(DEV), x2[:512].to(DEV), t[:512].to(DEV)
+    s0 = m(a, b).detach().clone()
+    loss = m.loss(m(a, b), tt); loss.backward(); opt.step()
+    s1 = m(a, b).detach()
+    assert float((s1 - s0).abs().max()) > 0
+    p = m.state_dict()
+    ref = O.nplda_score(a.cpu(), b.cpu(), *(p[k].cpu() for k in (
+        "centering_and_LDA.weight", "centering_and_LDA.bias", "centering_and_wccn_plda.weight",
+        "centering_and_wccn_plda.bias", "P_sqrt", "Q")))
+    ok, worst = parity_ok(s1, ref, rel=1e-4)
+    assert ok, worst
+
+
+def test_pickle_roundtrip(tmp_path, kaldi_params, cfg1):
+    x1, x2, _ = cfg1
+    m = make_nplda(kaldi_params)
+    a, b = x1[:100].to(DEV), x2[:100].to(DEV)
+    with torch.no_grad():
+        s0 = m(a, b)
+    f = tmp_path / "m.pt"
+    m.SaveModel(str(f))
+    m2 = pickle.load(open(f, "rb"))
+    assert m2.threshold[99.0] is m2.Th99
+    with torch.no_grad():
+        s1 = m2(a, b)
+    np.testing.assert_array_equal(s0.cpu().numpy(), s1.cpu().numpy())
+
+
+def test_host_entry_matches_device_entry(kaldi_params, cfg1):
+    x1, x2, _ = cfg1
+    n = 5000
+    m = make_nplda(kaldi_params)
+    with torch.no_grad():
+        s_dev = m(x1[:n].to(DEV), x2[:n].to(DEV)).cpu()
+    pack = m.packed.get("nplda", m._params(), 512, 170, 170)
+    h1, h2 = x1[:n].contiguous().pin_memory(), x2[:n].contiguous().pin_memory()
+    out = torch.empty(n).pin_memory()
+    chunk = 1536
+    nbytes = _lib.lib().nplda_host_scratch_bytes(chunk, 512)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    torch.cuda.synchronize()
+    rc = _lib.lib().nplda_score_fwd_host(ctypes.c_void_p(h1.data_ptr()), ctypes.c_void_p(h2.data_ptr()), n, 512, 170,
+                                         170, _lib.ptr(pack), ctypes.c_void_p(out.data_ptr()), chunk,
+                                         _lib.ptr(scratch), nbytes, 0, _lib.IMPL_AUTO)
+    assert rc == 0
+    np.testing.assert_array_equal(out.numpy(), s_dev.numpy())
+
+
+def test_scorefile_generation_matches_reference_files(tmp_path, kaldi_params):
+    from neuralplda_b200 import scorefile_generator as sg
+    z = np.load(os.path.join(GOLDEN, "c6_mega.npz"))
+    mega = {str(u): z["vecs"][i] for i, u in enumerate(z["ids"])}
+    m = make_nplda(kaldi_params)
+    for fn, trials, golden in ((sg.generate_voices_scores, "c6_voices_trials.txt", "c6_voices_scores.txt"),
+                               (sg.generate_sre_scores, "c6_sre_trials.tsv", "c6_sre_scores.tsv")):
+        out = tmp_path / golden
+        fn(str(out), os.path.join(GOLDEN, trials), mega, m, torch.device(DEV), batch_size=10)
+        got = open(out).read().strip().split("\n")
+        ref = open(os.path.join(GOLDEN, golden)).read().strip().split("\n")
+        assert len(got) == len(ref)
+        for lg, lr in zip(got, ref):
+            cg, cr = lg.split("\t"), lr.split("\t")
+            assert cg[:-1] == cr[:-1]
+            if cr[-1] != "LLR":
+                assert float(cg[-1]) == pytest.approx(float(cr[-1]), rel=1e-4, abs=1e-5)
+
+
+def test_large_properties_1m(kaldi_params):
+    """BASELINE.json configs[1] size: 1M pairs.  Oracle on a strided subsample, plus
+    size-independent properties: pair symmetry S(x1,x2)=S(x2,x1) and chunking invariance."""
+    mean = kaldi_params["mean"].to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1002)
+    n = 1_000_000
+    spk = torch.randn(2000, 512, generator=g, device=DEV)
+    s1 = torch.randint(0, 2000, (n,), generator=g, device=DEV)
+    s2 = torch.where(torch.rand(n, generator=g, device=DEV) < 0.1, s1, torch.randint(0, 2000, (n,), generator=g, device=DEV))
+    x1 = mean + spk[s1] + 0.7 * torch.randn(n, 512, generator=g, device=DEV)
+    x2 = mean + spk[s2] + 0.7 * torch.randn(n, 512, generator=g, device=DEV)
+    kp = kaldi_params
+    for impl in IMPLS:
+        m = make_nplda(kp, impl)
+        with torch.no_grad():
+            s = m(x1, x2)
+            s_sw = m(x2, x1)
+            s_part = torch.cat([m(x1[a:a + 333_333], x2[a:a + 333_333]) for a in range(0, n, 333_333)])
+        assert torch.isfinite(s).all()
+        np.testing.assert_allclose(s.cpu().numpy(), s_sw.cpu().numpy(), rtol=1e-4, atol=1e-4)
+        ok, worst = parity_ok(s_part, s.cpu(), rel=1e-4)
+        assert ok, worst
+        idx = torch.arange(0, n, 97, device=DEV)
+        ref = O.nplda_score(x1[idx].cpu(), x2[idx].cpu(), kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+        ok, worst = parity_ok(s[idx], ref, rel=1e-4)
+        assert ok, worst
