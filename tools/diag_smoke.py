@@ -11,7 +11,7 @@ m = npl.NeuralPlda(NC).to(dev)
 sd = m.state_dict()
 for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias", "b1"), ("centering_and_wccn_plda.weight", "W2"), ("centering_and_wccn_plda.bias", "b2"), ("P_sqrt", "P_sqrt"), ("Q", "Q")):
     sd[name].copy_(kp[key])
-m.impl = npl.IMPL_SIMT
+m.impl = int(os.environ.get("NPLDA_IMPL", "1"))
 for (n, spk, seed) in ((4096, 64, 7), (4096, 200, 7), (4096, 64, 8), (10000, 200, 1001), (4000, 64, 7)):
     x1, x2, t = O.synth_pairs(n, spk, seed=seed, mean=kp["mean"])
     ref = O.nplda_score(x1, x2, kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"]).double()
