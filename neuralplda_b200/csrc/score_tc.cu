@@ -6,7 +6,7 @@
 // the scores within ~1e-5 of the fp32 reference (numerics).
 //
 // One persistent CTA per SM, warp-specialised, tiles of 64 trial pairs = 128 rows with
-// the two sides of a pair in adjacent rows (row m = 2*pair + side):
+// in every 16-row group rows 0-7 are side 0 and rows 8-15 side 1 of the same 8 pairs:
 //   converters (8 warps)  x rows: global -> registers (16 B per lane, 64 B per row per
 //                         request) -> bf16 hi/lo -> tcgen05.st.16x256b into a 5-stage
 //                         ring of A operands in TENSOR MEMORY (no shared-memory traffic)
@@ -23,6 +23,7 @@
 //                         S = sum Q y1^2 + Q y2^2 + 2 P y1 y2 with the partner row
 //                         fetched by warp shuffle; one 4-byte store per pair
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -70,6 +71,7 @@ struct Args {
     const uint8_t *w1img, *w2img;
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
     float *scores;
+    int dbg;                // bottleneck experiments (env NPLDA_TC_DEBUG): 1 cached x, 2 no weight copies, 4 no MMAs
 };
 
 struct Ring {
@@ -90,6 +92,13 @@ __device__ __forceinline__ float4 ldg_stream(const float *p) {
 __device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
                  : "memory");
 }
 
@@ -130,73 +139,97 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
 
     if (warp < EPI_WARPS) {
         // =============================== EPILOGUE ===============================
-        const int m = warp * 32 + lane;                       // tile row = TMEM lane
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        uint8_t *u_hi = Us + (m >> 3) * 128 + (m & 7) * 16;   // + kchunk * KCH_U
-        uint8_t *u_lo = u_hi + U_HALF;
-        const float *b1s = par, *b2s = par + NPAD, *ps = par + 2 * NPAD, *qs = par + 3 * NPAD;
+        // Row map inside each 16-lane group: lanes 0-7 = side 0, lanes 8-15 = side 1 of pairs 0-7, so a
+        // tcgen05.ld.16x256b hands thread t both sides of pair (t >> 2) for columns {2(t&3), 2(t&3)+1} of
+        // every 8-column block: no cross-lane traffic per element, two shuffles per row sum at the end.
+        const int rsub = lane >> 2, cq = lane & 3;
+        const float2 *b1s = reinterpret_cast<const float2 *>(par);
+        const float2 *b2s = reinterpret_cast<const float2 *>(par + NPAD);
+        const float2 *ps = reinterpret_cast<const float2 *>(par + 2 * NPAD);
+        const float2 *qs = reinterpret_cast<const float2 *>(par + 3 * NPAD);
         for (int64_t i = 0; i < T; ++i) {
             const int d = (int)(i & 1);
-            const uint32_t dcol = lane_addr + d * NPAD;
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
-            // ---- layer-1 accumulator -> length norm ----
+            float rinv[2][2];
+            // ---- layer-1 accumulator: a = D + b1, |a|, bf16 hi/lo of a -> U (normalised after layer 2) ----
             mbar_wait(&d_full[d], par_d);
             tc_fence_after();
-            float ss = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < NPAD; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(dcol + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float a = __uint_as_float(v[j]) + b1s[c0 + j];
-                    ss = fmaf(a, a, ss);
-                }
-            }
-            const float rinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize eps (models.py:368)
             mbar_wait(u_empty, (uint32_t)((i & 1) ^ 1));           // layer 2 of the previous tile has read U
-#pragma unroll 1
-            for (int c0 = 0; c0 < NPAD; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(dcol + c0, v);
-                tmem_ld_wait();
-                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float u0 = (__uint_as_float(v[2 * j]) + b1s[c0 + 2 * j]) * rinv;
-                    float u1 = (__uint_as_float(v[2 * j + 1]) + b1s[c0 + 2 * j + 1]) * rinv;
-                    split_bf16x2(u0, u1, hi[j], lo[j]);
+            for (int h = 0; h < 2; ++h) {
+                const int mrow = warp * 32 + h * 16 + rsub;          // side-0 row; side 1 is mrow + 8
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32 + h * 16) << 16) + d * NPAD;
+                uint8_t *u0 = Us + (mrow >> 3) * 128 + (mrow & 7) * 16 + cq * 4;   // + kchunk * KCH_U
+                uint8_t *u1 = u0 + 128;                                               // row + 8: next core matrix
+                float ss0a = 0.f, ss0b = 0.f, ss1a = 0.f, ss1b = 0.f;
+#pragma unroll 2
+                for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                    uint32_t v[8];
+                    tmem_ld_16x256b_x2(taddr + c0, v);
+                    tmem_ld_wait();
+                    const float2 ba = b1s[(c0 >> 1) + cq], bb = b1s[(c0 >> 1) + 4 + cq];
+                    const float a00 = __uint_as_float(v[0]) + ba.x, a01 = __uint_as_float(v[1]) + ba.y;
+                    const float a10 = __uint_as_float(v[2]) + ba.x, a11 = __uint_as_float(v[3]) + ba.y;
+                    const float a02 = __uint_as_float(v[4]) + bb.x, a03 = __uint_as_float(v[5]) + bb.y;
+                    const float a12 = __uint_as_float(v[6]) + bb.x, a13 = __uint_as_float(v[7]) + bb.y;
+                    ss0a = fmaf(a00, a00, ss0a); ss0b = fmaf(a01, a01, ss0b);
+                    ss0a = fmaf(a02, a02, ss0a); ss0b = fmaf(a03, a03, ss0b);
+                    ss1a = fmaf(a10, a10, ss1a); ss1b = fmaf(a11, a11, ss1b);
+                    ss1a = fmaf(a12, a12, ss1a); ss1b = fmaf(a13, a13, ss1b);
+                    uint32_t hi, lo;
+                    const int kc = c0 >> 3;
+                    split_bf16x2(a00, a01, hi, lo);
+                    *reinterpret_cast<uint32_t *>(u0 + kc * KCH_U) = hi;
+                    *reinterpret_cast<uint32_t *>(u0 + U_HALF + kc * KCH_U) = lo;
+                    split_bf16x2(a02, a03, hi, lo);
+                    *reinterpret_cast<uint32_t *>(u0 + (kc + 1) * KCH_U) = hi;
+                    *reinterpret_cast<uint32_t *>(u0 + U_HALF + (kc + 1) * KCH_U) = lo;
+                    split_bf16x2(a10, a11, hi, lo);
+                    *reinterpret_cast<uint32_t *>(u1 + kc * KCH_U) = hi;
+                    *reinterpret_cast<uint32_t *>(u1 + U_HALF + kc * KCH_U) = lo;
+                    split_bf16x2(a12, a13, hi, lo);
+                    *reinterpret_cast<uint32_t *>(u1 + (kc + 1) * KCH_U) = hi;
+                    *reinterpret_cast<uint32_t *>(u1 + U_HALF + (kc + 1) * KCH_U) = lo;
                 }
-                const int kc = c0 >> 3;
-                *reinterpret_cast<uint4 *>(u_hi + kc * KCH_U) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(u_hi + (kc + 1) * KCH_U) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                *reinterpret_cast<uint4 *>(u_lo + kc * KCH_U) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<uint4 *>(u_lo + (kc + 1) * KCH_U) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                float ss0 = ss0a + ss0b, ss1 = ss1a + ss1b;
+                ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+                ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+                rinv[h][0] = 1.f / fmaxf(sqrtf(ss0), 1e-12f);      // F.normalize eps (models.py:368)
+                rinv[h][1] = 1.f / fmaxf(sqrtf(ss1), 1e-12f);
             }
             fence_proxy_async();      // U is read by tcgen05.mma (async proxy)
             tc_fence_before();        // our TMEM reads of D are done before Y overwrites it
             mbar_arrive(u_full);
-            // ---- layer-2 accumulator -> pair score ----
+            // ---- layer-2 accumulator: y = Y / |a| + b2, pair score ----
             mbar_wait(&y_full[d], par_d);
             tc_fence_after();
-            float s = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < NPAD; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(dcol + c0, v);
-                tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float y = __uint_as_float(v[j]) + b2s[c0 + j];
-                    float yo = __shfl_xor_sync(0xffffffffu, y, 1);      // the other side of this pair
-                    s = fmaf(qs[c0 + j] * y, y, s);
-                    s = fmaf(ps[c0 + j] * y, yo, s);                    // both lanes add P y1 y2 -> factor 2
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32 + h * 16) << 16) + d * NPAD;
+                const float r0 = rinv[h][0], r1 = rinv[h][1];
+                float sa = 0.f, sb = 0.f;
+#pragma unroll 2
+                for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                    uint32_t v[8];
+                    tmem_ld_16x256b_x2(taddr + c0, v);
+                    tmem_ld_wait();
+                    const int ci = (c0 >> 1) + cq;
+                    const float2 ba = b2s[ci], bb = b2s[ci + 4], pa = ps[ci], pb = ps[ci + 4], qa = qs[ci], qb = qs[ci + 4];
+                    const float y00 = fmaf(__uint_as_float(v[0]), r0, ba.x), y01 = fmaf(__uint_as_float(v[1]), r0, ba.y);
+                    const float y10 = fmaf(__uint_as_float(v[2]), r1, ba.x), y11 = fmaf(__uint_as_float(v[3]), r1, ba.y);
+                    const float y02 = fmaf(__uint_as_float(v[4]), r0, bb.x), y03 = fmaf(__uint_as_float(v[5]), r0, bb.y);
+                    const float y12 = fmaf(__uint_as_float(v[6]), r1, bb.x), y13 = fmaf(__uint_as_float(v[7]), r1, bb.y);
+                    sa = fmaf(qa.x, fmaf(y00, y00, y10 * y10), sa); sa = fmaf(2.f * pa.x, y00 * y10, sa);
+                    sb = fmaf(qa.y, fmaf(y01, y01, y11 * y11), sb); sb = fmaf(2.f * pa.y, y01 * y11, sb);
+                    sa = fmaf(qb.x, fmaf(y02, y02, y12 * y12), sa); sa = fmaf(2.f * pb.x, y02 * y12, sa);
+                    sb = fmaf(qb.y, fmaf(y03, y03, y13 * y13), sb); sb = fmaf(2.f * pb.y, y03 * y13, sb);
                 }
+                float sc = sa + sb;
+                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+                const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + warp * 16 + h * 8 + rsub;
+                if (cq == 0 && pr < g.n) g.scores[pr] = sc;
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + (m >> 1);
-            if ((m & 1) == 0 && pr < g.n) g.scores[pr] = s;
             tc_fence_before();
             mbar_arrive(&d_empty[d]);
         }
@@ -204,59 +237,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
         // =============================== CONVERTERS ===============================
         const int cw = warp - EPI_WARPS;
         const int q = warp & 3, h = cw >> 2;                  // TMEM quadrant of this warp, 16-row half
-        const int m0 = q * 32 + h * 16 + (lane >> 2);         // rows m0 and m0 + 8
+        const int pl = q * 16 + h * 8 + (lane >> 2);          // pair (within the tile) of TMEM rows m and m + 8
         const int kq = (lane & 3) * 4;                        // k offset inside a 16-wide K step
         const uint32_t st_addr = tmem + ((uint32_t)(q * 32 + h * 16) << 16) + A_COL0;
         Ring ra(NA);
         const float *r0 = nullptr, *r1 = nullptr;
-        auto set_rows = [&](int64_t i) {
-            const int64_t pair0 = (blockIdx.x + i * gridDim.x) * TP;
-            const int side = m0 & 1;                           // (m0 + 8) has the same parity
-            int64_t pa = min(pair0 + (m0 >> 1), g.n - 1), pb = min(pair0 + ((m0 + 8) >> 1), g.n - 1);
+        auto set_rows = [&](int64_t i) {                       // r0: side 0 (x1), r1: side 1 (x2) of pair pl
+            const int64_t pr = min((blockIdx.x + i * gridDim.x) * TP + pl, g.n - 1);
             if (INDEXED) {
-                const int64_t *ix = side ? g.i2 : g.i1;
-                int64_t ia = ix[pa], ib = ix[pb];
+                int64_t ia = g.i1[pr], ib = g.i2[pr];
                 if (ia < 0 || ia >= g.n_rows) { *g.bad_flag = 1; ia = 0; }
                 if (ib < 0 || ib >= g.n_rows) { *g.bad_flag = 1; ib = 0; }
                 r0 = g.x1 + ia * g.d_in + kq;
                 r1 = g.x1 + ib * g.d_in + kq;
             } else {
-                const float *base = side ? g.x2 : g.x1;
-                r0 = base + pa * g.d_in + kq;
-                r1 = base + pb * g.d_in + kq;
+                r0 = g.x1 + pr * g.d_in + kq;
+                r1 = g.x2 + pr * g.d_in + kq;
             }
         };
-        float4 cur[4], nxt[4];
-        auto load = [&](float4 (&v)[4], int s) {
-            const int k = s * KST;
-            v[0] = ldg_stream(r0 + k); v[1] = ldg_stream(r0 + k + 16);
-            v[2] = ldg_stream(r1 + k); v[3] = ldg_stream(r1 + k + 16);
+        // Software pipeline: PF stages (PF * 64 B per thread) of x are in flight while one is
+        // converted -- 8 warps x 32 lanes x PF x 64 B = 64 KB per SM.
+        constexpr int PF = 4;
+        int64_t ip = 0;
+        int sp = 0;
+        auto issue = [&](float4 (&v)[4]) {
+            if (ip < T) {
+                const int k = (g.dbg & 1) ? 0 : sp * KST;           // dbg 1: every load hits the same (cached) line
+                v[0] = ldg_stream(r0 + k); v[1] = ldg_stream(r0 + k + 16);
+                v[2] = ldg_stream(r1 + k); v[3] = ldg_stream(r1 + k + 16);
+                if (++sp == g.nst1) { sp = 0; if (++ip < T) set_rows(ip); }
+            }
         };
-        if (T > 0) { set_rows(0); load(cur, 0); }
-        for (int64_t i = 0; i < T; ++i) {
-            for (int s = 0; s < g.nst1; ++s) {
-                // prefetch the next stage (of the next tile at the end of this one)
-                if (s + 1 < g.nst1) load(nxt, s + 1);
-                else if (i + 1 < T) { set_rows(i + 1); load(nxt, 0); }
-                // registers of tcgen05.st.16x256b.x2: r0,r1 -> (row, cols 2j,2j+1) r2,r3 -> (row+8, same cols),
-                // r4..r7 the same for the next 8 columns (k + 16)
-                uint32_t hi[8], lo[8];
-                split_bf16x2(cur[0].x, cur[0].y, hi[0], lo[0]); split_bf16x2(cur[0].z, cur[0].w, hi[1], lo[1]);
-                split_bf16x2(cur[2].x, cur[2].y, hi[2], lo[2]); split_bf16x2(cur[2].z, cur[2].w, hi[3], lo[3]);
-                split_bf16x2(cur[1].x, cur[1].y, hi[4], lo[4]); split_bf16x2(cur[1].z, cur[1].w, hi[5], lo[5]);
-                split_bf16x2(cur[3].x, cur[3].y, hi[6], lo[6]); split_bf16x2(cur[3].z, cur[3].w, hi[7], lo[7]);
-                mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
-                tc_fence_after();
-                const uint32_t col = st_addr + ra.stage * A_STAGE_COLS;
-                tmem_st_16x256b_x2(col, hi);
-                tmem_st_16x256b_x2(col + 16, lo);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[ra.stage]);
-                ra.advance();
+        float4 buf[PF][4];
+        if (T > 0) set_rows(0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+        for (int u = 0; u < PF; ++u) issue(buf[u]);
+        const int64_t total = T * g.nst1;
+        for (int64_t it = 0; it < total; it += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                if (it + u < total) {
+                    // registers of tcgen05.st.16x256b.x2: r0,r1 -> (row, cols 2j,2j+1)  r2,r3 -> (row+8, same
+                    // cols); r4..r7 the same for the next 8 columns (k + 16)
+                    const float4(&c)[4] = buf[u];
+                    uint32_t hi[8], lo[8];
+                    split_bf16x2(c[0].x, c[0].y, hi[0], lo[0]); split_bf16x2(c[0].z, c[0].w, hi[1], lo[1]);
+                    split_bf16x2(c[2].x, c[2].y, hi[2], lo[2]); split_bf16x2(c[2].z, c[2].w, hi[3], lo[3]);
+                    split_bf16x2(c[1].x, c[1].y, hi[4], lo[4]); split_bf16x2(c[1].z, c[1].w, hi[5], lo[5]);
+                    split_bf16x2(c[3].x, c[3].y, hi[6], lo[6]); split_bf16x2(c[3].z, c[3].w, hi[7], lo[7]);
+                    issue(buf[u]);                                   // refill this slot: PF stages ahead
+                    mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t col = st_addr + ra.stage * A_STAGE_COLS;
+                    tmem_st_16x256b_x2(col, hi);
+                    tmem_st_16x256b_x2(col + 16, lo);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[ra.stage]);
+                    ra.advance();
+                }
             }
         }
     } else if (warp == WARP_MMA) {
@@ -264,18 +304,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
         if (lane == 0) {
             Ring ra(NA), rb(NB);
             const uint32_t b_base = smem_addr(Bs), u_base = smem_addr(Us);
-            for (int64_t i = 0; i <= T; ++i) {
-                if (i < T) {       // layer 1 of tile i
-                    const int d = (int)(i & 1);
-                    mbar_wait(&d_empty[d], (uint32_t)(((i >> 1) & 1) ^ 1));
+            const int half = g.nst1 / 2;
+            const bool skip_mma = (g.dbg & 4) != 0;
+            auto layer1 = [&](uint32_t dcol, int s_begin, int s_end) {
+                for (int s = s_begin; s < s_end; ++s) {
+                    mbar_wait(&a_full[ra.stage], ra.phase);
+                    mbar_wait(&b_full[rb.stage], rb.phase);
                     tc_fence_after();
-                    const uint32_t dcol = tmem + d * NPAD;
-                    for (int s = 0; s < g.nst1; ++s) {
-                        mbar_wait(&a_full[ra.stage], ra.phase);
-                        mbar_wait(&b_full[rb.stage], rb.phase);
-                        tc_fence_after();
-                        const uint32_t acol = tmem + A_COL0 + ra.stage * A_STAGE_COLS;
-                        const uint32_t bs = b_base + rb.stage * B_STAGE;
+                    const uint32_t acol = tmem + A_COL0 + ra.stage * A_STAGE_COLS;
+                    const uint32_t bs = b_base + rb.stage * B_STAGE;
+                    if (!skip_mma) {
 #pragma unroll
                         for (int st = 0; st < 2; ++st) {
                             const uint64_t bhi = make_smem_desc(bs + st * 2 * KCH_B, KCH_B, 128);
@@ -284,14 +322,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
                             mma_ts(dcol, acol + 16 + st * 8, bhi, IDESC, 1);
                             mma_ts(dcol, acol + st * 8, blo, IDESC, 1);
                         }
-                        mma_commit(&a_empty[ra.stage]);
-                        mma_commit(&b_empty[rb.stage]);
-                        ra.advance();
-                        rb.advance();
                     }
-                    mma_commit(&d_full[d]);
+                    mma_commit(&a_empty[ra.stage]);
+                    mma_commit(&b_empty[rb.stage]);
+                    ra.advance();
+                    rb.advance();
                 }
-                if (i >= 1) {      // layer 2 of tile i - 1 (its U was written while layer 1 of tile i ran)
+            };
+            // Order per iteration: first half of layer 1 (tile i), layer 2 (tile i-1), second half of layer 1.
+            // Layer 2 lands mid-way so that the final epilogue of tile i-1 runs under the second half and
+            // the D buffer it frees is ready when layer 1 of tile i+1 starts.  The B loader follows the
+            // same order.
+            for (int64_t i = 0; i <= T; ++i) {
+                const uint32_t dcol_i = tmem + (uint32_t)(i & 1) * NPAD;
+                if (i < T) {
+                    mbar_wait(&d_empty[i & 1], (uint32_t)(((i >> 1) & 1) ^ 1));
+                    tc_fence_after();
+                    layer1(dcol_i, 0, half);
+                }
+                if (i >= 1) {      // layer 2 of tile i - 1
                     const int64_t j = i - 1;
                     const int d = (int)(j & 1);
                     const uint32_t dcol = tmem + d * NPAD;
@@ -302,7 +351,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
                         mbar_wait(&b_full[rb.stage], rb.phase);
                         tc_fence_after();
                         const uint32_t bs = b_base + rb.stage * B_STAGE;
-                        for (int st = 0; st < nst; ++st) {
+                        for (int st = 0; st < nst && !skip_mma; ++st) {
                             const uint64_t bhi = make_smem_desc(bs + st * 2 * KCH_B, KCH_B, 128);
                             const uint64_t blo = make_smem_desc(bs + nst * 2 * KCH_B + st * 2 * KCH_B, KCH_B, 128);
                             const uint64_t uhi = make_smem_desc(u_base + (ks + st) * 2 * KCH_U, KCH_U, 128);
@@ -317,6 +366,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
                     mma_commit(&y_full[d]);
                     mma_commit(u_empty);
                 }
+                if (i < T) {
+                    layer1(dcol_i, half, g.nst1);
+                    mma_commit(&d_full[i & 1]);
+                }
             }
         }
     } else {
@@ -324,25 +377,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
         if (lane == 0) {
             Ring rb(NB);
             const int nst2 = (g.ksteps2 + 1) / 2;
+            const int half = g.nst1 / 2;
+            const bool skip_b = (g.dbg & 2) != 0;                  // dbg 2: arrive without copying the weights
+            auto put = [&](const uint8_t *src, uint32_t bytes) {
+                mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
+                if (skip_b) {
+                    mbar_arrive(&b_full[rb.stage]);
+                } else {
+                    mbar_arrive_expect_tx(&b_full[rb.stage], bytes);
+                    bulk_g2s(Bs + rb.stage * B_STAGE, src, bytes, &b_full[rb.stage]);
+                }
+                rb.advance();
+            };
             for (int64_t i = 0; i <= T; ++i) {
-                if (i < T) {
-                    for (int s = 0; s < g.nst1; ++s) {
-                        mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
-                        mbar_arrive_expect_tx(&b_full[rb.stage], B_STAGE);
-                        bulk_g2s(Bs + rb.stage * B_STAGE, g.w1img + (size_t)s * B_STAGE, B_STAGE, &b_full[rb.stage]);
-                        rb.advance();
-                    }
-                }
-                if (i >= 1) {
-                    for (int s = 0; s < nst2; ++s) {
-                        const int nst = min(2, g.ksteps2 - 2 * s);
-                        const uint32_t bytes = nst * (B_STAGE / 2);
-                        mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
-                        mbar_arrive_expect_tx(&b_full[rb.stage], bytes);
-                        bulk_g2s(Bs + rb.stage * B_STAGE, g.w2img + (size_t)s * B_STAGE, bytes, &b_full[rb.stage]);
-                        rb.advance();
-                    }
-                }
+                if (i < T)
+                    for (int s = 0; s < half; ++s) put(g.w1img + (size_t)s * B_STAGE, B_STAGE);
+                if (i >= 1)
+                    for (int s = 0; s < nst2; ++s) put(g.w2img + (size_t)s * B_STAGE, min(2, g.ksteps2 - 2 * s) * (B_STAGE / 2));
+                if (i < T)
+                    for (int s = half; s < g.nst1; ++s) put(g.w1img + (size_t)s * B_STAGE, B_STAGE);
             }
         }
     }
@@ -426,6 +479,10 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
     a.b1 = (const float *)(pack + L.b1); a.b2 = (const float *)(pack + L.b2);
     a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.q);
     a.scores = scores;
+    {
+        const char *e = getenv("NPLDA_TC_DEBUG");
+        a.dbg = e ? atoi(e) : 0;
+    }
     const int64_t ntiles = (n + tcg::TP - 1) / tcg::TP;
     const int grid = (int)std::min<int64_t>(ntiles, sm_count());
     auto kern = i1 ? tcg::score_tc_kernel<true> : tcg::score_tc_kernel<false>;
