@@ -5,25 +5,31 @@
 // ("bf16x3"; the dropped lo*lo term and the split residuals are O(2^-17)), which keeps
 // the scores within ~1e-5 of the fp32 reference (numerics).
 //
-// One persistent CTA per SM, warp-specialised, tiles of 64 trial pairs = 128 rows with
-// in every 16-row group rows 0-7 are side 0 and rows 8-15 side 1 of the same 8 pairs:
-//   converters (8 warps)  x rows: global -> registers (16 B per lane, 64 B per row per
-//                         request) -> bf16 hi/lo -> tcgen05.st.16x256b into a 5-stage
-//                         ring of A operands in TENSOR MEMORY (no shared-memory traffic)
-//   B loader   (1 thread) weight images (bf16 hi/lo, already in the tcgen05 K-major
-//                         core-matrix layout, packed once per parameter update) ->
-//                         5-stage shared-memory ring with 1-D bulk async copies (TMA
-//                         engine) completing on mbarriers
+// One persistent CTA per SM, warp-specialised, tiles of 64 trial pairs = 128 rows; in every
+// 16-row group rows 0-7 are side 0 and rows 8-15 side 1 of the same 8 pairs:
+//   X loader   (1 thread) [64 pairs x 32 floats] boxes of x1 and x2 -> 4-stage shared-memory ring
+//                         with cp.async.bulk.tensor.2d (TMA, 128-byte swizzle).  Measured on B200
+//                         (tools/tmapattern.cu, tools/ldpattern.cu) this row-sliced pattern streams at
+//                         6.9 TB/s through TMA but only 3.4 TB/s through LDG.
+//   converters (2x8 warps) shared memory -> registers (conflict-free thanks to the swizzle) -> bf16
+//                         hi/lo -> tcgen05.st.16x256b into a 5-stage ring of A operands in TENSOR
+//                         MEMORY (the A operand never goes back to shared memory)
+//   B loader   (1 thread) weight images (bf16 hi/lo, already in the tcgen05 K-major core-matrix
+//                         layout, packed once per parameter update) -> 3-stage shared-memory ring
+//                         with 1-D bulk async copies completing on mbarriers (L2-resident source)
 //   MMA issuer (1 thread) layer 1:  D[128x176] += A(tmem) * W1^T   (3 MMAs per K=16 step)
 //                         layer 2:  Y[128x176]  = U(smem) * W2^T   (Y overwrites D)
-//                         two D buffers in TMEM: layer 1 of tile t+1 runs under the
-//                         epilogue of tile t
-//   epilogue   (4 warps)  thread = row: D -> +b1 -> |a| -> u = a/|a| -> bf16 hi/lo ->
-//                         shared memory (A operand of layer 2); then Y -> +b2 ->
-//                         S = sum Q y1^2 + Q y2^2 + 2 P y1 y2 with the partner row
-//                         fetched by warp shuffle; one 4-byte store per pair
+//                         two D buffers in TMEM; layer 2 of tile t-1 is issued in the middle of
+//                         layer 1 of tile t so both epilogue halves run under MMA work
+//   epilogue   (8 warps)  tcgen05.ld.16x256b gives a thread both sides of one pair for 4 of every 16
+//                         columns.  Pass 1: a = D + b1, |a|^2, bf16 hi/lo of the UN-normalised a ->
+//                         shared memory (A operand of layer 2; the length norm commutes with the
+//                         linear layer 2).  Pass 2: y = Y/|a| + b2, S = sum Q y1^2 + Q y2^2 + 2 P y1 y2,
+//                         two shuffles per pair, one 4-byte store per pair.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -34,44 +40,47 @@ namespace tcg {
 
 using namespace tc;
 
-constexpr int TP = 64;               // pairs per tile
-constexpr int NPAD = 176;            // MMA N (both layers): 170 padded to a multiple of 16
-constexpr int KST = 32;              // K per pipeline stage (two MMA K-steps)
-constexpr int KCH_B = (NPAD / 8) * 128;        // 2816 B: one 8-wide k-chunk of B (22 core matrices)
-constexpr int B_STAGE = 2 * 4 * KCH_B;         // 22528 B: hi + lo, K = 32
-constexpr int NB = 5;                          // B ring stages
-constexpr int KCH_U = (128 / 8) * 128;         // 2048 B: one k-chunk of U (16 core matrices)
-constexpr int U_HALF = (NPAD / 8) * KCH_U;     // 45056 B (hi or lo), K = 176
-constexpr int NA = 5;                          // A ring stages in TMEM
-constexpr int A_COL0 = 2 * NPAD;               // TMEM columns: D0 [0,176) D1 [176,352) A ring [352,512)
-constexpr int A_STAGE_COLS = 32;               // per stage: 16 columns hi + 16 columns lo (K = 32)
+constexpr int TP = 64;                          // pairs per tile
+constexpr int NPAD = 176;                       // MMA N (both layers): 170 padded to a multiple of 16
+constexpr int KST = 32;                         // K per x / A stage (two MMA K-steps)
+constexpr int KCH_B = (NPAD / 8) * 128;         // 2816 B: one 8-wide k-chunk of B (22 core matrices)
+constexpr int B_STEP = 4 * KCH_B;               // 11264 B: hi (2 chunks) + lo (2 chunks), K = 16
+constexpr int B_STAGE = 2 * B_STEP;             // 22528 B: two K=16 steps
+constexpr int NBS = 3;                          // B ring stages (K = 32 each)
+constexpr int X_BOX = TP * KST * 4;             // 8192 B: [64 rows x 32 floats]
+constexpr int X_STAGE = 2 * X_BOX;              // x1 box + x2 box
+constexpr int NX = 4;                           // x ring stages
+constexpr int KCH_U = (128 / 8) * 128;          // 2048 B: one k-chunk of U (16 core matrices)
+constexpr int U_HALF = (NPAD / 8) * KCH_U;      // 45056 B (hi or lo), K = 176
+constexpr int NA = 5;                           // A ring stages in TMEM
+constexpr int A_COL0 = 2 * NPAD;                // TMEM columns: D0 [0,176) D1 [176,352) A ring [352,512)
+constexpr int A_STAGE_COLS = 32;                // per stage: 16 columns hi + 16 columns lo (K = 32)
 
-constexpr int EPI_WARPS = 4, CONV_WARPS = 8;
-constexpr int WARP_MMA = EPI_WARPS + CONV_WARPS, WARP_LOAD = WARP_MMA + 1;
-constexpr int NTHREADS = (WARP_LOAD + 1) * 32;   // 448
+constexpr int EPI_WARPS = 8, CONV_WARPS = 8, CONV_SETS = 2;   // converter sets alternate stages
+constexpr int WARP_MMA = EPI_WARPS + CONV_SETS * CONV_WARPS, WARP_BLOAD = WARP_MMA + 1, WARP_XLOAD = WARP_MMA + 2;
+constexpr int NTHREADS = (WARP_XLOAD + 1) * 32;  // 864
 
-// shared-memory map (bytes)
-constexpr int SM_B = 0;
-constexpr int SM_U = SM_B + NB * B_STAGE;                // 112640
-constexpr int SM_PAR = SM_U + 2 * U_HALF;                // 202752: b1, b2, P, Q (NPAD floats each)
-constexpr int SM_BAR = SM_PAR + 4 * NPAD * 4;            // 205568
-constexpr int N_BARS = 2 * NA + 2 * NB + 2 + 2 + 2 + 2;  // a_full/empty, b_full/empty, d_full, d_empty, y_full, u_full/u_empty
+// shared-memory map (bytes); the x ring needs 1024-byte alignment (128B swizzle atoms)
+constexpr int SM_X = 0;
+constexpr int SM_B = SM_X + NX * X_STAGE;
+constexpr int SM_U = SM_B + NBS * B_STAGE;
+constexpr int SM_PAR = SM_U + 2 * U_HALF;                 // b1, b2, P, Q (NPAD floats each)
+constexpr int SM_BAR = SM_PAR + 4 * NPAD * 4;
+constexpr int N_BARS = 2 * NX + 2 * NA + 2 * NBS + 8;
 constexpr int SM_TMEM = SM_BAR + N_BARS * 8;
-constexpr int SMEM_BYTES = SM_TMEM + 16;
+constexpr int SMEM_BYTES = SM_TMEM + 16 + 1024;       // + slack for the 1 KB alignment
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 struct Args {
     const float *x1, *x2;
-    const int64_t *i1, *i2;
-    int64_t n_rows;
-    int32_t *bad_flag;
     int64_t n;
-    int d_in;               // multiple of 32
     int nst1;               // layer-1 stages  = d_in / 32
     int ksteps2;            // layer-2 K steps = round_up(d1, 16) / 16
     const uint8_t *w1img, *w2img;
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
     float *scores;
-    int dbg;                // bottleneck experiments (env NPLDA_TC_DEBUG): 1 cached x, 2 no weight copies, 4 no MMAs
+    long long *trace;       // optional timeline buffer (env NPLDA_TC_TRACE), CTA 0 only
+    int dbg;                // bottleneck experiments (env NPLDA_TC_DEBUG): 1 no x loads, 2 no weight copies, 4 no MMAs
 };
 
 struct Ring {
@@ -81,20 +90,18 @@ struct Ring {
     __device__ void advance() { if (++stage == (uint32_t)n) { stage = 0; phase ^= 1; } }
 };
 
-__device__ __forceinline__ float4 ldg_stream(const float *p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p));
-    return v;
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_addr(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+        : "memory");
 }
-
 __device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
-
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -102,15 +109,22 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
                  : "memory");
 }
 
-template <bool INDEXED>
-__global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+// timeline slots (CTA 0, tile TRACE_TILE): role * 64 + index
+constexpr int TRACE_TILE = 5;
+#define TRACE(role, idx) do { if (g.trace && blockIdx.x == 0) g.trace[(role) * 64 + (idx)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: 1 KB aligned
+    uint8_t *Xs = smem + SM_X;
     uint8_t *Bs = smem + SM_B;
     uint8_t *Us = smem + SM_U;
     float *par = reinterpret_cast<float *>(smem + SM_PAR);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR);
-    uint64_t *a_full = bars, *a_empty = bars + NA, *b_full = bars + 2 * NA, *b_empty = bars + 2 * NA + NB;
-    uint64_t *d_full = bars + 2 * NA + 2 * NB, *d_empty = d_full + 2, *y_full = d_full + 4;
+    uint64_t *x_full = bars, *x_empty = x_full + NX, *a_full = x_empty + NX, *a_empty = a_full + NA;
+    uint64_t *b_full = a_empty + NA, *b_empty = b_full + NBS;
+    uint64_t *d_full = b_empty + NBS, *d_empty = d_full + 2, *y_full = d_full + 4;
     uint64_t *u_full = d_full + 6, *u_empty = d_full + 7;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM);
 
@@ -123,8 +137,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
         par[i] = g.b1[i]; par[NPAD + i] = g.b2[i]; par[2 * NPAD + i] = g.p[i]; par[3 * NPAD + i] = g.q[i];
     }
     if (tid == 0) {
+        for (int s = 0; s < NX; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], CONV_WARPS); }
         for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], CONV_WARPS); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < NBS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int d = 0; d < 2; ++d) { mbar_init(&d_full[d], 1); mbar_init(&d_empty[d], EPI_WARPS * 32); mbar_init(&y_full[d], 1); }
         mbar_init(u_full, EPI_WARPS * 32);
         mbar_init(u_empty, 1);
@@ -139,194 +154,235 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
 
     if (warp < EPI_WARPS) {
         // =============================== EPILOGUE ===============================
-        // Row map inside each 16-lane group: lanes 0-7 = side 0, lanes 8-15 = side 1 of pairs 0-7, so a
-        // tcgen05.ld.16x256b hands thread t both sides of pair (t >> 2) for columns {2(t&3), 2(t&3)+1} of
-        // every 8-column block: no cross-lane traffic per element, two shuffles per row sum at the end.
+        const int q = warp & 3, h = warp >> 2;                  // TMEM quadrant, 16-lane half
         const int rsub = lane >> 2, cq = lane & 3;
+        const int mrow = q * 32 + h * 16 + rsub;                 // side-0 row; side 1 is mrow + 8
+        const int pl = q * 16 + h * 8 + rsub;                    // pair within the tile
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32 + h * 16) << 16);
+        uint8_t *u0 = Us + (mrow >> 3) * 128 + (mrow & 7) * 16 + cq * 4;   // + kchunk * KCH_U
+        uint8_t *u1 = u0 + 128;                                            // row + 8: next core matrix
         const float2 *b1s = reinterpret_cast<const float2 *>(par);
         const float2 *b2s = reinterpret_cast<const float2 *>(par + NPAD);
         const float2 *ps = reinterpret_cast<const float2 *>(par + 2 * NPAD);
         const float2 *qs = reinterpret_cast<const float2 *>(par + 3 * NPAD);
+
+        auto pass1 = [&](const uint32_t (&v)[8], int c0, float (&ss)[4]) {
+            const float2 ba = b1s[(c0 >> 1) + cq], bb = b1s[(c0 >> 1) + 4 + cq];
+            const float a00 = __uint_as_float(v[0]) + ba.x, a01 = __uint_as_float(v[1]) + ba.y;
+            const float a10 = __uint_as_float(v[2]) + ba.x, a11 = __uint_as_float(v[3]) + ba.y;
+            const float a02 = __uint_as_float(v[4]) + bb.x, a03 = __uint_as_float(v[5]) + bb.y;
+            const float a12 = __uint_as_float(v[6]) + bb.x, a13 = __uint_as_float(v[7]) + bb.y;
+            ss[0] = fmaf(a00, a00, ss[0]); ss[1] = fmaf(a01, a01, ss[1]);
+            ss[0] = fmaf(a02, a02, ss[0]); ss[1] = fmaf(a03, a03, ss[1]);
+            ss[2] = fmaf(a10, a10, ss[2]); ss[3] = fmaf(a11, a11, ss[3]);
+            ss[2] = fmaf(a12, a12, ss[2]); ss[3] = fmaf(a13, a13, ss[3]);
+            uint32_t hi, lo;
+            const int kc = c0 >> 3;
+            split_bf16x2(a00, a01, hi, lo);
+            *reinterpret_cast<uint32_t *>(u0 + kc * KCH_U) = hi;
+            *reinterpret_cast<uint32_t *>(u0 + U_HALF + kc * KCH_U) = lo;
+            split_bf16x2(a02, a03, hi, lo);
+            *reinterpret_cast<uint32_t *>(u0 + (kc + 1) * KCH_U) = hi;
+            *reinterpret_cast<uint32_t *>(u0 + U_HALF + (kc + 1) * KCH_U) = lo;
+            split_bf16x2(a10, a11, hi, lo);
+            *reinterpret_cast<uint32_t *>(u1 + kc * KCH_U) = hi;
+            *reinterpret_cast<uint32_t *>(u1 + U_HALF + kc * KCH_U) = lo;
+            split_bf16x2(a12, a13, hi, lo);
+            *reinterpret_cast<uint32_t *>(u1 + (kc + 1) * KCH_U) = hi;
+            *reinterpret_cast<uint32_t *>(u1 + U_HALF + (kc + 1) * KCH_U) = lo;
+        };
+        auto pass2 = [&](const uint32_t (&v)[8], int c0, float r0, float r1, float (&sc)[2]) {
+            const int ci = (c0 >> 1) + cq;
+            const float2 ba = b2s[ci], bb = b2s[ci + 4], pa = ps[ci], pb = ps[ci + 4], qa = qs[ci], qb = qs[ci + 4];
+            const float y00 = fmaf(__uint_as_float(v[0]), r0, ba.x), y01 = fmaf(__uint_as_float(v[1]), r0, ba.y);
+            const float y10 = fmaf(__uint_as_float(v[2]), r1, ba.x), y11 = fmaf(__uint_as_float(v[3]), r1, ba.y);
+            const float y02 = fmaf(__uint_as_float(v[4]), r0, bb.x), y03 = fmaf(__uint_as_float(v[5]), r0, bb.y);
+            const float y12 = fmaf(__uint_as_float(v[6]), r1, bb.x), y13 = fmaf(__uint_as_float(v[7]), r1, bb.y);
+            sc[0] = fmaf(qa.x, fmaf(y00, y00, y10 * y10), sc[0]); sc[0] = fmaf(2.f * pa.x, y00 * y10, sc[0]);
+            sc[1] = fmaf(qa.y, fmaf(y01, y01, y11 * y11), sc[1]); sc[1] = fmaf(2.f * pa.y, y01 * y11, sc[1]);
+            sc[0] = fmaf(qb.x, fmaf(y02, y02, y12 * y12), sc[0]); sc[0] = fmaf(2.f * pb.x, y02 * y12, sc[0]);
+            sc[1] = fmaf(qb.y, fmaf(y03, y03, y13 * y13), sc[1]); sc[1] = fmaf(2.f * pb.y, y03 * y13, sc[1]);
+        };
+
         for (int64_t i = 0; i < T; ++i) {
             const int d = (int)(i & 1);
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
-            float rinv[2][2];
+            const uint32_t taddr = tbase + d * NPAD;
             // ---- layer-1 accumulator: a = D + b1, |a|, bf16 hi/lo of a -> U (normalised after layer 2) ----
+            if (i == TRACE_TILE && tid == 0) TRACE(0, 0);
             mbar_wait(&d_full[d], par_d);
             tc_fence_after();
+            if (i == TRACE_TILE && tid == 0) TRACE(0, 1);
             mbar_wait(u_empty, (uint32_t)((i & 1) ^ 1));           // layer 2 of the previous tile has read U
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int mrow = warp * 32 + h * 16 + rsub;          // side-0 row; side 1 is mrow + 8
-                const uint32_t taddr = tmem + ((uint32_t)(warp * 32 + h * 16) << 16) + d * NPAD;
-                uint8_t *u0 = Us + (mrow >> 3) * 128 + (mrow & 7) * 16 + cq * 4;   // + kchunk * KCH_U
-                uint8_t *u1 = u0 + 128;                                               // row + 8: next core matrix
-                float ss0a = 0.f, ss0b = 0.f, ss1a = 0.f, ss1b = 0.f;
-#pragma unroll 2
-                for (int c0 = 0; c0 < NPAD; c0 += 16) {
-                    uint32_t v[8];
-                    tmem_ld_16x256b_x2(taddr + c0, v);
-                    tmem_ld_wait();
-                    const float2 ba = b1s[(c0 >> 1) + cq], bb = b1s[(c0 >> 1) + 4 + cq];
-                    const float a00 = __uint_as_float(v[0]) + ba.x, a01 = __uint_as_float(v[1]) + ba.y;
-                    const float a10 = __uint_as_float(v[2]) + ba.x, a11 = __uint_as_float(v[3]) + ba.y;
-                    const float a02 = __uint_as_float(v[4]) + bb.x, a03 = __uint_as_float(v[5]) + bb.y;
-                    const float a12 = __uint_as_float(v[6]) + bb.x, a13 = __uint_as_float(v[7]) + bb.y;
-                    ss0a = fmaf(a00, a00, ss0a); ss0b = fmaf(a01, a01, ss0b);
-                    ss0a = fmaf(a02, a02, ss0a); ss0b = fmaf(a03, a03, ss0b);
-                    ss1a = fmaf(a10, a10, ss1a); ss1b = fmaf(a11, a11, ss1b);
-                    ss1a = fmaf(a12, a12, ss1a); ss1b = fmaf(a13, a13, ss1b);
-                    uint32_t hi, lo;
-                    const int kc = c0 >> 3;
-                    split_bf16x2(a00, a01, hi, lo);
-                    *reinterpret_cast<uint32_t *>(u0 + kc * KCH_U) = hi;
-                    *reinterpret_cast<uint32_t *>(u0 + U_HALF + kc * KCH_U) = lo;
-                    split_bf16x2(a02, a03, hi, lo);
-                    *reinterpret_cast<uint32_t *>(u0 + (kc + 1) * KCH_U) = hi;
-                    *reinterpret_cast<uint32_t *>(u0 + U_HALF + (kc + 1) * KCH_U) = lo;
-                    split_bf16x2(a10, a11, hi, lo);
-                    *reinterpret_cast<uint32_t *>(u1 + kc * KCH_U) = hi;
-                    *reinterpret_cast<uint32_t *>(u1 + U_HALF + kc * KCH_U) = lo;
-                    split_bf16x2(a12, a13, hi, lo);
-                    *reinterpret_cast<uint32_t *>(u1 + (kc + 1) * KCH_U) = hi;
-                    *reinterpret_cast<uint32_t *>(u1 + U_HALF + (kc + 1) * KCH_U) = lo;
-                }
-                float ss0 = ss0a + ss0b, ss1 = ss1a + ss1b;
-                ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
-                ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
-                rinv[h][0] = 1.f / fmaxf(sqrtf(ss0), 1e-12f);      // F.normalize eps (models.py:368)
-                rinv[h][1] = 1.f / fmaxf(sqrtf(ss1), 1e-12f);
+            float ss[4] = {0.f, 0.f, 0.f, 0.f};
+            const int cend = (g.dbg & 32) ? 0 : NPAD - 16;          // dbg 32: epilogue does (almost) no work
+#pragma unroll 1
+            for (int c0 = 0; c0 < cend; c0 += 32) {                 // two 16-column loads per wait
+                uint32_t va[8], vb[8];
+                tmem_ld_16x256b_x2(taddr + c0, va);
+                tmem_ld_16x256b_x2(taddr + c0 + 16, vb);
+                tmem_ld_wait();
+                pass1(va, c0, ss);
+                pass1(vb, c0 + 16, ss);
             }
+            {
+                uint32_t va[8];
+                tmem_ld_16x256b_x2(taddr + NPAD - 16, va);
+                tmem_ld_wait();
+                pass1(va, NPAD - 16, ss);
+            }
+            float ss0 = ss[0] + ss[1], ss1 = ss[2] + ss[3];
+            ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+            ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+            const float r0 = 1.f / fmaxf(sqrtf(ss0), 1e-12f);      // F.normalize eps (models.py:368)
+            const float r1 = 1.f / fmaxf(sqrtf(ss1), 1e-12f);
             fence_proxy_async();      // U is read by tcgen05.mma (async proxy)
             tc_fence_before();        // our TMEM reads of D are done before Y overwrites it
             mbar_arrive(u_full);
+            if (i == TRACE_TILE && tid == 0) TRACE(0, 2);
             // ---- layer-2 accumulator: y = Y / |a| + b2, pair score ----
             mbar_wait(&y_full[d], par_d);
             tc_fence_after();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t taddr = tmem + ((uint32_t)(warp * 32 + h * 16) << 16) + d * NPAD;
-                const float r0 = rinv[h][0], r1 = rinv[h][1];
-                float sa = 0.f, sb = 0.f;
-#pragma unroll 2
-                for (int c0 = 0; c0 < NPAD; c0 += 16) {
-                    uint32_t v[8];
-                    tmem_ld_16x256b_x2(taddr + c0, v);
-                    tmem_ld_wait();
-                    const int ci = (c0 >> 1) + cq;
-                    const float2 ba = b2s[ci], bb = b2s[ci + 4], pa = ps[ci], pb = ps[ci + 4], qa = qs[ci], qb = qs[ci + 4];
-                    const float y00 = fmaf(__uint_as_float(v[0]), r0, ba.x), y01 = fmaf(__uint_as_float(v[1]), r0, ba.y);
-                    const float y10 = fmaf(__uint_as_float(v[2]), r1, ba.x), y11 = fmaf(__uint_as_float(v[3]), r1, ba.y);
-                    const float y02 = fmaf(__uint_as_float(v[4]), r0, bb.x), y03 = fmaf(__uint_as_float(v[5]), r0, bb.y);
-                    const float y12 = fmaf(__uint_as_float(v[6]), r1, bb.x), y13 = fmaf(__uint_as_float(v[7]), r1, bb.y);
-                    sa = fmaf(qa.x, fmaf(y00, y00, y10 * y10), sa); sa = fmaf(2.f * pa.x, y00 * y10, sa);
-                    sb = fmaf(qa.y, fmaf(y01, y01, y11 * y11), sb); sb = fmaf(2.f * pa.y, y01 * y11, sb);
-                    sa = fmaf(qb.x, fmaf(y02, y02, y12 * y12), sa); sa = fmaf(2.f * pb.x, y02 * y12, sa);
-                    sb = fmaf(qb.y, fmaf(y03, y03, y13 * y13), sb); sb = fmaf(2.f * pb.y, y03 * y13, sb);
-                }
-                float sc = sa + sb;
-                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-                const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + warp * 16 + h * 8 + rsub;
-                if (cq == 0 && pr < g.n) g.scores[pr] = sc;
+            if (i == TRACE_TILE && tid == 0) TRACE(0, 3);
+            float sc[2] = {0.f, 0.f};
+#pragma unroll 1
+            for (int c0 = 0; c0 < cend; c0 += 32) {
+                uint32_t va[8], vb[8];
+                tmem_ld_16x256b_x2(taddr + c0, va);
+                tmem_ld_16x256b_x2(taddr + c0 + 16, vb);
+                tmem_ld_wait();
+                pass2(va, c0, r0, r1, sc);
+                pass2(vb, c0 + 16, r0, r1, sc);
+            }
+            {
+                uint32_t va[8];
+                tmem_ld_16x256b_x2(taddr + NPAD - 16, va);
+                tmem_ld_wait();
+                pass2(va, NPAD - 16, r0, r1, sc);
             }
             tc_fence_before();
-            mbar_arrive(&d_empty[d]);
+            mbar_arrive(&d_empty[d]);                               // D buffer free before the shuffles/store
+            if (i == TRACE_TILE && tid == 0) TRACE(0, 4);
+            float s = sc[0] + sc[1];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + pl;
+            if (cq == 0 && pr < g.n) g.scores[pr] = s;
         }
-    } else if (warp < EPI_WARPS + CONV_WARPS) {
+    } else if (warp < WARP_MMA) {
         // =============================== CONVERTERS ===============================
-        const int cw = warp - EPI_WARPS;
-        const int q = warp & 3, h = cw >> 2;                  // TMEM quadrant of this warp, 16-row half
-        const int pl = q * 16 + h * 8 + (lane >> 2);          // pair (within the tile) of TMEM rows m and m + 8
-        const int kq = (lane & 3) * 4;                        // k offset inside a 16-wide K step
+        // Two sets of 8 warps; set s handles stages it = s, s + 2, ...: one warp's chain of waits, LDS,
+        // conversion, TMEM store and store-wait (~800 cycles) then spans two MMA stage times.
+        const int cset = (warp - EPI_WARPS) >> 3;
+        const int q = warp & 3, h = ((warp - EPI_WARPS) >> 2) & 1;
+        const int rsub = lane >> 2, cq = lane & 3;
+        const int pl = q * 16 + h * 8 + rsub;                    // pair within the tile = row of both x boxes
         const uint32_t st_addr = tmem + ((uint32_t)(q * 32 + h * 16) << 16) + A_COL0;
-        Ring ra(NA);
-        const float *r0 = nullptr, *r1 = nullptr;
-        auto set_rows = [&](int64_t i) {                       // r0: side 0 (x1), r1: side 1 (x2) of pair pl
-            const int64_t pr = min((blockIdx.x + i * gridDim.x) * TP + pl, g.n - 1);
-            if (INDEXED) {
-                int64_t ia = g.i1[pr], ib = g.i2[pr];
-                if (ia < 0 || ia >= g.n_rows) { *g.bad_flag = 1; ia = 0; }
-                if (ib < 0 || ib >= g.n_rows) { *g.bad_flag = 1; ib = 0; }
-                r0 = g.x1 + ia * g.d_in + kq;
-                r1 = g.x1 + ib * g.d_in + kq;
-            } else {
-                r0 = g.x1 + pr * g.d_in + kq;
-                r1 = g.x2 + pr * g.d_in + kq;
-            }
-        };
-        // Software pipeline: PF stages (PF * 64 B per thread) of x are in flight while one is
-        // converted -- 8 warps x 32 lanes x PF x 64 B = 64 KB per SM.
-        constexpr int PF = 4;
-        int64_t ip = 0;
-        int sp = 0;
-        auto issue = [&](float4 (&v)[4]) {
-            if (ip < T) {
-                const int k = (g.dbg & 1) ? 0 : sp * KST;           // dbg 1: every load hits the same (cached) line
-                v[0] = ldg_stream(r0 + k); v[1] = ldg_stream(r0 + k + 16);
-                v[2] = ldg_stream(r1 + k); v[3] = ldg_stream(r1 + k + 16);
-                if (++sp == g.nst1) { sp = 0; if (++ip < T) set_rows(ip); }
-            }
-        };
-        float4 buf[PF][4];
-        if (T > 0) set_rows(0);
-#pragma unroll
-        for (int u = 0; u < PF; ++u) issue(buf[u]);
+        // 128-byte swizzle of the x boxes: 16-byte chunk c of row r sits at chunk (c ^ (r & 7))
+        const int off0 = pl * 128 + ((cq ^ rsub) << 4);          // k-step 0: chunks 0-3
+        const int off1 = pl * 128 + (((4 + cq) ^ rsub) << 4);    // k-step 1: chunks 4-7
         const int64_t total = T * g.nst1;
-        for (int64_t it = 0; it < total; it += PF) {
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                if (it + u < total) {
-                    // registers of tcgen05.st.16x256b.x2: r0,r1 -> (row, cols 2j,2j+1)  r2,r3 -> (row+8, same
-                    // cols); r4..r7 the same for the next 8 columns (k + 16)
-                    const float4(&c)[4] = buf[u];
-                    uint32_t hi[8], lo[8];
-                    split_bf16x2(c[0].x, c[0].y, hi[0], lo[0]); split_bf16x2(c[0].z, c[0].w, hi[1], lo[1]);
-                    split_bf16x2(c[2].x, c[2].y, hi[2], lo[2]); split_bf16x2(c[2].z, c[2].w, hi[3], lo[3]);
-                    split_bf16x2(c[1].x, c[1].y, hi[4], lo[4]); split_bf16x2(c[1].z, c[1].w, hi[5], lo[5]);
-                    split_bf16x2(c[3].x, c[3].y, hi[6], lo[6]); split_bf16x2(c[3].z, c[3].w, hi[7], lo[7]);
-                    issue(buf[u]);                                   // refill this slot: PF stages ahead
-                    mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
-                    tc_fence_after();
-                    const uint32_t col = st_addr + ra.stage * A_STAGE_COLS;
-                    tmem_st_16x256b_x2(col, hi);
-                    tmem_st_16x256b_x2(col + 16, lo);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[ra.stage]);
-                    ra.advance();
-                }
+        Ring rx(NX), ra(NA);
+        for (int64_t it = 0; it < total; ++it, rx.advance(), ra.advance()) {
+            // mbarrier parity waits are only unambiguous for a waiter that observes EVERY phase of a
+            // barrier, so both sets wait for every stage's x_full in order and skip the other set's data.
+            if ((it & 1) != cset) {
+                if (!(g.dbg & 1)) mbar_wait(&x_full[rx.stage], rx.phase);
+                continue;
             }
+            const uint8_t *xs = Xs + rx.stage * X_STAGE;
+            const bool tr = (warp == EPI_WARPS || warp == EPI_WARPS + 8) && lane == 0 && it / g.nst1 == TRACE_TILE;
+            const int ts = (int)(it % g.nst1);
+            if (tr) TRACE(1, 3 * ts);
+            if (!(g.dbg & 1)) mbar_wait(&x_full[rx.stage], rx.phase);
+            if (tr) TRACE(1, 3 * ts + 1);
+            float4 a0, a1, b0, b1;
+            if (g.dbg & 16) {                                       // dbg 16: no shared-memory reads
+                a0 = a1 = b0 = b1 = make_float4(1.f, 2.f, 3.f, (float)it);
+            } else {
+                a0 = *reinterpret_cast<const float4 *>(xs + off0);
+                a1 = *reinterpret_cast<const float4 *>(xs + off1);
+                b0 = *reinterpret_cast<const float4 *>(xs + X_BOX + off0);
+                b1 = *reinterpret_cast<const float4 *>(xs + X_BOX + off1);
+            }
+            // registers of tcgen05.st.16x256b.x2: r0,r1 -> (row, cols 2j,2j+1)  r2,r3 -> (row+8, same cols);
+            // r4..r7 the same for the next 8 columns (k + 16)
+            uint32_t hi[8], lo[8];
+            split_bf16x2(a0.x, a0.y, hi[0], lo[0]); split_bf16x2(a0.z, a0.w, hi[1], lo[1]);
+            split_bf16x2(b0.x, b0.y, hi[2], lo[2]); split_bf16x2(b0.z, b0.w, hi[3], lo[3]);
+            split_bf16x2(a1.x, a1.y, hi[4], lo[4]); split_bf16x2(a1.z, a1.w, hi[5], lo[5]);
+            split_bf16x2(b1.x, b1.y, hi[6], lo[6]); split_bf16x2(b1.z, b1.w, hi[7], lo[7]);
+            mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
+            tc_fence_after();
+            const uint32_t col = st_addr + ra.stage * A_STAGE_COLS;
+            if (!(g.dbg & 8)) {                                     // dbg 8: no TMEM stores
+                tmem_st_16x256b_x2(col, hi);
+                tmem_st_16x256b_x2(col + 16, lo);
+            } else if (hi[0] == 0x12345678u && lo[7] == 0x9abcdefu) {
+                g.scores[0] = 0.f;                                  // keep the conversion alive
+            }
+            // Release the x slot only now: the stores above consume every register the four LDS wrote,
+            // so the shared-memory reads have completed.  (Arriving right after the LDS were merely
+            // ISSUED let the TMA refill race them: the compiler sinks the conversions below the arrive.)
+            __syncwarp();
+            if (lane == 0 && !(g.dbg & 1)) mbar_arrive(&x_empty[rx.stage]);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[ra.stage]);
+            if (tr) TRACE(1, 3 * ts + 2);
         }
     } else if (warp == WARP_MMA) {
         // =============================== MMA ISSUER ===============================
-        if (lane == 0) {
-            Ring ra(NA), rb(NB);
+        // The whole warp runs this loop converged; only the tcgen05 instructions are issued by one elected
+        // lane.  Warp-uniform control flow lets the compiler keep ring indices and descriptors in uniform
+        // registers: issued from a divergent lane-0 branch every descriptor costs R2UR round trips and the
+        // single thread, not the tensor pipe, paces the kernel (measured: ~1000 instead of ~590 cycles/stage).
+        {
+            Ring ra(NA), rb(NBS);
             const uint32_t b_base = smem_addr(Bs), u_base = smem_addr(Us);
             const int half = g.nst1 / 2;
             const bool skip_mma = (g.dbg & 4) != 0;
+            int64_t cur_tile = -1;
+            // The MMA queue is shallow: a tcgen05.mma issue stalls until the pipe accepts it, so whatever the
+            // warp executes between two issues runs under the previous MMA.  The barrier waits of stage s+1
+            // (~100 cycles each even when already satisfied) are therefore placed between the two K-steps of
+            // stage s, not after its commits.
             auto layer1 = [&](uint32_t dcol, int s_begin, int s_end) {
+                if (s_begin >= s_end) return;
+                mbar_wait(&a_full[ra.stage], ra.phase);
+                mbar_wait(&b_full[rb.stage], rb.phase);
                 for (int s = s_begin; s < s_end; ++s) {
-                    mbar_wait(&a_full[ra.stage], ra.phase);
-                    mbar_wait(&b_full[rb.stage], rb.phase);
                     tc_fence_after();
                     const uint32_t acol = tmem + A_COL0 + ra.stage * A_STAGE_COLS;
                     const uint32_t bs = b_base + rb.stage * B_STAGE;
-                    if (!skip_mma) {
-#pragma unroll
-                        for (int st = 0; st < 2; ++st) {
-                            const uint64_t bhi = make_smem_desc(bs + st * 2 * KCH_B, KCH_B, 128);
-                            const uint64_t blo = make_smem_desc(bs + 4 * KCH_B + st * 2 * KCH_B, KCH_B, 128);
-                            mma_ts(dcol, acol + st * 8, bhi, IDESC, (s | st) != 0);
-                            mma_ts(dcol, acol + 16 + st * 8, bhi, IDESC, 1);
-                            mma_ts(dcol, acol + st * 8, blo, IDESC, 1);
-                        }
+                    const uint64_t bhi0 = make_smem_desc(bs, KCH_B, 128);
+                    if (elect_one() && !skip_mma) {
+                        mma_ts(dcol, acol, bhi0, IDESC, s != 0);
+                        mma_ts(dcol, acol + 16, bhi0, IDESC, 1);
+                        mma_ts(dcol, acol, bhi0 + ((2 * KCH_B) >> 4), IDESC, 1);
                     }
-                    mma_commit(&a_empty[ra.stage]);
-                    mma_commit(&b_empty[rb.stage]);
-                    ra.advance();
-                    rb.advance();
+                    __syncwarp();
+                    Ring na = ra, nb = rb;
+                    na.advance();
+                    nb.advance();
+                    if (s + 1 < s_end) {
+                        mbar_wait(&a_full[na.stage], na.phase);
+                        mbar_wait(&b_full[nb.stage], nb.phase);
+                    }
+                    if (elect_one()) {
+                        if (!skip_mma) {
+                            const uint64_t bhi1 = bhi0 + (B_STEP >> 4);
+                            mma_ts(dcol, acol + 8, bhi1, IDESC, 1);
+                            mma_ts(dcol, acol + 24, bhi1, IDESC, 1);
+                            mma_ts(dcol, acol + 8, bhi1 + ((2 * KCH_B) >> 4), IDESC, 1);
+                        }
+                        mma_commit(&a_empty[ra.stage]);
+                        mma_commit(&b_empty[rb.stage]);
+                    }
+                    __syncwarp();
+                    ra = na;
+                    rb = nb;
                 }
             };
             // Order per iteration: first half of layer 1 (tile i), layer 2 (tile i-1), second half of layer 1.
@@ -335,6 +391,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
             // same order.
             for (int64_t i = 0; i <= T; ++i) {
                 const uint32_t dcol_i = tmem + (uint32_t)(i & 1) * NPAD;
+                cur_tile = i;
+                if (i == TRACE_TILE && lane == 0) TRACE(2, 60);
                 if (i < T) {
                     mbar_wait(&d_empty[i & 1], (uint32_t)(((i >> 1) & 1) ^ 1));
                     tc_fence_after();
@@ -344,39 +402,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
                     const int64_t j = i - 1;
                     const int d = (int)(j & 1);
                     const uint32_t dcol = tmem + d * NPAD;
+                    if (i == TRACE_TILE && lane == 0) TRACE(2, 61);
                     mbar_wait(u_full, (uint32_t)(j & 1));
                     tc_fence_after();
+                    if (i == TRACE_TILE && lane == 0) TRACE(2, 62);
+                    mbar_wait(&b_full[rb.stage], rb.phase);
                     for (int ks = 0; ks < g.ksteps2; ks += 2) {
                         const int nst = min(2, g.ksteps2 - ks);
-                        mbar_wait(&b_full[rb.stage], rb.phase);
                         tc_fence_after();
                         const uint32_t bs = b_base + rb.stage * B_STAGE;
-                        for (int st = 0; st < nst && !skip_mma; ++st) {
-                            const uint64_t bhi = make_smem_desc(bs + st * 2 * KCH_B, KCH_B, 128);
-                            const uint64_t blo = make_smem_desc(bs + nst * 2 * KCH_B + st * 2 * KCH_B, KCH_B, 128);
-                            const uint64_t uhi = make_smem_desc(u_base + (ks + st) * 2 * KCH_U, KCH_U, 128);
-                            const uint64_t ulo = make_smem_desc(u_base + U_HALF + (ks + st) * 2 * KCH_U, KCH_U, 128);
-                            mma_ss(dcol, uhi, bhi, IDESC, (ks | st) != 0);
-                            mma_ss(dcol, ulo, bhi, IDESC, 1);
-                            mma_ss(dcol, uhi, blo, IDESC, 1);
+                        const uint64_t bhi0 = make_smem_desc(bs, KCH_B, 128);
+                        const uint64_t uhi0 = make_smem_desc(u_base + ks * 2 * KCH_U, KCH_U, 128);
+                        const uint64_t ulo0 = make_smem_desc(u_base + U_HALF + ks * 2 * KCH_U, KCH_U, 128);
+                        if (elect_one() && !skip_mma) {
+                            mma_ss(dcol, uhi0, bhi0, IDESC, ks != 0);
+                            mma_ss(dcol, ulo0, bhi0, IDESC, 1);
+                            mma_ss(dcol, uhi0, bhi0 + ((2 * KCH_B) >> 4), IDESC, 1);
                         }
-                        mma_commit(&b_empty[rb.stage]);
-                        rb.advance();
+                        __syncwarp();
+                        Ring nb = rb;
+                        nb.advance();
+                        if (ks + 2 < g.ksteps2) mbar_wait(&b_full[nb.stage], nb.phase);
+                        if (elect_one()) {
+                            if (nst == 2 && !skip_mma) {
+                                const uint64_t bhi1 = bhi0 + (B_STEP >> 4);
+                                const uint64_t uhi1 = uhi0 + ((2 * KCH_U) >> 4), ulo1 = ulo0 + ((2 * KCH_U) >> 4);
+                                mma_ss(dcol, uhi1, bhi1, IDESC, 1);
+                                mma_ss(dcol, ulo1, bhi1, IDESC, 1);
+                                mma_ss(dcol, uhi1, bhi1 + ((2 * KCH_B) >> 4), IDESC, 1);
+                            }
+                            mma_commit(&b_empty[rb.stage]);
+                        }
+                        __syncwarp();
+                        rb = nb;
                     }
-                    mma_commit(&y_full[d]);
-                    mma_commit(u_empty);
+                    if (elect_one()) {
+                        mma_commit(&y_full[d]);
+                        mma_commit(u_empty);
+                    }
+                    __syncwarp();
+                    if (i == TRACE_TILE && lane == 0) TRACE(2, 63);
                 }
                 if (i < T) {
                     layer1(dcol_i, half, g.nst1);
-                    mma_commit(&d_full[i & 1]);
+                    if (elect_one()) mma_commit(&d_full[i & 1]);
+                    __syncwarp();
                 }
             }
+            // Drain: the arrivals of the last commits on a_empty / b_empty / u_empty are not waited for by
+            // any producer.  They must land before this CTA exits, or they would hit the freshly
+            // initialised barriers of the next kernel's CTA on this SM (seen as a launch failure when
+            // launches are queued back to back).
+            if (T > 0) {
+                for (int k = 0; k < NA; ++k) { mbar_wait(&a_empty[ra.stage], ra.phase ^ 1); ra.advance(); }
+                for (int k = 0; k < NBS; ++k) { mbar_wait(&b_empty[rb.stage], rb.phase ^ 1); rb.advance(); }
+                mbar_wait(u_empty, (uint32_t)((T & 1) ^ 1));
+            }
         }
-    } else {
+    } else if (warp == WARP_BLOAD) {
         // =============================== B LOADER ===============================
         if (lane == 0) {
-            Ring rb(NB);
-            const int nst2 = (g.ksteps2 + 1) / 2;
+            Ring rb(NBS);
             const int half = g.nst1 / 2;
             const bool skip_b = (g.dbg & 2) != 0;                  // dbg 2: arrive without copying the weights
             auto put = [&](const uint8_t *src, uint32_t bytes) {
@@ -393,9 +479,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
                 if (i < T)
                     for (int s = 0; s < half; ++s) put(g.w1img + (size_t)s * B_STAGE, B_STAGE);
                 if (i >= 1)
-                    for (int s = 0; s < nst2; ++s) put(g.w2img + (size_t)s * B_STAGE, min(2, g.ksteps2 - 2 * s) * (B_STAGE / 2));
+                    for (int ks = 0; ks < g.ksteps2; ks += 2)
+                        put(g.w2img + (size_t)ks * B_STEP, min(2, g.ksteps2 - ks) * B_STEP);
                 if (i < T)
                     for (int s = half; s < g.nst1; ++s) put(g.w1img + (size_t)s * B_STAGE, B_STAGE);
+            }
+        }
+    } else {
+        // =============================== X LOADER ===============================
+        if (lane == 0 && !(g.dbg & 1)) {
+            Ring rx(NX);
+            for (int64_t i = 0; i < T; ++i) {
+                const int row0 = (int)((blockIdx.x + i * gridDim.x) * TP);
+                for (int s = 0; s < g.nst1; ++s) {
+                    mbar_wait(&x_empty[rx.stage], rx.phase ^ 1);
+                    mbar_arrive_expect_tx(&x_full[rx.stage], X_STAGE);
+                    uint8_t *dst = Xs + rx.stage * X_STAGE;
+                    tma_load_2d(dst, &map1, s * KST, row0, &x_full[rx.stage]);      // rows past n are zero-filled
+                    tma_load_2d(dst + X_BOX, &map2, s * KST, row0, &x_full[rx.stage]);
+                    rx.advance();
+                }
             }
         }
     }
@@ -407,31 +510,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_tc_kernel(Args g) {
 }
 
 // ---- weight images --------------------------------------------------------------------------
-// Stage s of an image covers K = [32 s, 32 s + 32) (the last layer-2 stage may cover 16):
-//   [hi: nkch k-chunks][lo: nkch k-chunks], k-chunk = 22 core matrices of 8 rows x 8 k (128 B each);
-//   element (row n, k) of chunk c sits at c*2816 + (n/8)*128 + (n%8)*16 + (k%8)*2.
+// Step s of an image covers K = [16 s, 16 s + 16):  [hi chunk 0][hi chunk 1][lo chunk 0][lo chunk 1],
+// a chunk = 22 core matrices of 8 rows x 8 k (128 B each); element (row n, k) of a chunk sits at
+// (n/8)*128 + (n%8)*16 + (k%8)*2.
 __global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ksteps, uint8_t *__restrict__ img) {
-    const int nstages = (ksteps + 1) / 2;
-    const int64_t total = (int64_t)nstages * 4 * NPAD * 8;       // one thread per (stage, chunk, row, 8 k) pair-of-chunks unit
+    const int64_t total = (int64_t)ksteps * 2 * NPAD * 8;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int kk = (int)(e & 7);
         const int n = (int)((e >> 3) % NPAD);
-        const int c = (int)(((e >> 3) / NPAD) & 3);
-        const int s = (int)(((e >> 3) / NPAD) >> 2);
-        const int nkch = 2 * min(2, ksteps - 2 * s);
-        if (c >= nkch) continue;
-        const int k = s * KST + c * 8 + kk;
+        const int c = (int)(((e >> 3) / NPAD) & 1);
+        const int s = (int)(((e >> 3) / NPAD) >> 1);
+        const int k = s * 16 + c * 8 + kk;
         const float w = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        uint8_t *st = img + (size_t)s * B_STAGE;
+        uint8_t *st = img + (size_t)s * B_STEP;
         const size_t off = (size_t)c * KCH_B + (n >> 3) * 128 + (n & 7) * 16 + kk * 2;
         *reinterpret_cast<__nv_bfloat16 *>(st + off) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(st + (size_t)nkch * KCH_B + off) = lo;
+        *reinterpret_cast<__nv_bfloat16 *>(st + 2 * KCH_B + off) = lo;
     }
 }
 
-static int64_t image_bytes(int ksteps) { return (int64_t)((ksteps + 1) / 2) * B_STAGE; }
+static int64_t image_bytes(int ksteps) { return (int64_t)ksteps * B_STEP; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+static bool make_x_map(CUtensorMap *m, const float *x, int64_t n, int d_in) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)d_in, (cuuint64_t)n};
+    cuuint64_t strides[1] = {(cuuint64_t)d_in * 4};
+    cuuint32_t box[2] = {KST, TP}, es[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 }  // namespace tcg
 
@@ -446,8 +572,7 @@ int64_t tc_image_bytes(int d_in, int d1, int d2) {
 }
 
 bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed) {
-    (void)indexed;
-    return !dplda && tc_dims_ok(L.d_in, L.d1, L.d2) && L.tc_bytes > 0;
+    return !dplda && !indexed && tc_dims_ok(L.d_in, L.d1, L.d2) && L.tc_bytes > 0;
 }
 
 int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float *b2, const float *p_sqrt,
@@ -470,10 +595,14 @@ int tc_pack_dplda(const float *, const float *, const float *, const float *, co
 
 int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2, int64_t n_rows,
              int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack, float *scores, cudaStream_t st) {
-    if (dplda || !tc_dims_ok(L.d_in, L.d1, L.d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    (void)i2; (void)n_rows; (void)bad_flag;
+    if (dplda || i1 || !tc_dims_ok(L.d_in, L.d1, L.d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n >= (int64_t)1 << 31) return NPLDA_ERR_UNSUPPORTED_DIM;   // TMA row coordinates are int32
+    CUtensorMap m1, m2;
+    if (!tcg::make_x_map(&m1, x1, n, L.d_in) || !tcg::make_x_map(&m2, x2, n, L.d_in)) return NPLDA_ERR_NO_DEVICE;
     tcg::Args a;
-    a.x1 = x1; a.x2 = x2; a.i1 = i1; a.i2 = i2; a.n_rows = n_rows; a.bad_flag = bad_flag; a.n = n;
-    a.d_in = L.d_in; a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
+    a.x1 = x1; a.x2 = x2; a.n = n;
+    a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
     a.w1img = (const uint8_t *)pack + L.tc;
     a.w2img = a.w1img + (tcg::image_bytes(L.d_in / 16) + 255) / 256 * 256;
     a.b1 = (const float *)(pack + L.b1); a.b2 = (const float *)(pack + L.b2);
@@ -483,12 +612,27 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
         const char *e = getenv("NPLDA_TC_DEBUG");
         a.dbg = e ? atoi(e) : 0;
     }
+    a.trace = nullptr;
+    if (getenv("NPLDA_TC_TRACE")) {
+        NPLDA_CUDA_TRY(cudaMalloc(&a.trace, 3 * 64 * sizeof(long long)));
+        NPLDA_CUDA_TRY(cudaMemsetAsync(a.trace, 0, 3 * 64 * sizeof(long long), st));
+    }
     const int64_t ntiles = (n + tcg::TP - 1) / tcg::TP;
     const int grid = (int)std::min<int64_t>(ntiles, sm_count());
-    auto kern = i1 ? tcg::score_tc_kernel<true> : tcg::score_tc_kernel<false>;
-    NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
-    kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(a);
+    NPLDA_CUDA_TRY(cudaFuncSetAttribute(tcg::score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
+    tcg::score_tc_kernel<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
     NPLDA_LAUNCH_CHECK();
+    if (a.trace) {   // debug only: synchronises
+        long long h[3 * 64];
+        NPLDA_CUDA_TRY(cudaStreamSynchronize(st));
+        NPLDA_CUDA_TRY(cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(a.trace);
+        long long t0 = h[2 * 64 + 60];
+        printf("[trace] tile %d of CTA 0, cycles relative to MMA-thread iteration start\n", tcg::TRACE_TILE);
+        printf("[trace] MMA: iter_start 0, L2 wait_u start %lld done %lld, L2 issued %lld\n", h[2*64+61]-t0, h[2*64+62]-t0, h[2*64+63]-t0);
+        for (int s2 = 0; s2 < 16; ++s2) printf("[trace] MMA st %2d: wait_a start %6lld got_a %6lld issued+committed %6lld | CONV st %2d: start %6lld got_x %6lld a_full_arrive %6lld\n", s2, h[2*64+3*s2]-t0, h[2*64+3*s2+1]-t0, h[2*64+3*s2+2]-t0, s2, h[64+3*s2]-t0, h[64+3*s2+1]-t0, h[64+3*s2+2]-t0);
+        printf("[trace] EPI: wait_d start %lld got_d %lld u_full_arrive %lld got_y %lld d_empty_arrive %lld\n", h[0]-t0, h[1]-t0, h[2]-t0, h[3]-t0, h[4]-t0);
+    }
     return NPLDA_OK;
 }
 

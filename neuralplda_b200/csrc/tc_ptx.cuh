@@ -88,6 +88,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
            | ((uint32_t)(M >> 4) << 24);  // M / 16
 }
 
+// One lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- MMA issue (one thread) -------------------------------------------------------------------
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
