@@ -47,7 +47,7 @@ def make_dplda(kp, ref_out, impl=None):
     return m
 
 
-IMPLS = [npl.IMPL_SIMT, npl.IMPL_AUTO]
+IMPLS = [npl.IMPL_SIMT, npl.IMPL_AUTO]       # AUTO = tcgen05 kernel for the reference dims (512-170-170)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -74,6 +74,33 @@ def test_nplda_forward_ragged_sizes(kaldi_params, cfg1, impl, n):
     ok, worst = parity_ok(s, ref, rel=1e-4)
     assert ok or n < 8, worst          # rms of a handful of scores is not a meaningful scale
     np.testing.assert_allclose(s.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-4)
+
+
+def test_tc_kernel_is_selected_and_deterministic(kaldi_params, cfg1):
+    """IMPL_TC must run (no silent fallback) for the reference dims, agree with the SIMT kernel, and be
+    bit-reproducible over back-to-back launches (the mbarrier pipelines have no data races)."""
+    x1, x2, _ = cfg1
+    a, b = x1.to(DEV), x2.to(DEV)
+    m = make_nplda(kaldi_params, npl.IMPL_TC)
+    with torch.no_grad():
+        first = m(a, b)
+        for _ in range(20):
+            again = m(a, b)
+        torch.cuda.synchronize()
+        assert torch.equal(first, again)
+        m.impl = npl.IMPL_SIMT
+        simt = m(a, b)
+    ok, worst = parity_ok(first, simt.cpu(), rel=1e-4)
+    assert ok, worst
+    class C(NC):
+        xvector_dim = 96
+    m2 = npl.NeuralPlda(C).to(DEV)
+    m2.impl = npl.IMPL_TC
+    with pytest.raises(RuntimeError):            # 96 % 32 == 0 is fine, but explicit TC on DPlda-only shapes must fail loudly
+        class D(NC):
+            xvector_dim = 100
+        m3 = npl.NeuralPlda(D).to(DEV); m3.impl = npl.IMPL_TC
+        m3(torch.zeros(4, 100, device=DEV), torch.zeros(4, 100, device=DEV))
 
 
 def test_empty_input(kaldi_params):
@@ -153,7 +180,15 @@ def test_indexed_matches_materialised(kaldi_params, impl):
         s_idx, flag = m.forward_indexed(t, i1.to(DEV), i2.to(DEV))
         s_mat = m(t[i1.to(DEV)], t[i2.to(DEV)])
     assert int(flag.item()) == 0
-    np.testing.assert_array_equal(s_idx.cpu().numpy(), s_mat.cpu().numpy())
+    if impl == npl.IMPL_SIMT:       # same kernel, same arithmetic: bit-identical
+        np.testing.assert_array_equal(s_idx.cpu().numpy(), s_mat.cpu().numpy())
+    else:                           # AUTO: materialised pairs take the tcgen05 kernel, the indexed gather the SIMT one
+        ok, worst = parity_ok(s_idx, s_mat.cpu(), rel=1e-4)
+        assert ok, worst
+    kp = kaldi_params
+    ref = O.nplda_score(table[i1], table[i2], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    ok, worst = parity_ok(s_idx, ref, rel=1e-4)
+    assert ok, worst
     bad = i1.clone(); bad[5] = 10 ** 6
     with torch.no_grad():
         _, flag = m.forward_indexed(t, bad.to(DEV), i2.to(DEV))
