@@ -88,6 +88,17 @@ int nplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d
 int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,
                     const void *pack, float *scores, int impl, void *stream);
 
+/* The two half-steps of forward, which the reference exposes as public methods:
+ * embeddings (models.py:366-370: y = W2 normalize(W1 x + b1) + b2, [n, d2]; DPlda 478-481:
+ * u = normalize(W1 x + b1), [n, d1]) and the score from materialised embeddings (372-376 / 483-489).
+ * Not on the trial-scoring hot path (forward never materialises embeddings); fp32 SIMT kernels. */
+int nplda_embed_fwd(const float *x, int64_t n, int d_in, int d1, int d2, const void *pack, float *emb,
+                    int is_dplda, void *stream);
+int nplda_score_from_embeddings(const float *y1, const float *y2, int64_t n, int d2, const float *p_sqrt,
+                                const float *q, float *scores, void *stream);
+int dplda_score_from_embeddings(const float *u1, const float *u2, int64_t n, int d_in, int d1,
+                                const void *pack, float *scores, void *stream);
+
 /* Same scores with the pair gather fused in: row i scores table[idx1[i]] vs
  * table[idx2[i]].  Replaces load_xvec_trials_from_numbatch
  * (sv_trials_loaders.py:418-426) + forward.  table: [n_rows, d_in] fp32;

@@ -43,6 +43,9 @@ SIGNATURES = {
                                         c_vp, c_int, c_vp]),
     "dplda_score_fwd_indexed": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
                                         c_int, c_vp]),
+    "nplda_embed_fwd": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "nplda_score_from_embeddings": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "dplda_score_from_embeddings": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     "nplda_loss_accum": (c_int, [c_vp, c_vp, c_i64, c_vp, c_int, ctypes.c_float, c_vp, c_vp, c_vp]),
     "nplda_loss_finalize": (c_int, [c_vp, ctypes.POINTER(ctypes.c_double), c_int, c_vp, c_vp]),
     "nplda_loss_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, ctypes.POINTER(ctypes.c_double), c_int,

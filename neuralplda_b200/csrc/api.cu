@@ -30,6 +30,26 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
              int64_t n_rows, int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack,
              float *scores, cudaStream_t st);   // score_tc.cu
 
+int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
+             float *out, cudaStream_t st);   // score_simt.cu
+
+// S = sum_k Q y1^2 + Q y2^2 + 2 P_sqrt^2 y1 y2 from materialised embeddings (models.py:372-376): one warp per pair
+__global__ void __launch_bounds__(256) score_from_emb_kernel(const float *__restrict__ y1, const float *__restrict__ y2,
+                                                             int64_t n, int d, const float *__restrict__ p_sqrt,
+                                                             const float *__restrict__ q, float *__restrict__ s) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = w0; i < n; i += nw) {
+        float acc = 0.f;
+        for (int k = lane; k < d; k += 32) {
+            const float a = y1[i * d + k], b = y2[i * d + k], ps = p_sqrt[k];
+            acc += q[k] * (a * a + b * b) + 2.f * (ps * ps) * (a * b);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s[i] = acc;
+    }
+}
+
 static int score_dispatch(bool dplda, const float *x1, const float *x2, const int64_t *i1,
                           const int64_t *i2, int64_t n_rows, int32_t *bad_flag, int64_t n, int d_in,
                           int d1, int d2, const void *pack, float *scores, int impl, void *stream) {
@@ -95,6 +115,34 @@ extern "C" int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const
                                        int impl, void *stream) {
     if (!idx1 || !idx2) return n == 0 ? NPLDA_OK : NPLDA_ERR_BAD_ARG;
     return score_dispatch(true, table, table, idx1, idx2, n_rows, bad_index_flag, n, d_in, d1, d1, pack, scores, impl, stream);
+}
+
+extern "C" int nplda_embed_fwd(const float *x, int64_t n, int d_in, int d1, int d2, const void *pack,
+                               float *emb, int is_dplda, void *stream) {
+    if (n < 0 || !pack || (n > 0 && (!x || !emb))) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n == 0) return NPLDA_OK;
+    PackLayout L = make_pack_layout(d_in, d1, d2);
+    return simt_aux(is_dplda ? 3 : 2, x, nullptr, n, L, (const char *)pack, emb, (cudaStream_t)stream);
+}
+
+extern "C" int nplda_score_from_embeddings(const float *y1, const float *y2, int64_t n, int d2,
+                                           const float *p_sqrt, const float *q, float *scores, void *stream) {
+    if (n < 0 || d2 <= 0 || (n > 0 && (!y1 || !y2 || !p_sqrt || !q || !scores))) return NPLDA_ERR_BAD_ARG;
+    if (n == 0) return NPLDA_OK;
+    const int grid = (int)std::min<int64_t>((n + 7) / 8, 8 * (int64_t)sm_count());
+    score_from_emb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y1, y2, n, d2, p_sqrt, q, scores);
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
+}
+
+extern "C" int dplda_score_from_embeddings(const float *u1, const float *u2, int64_t n, int d_in, int d1,
+                                           const void *pack, float *scores, void *stream) {
+    if (n < 0 || !pack || (n > 0 && (!u1 || !u2 || !scores))) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n == 0) return NPLDA_OK;
+    PackLayout L = make_pack_layout(d_in, d1, d1);
+    return simt_aux(4, u1, u2, n, L, (const char *)pack, scores, (cudaStream_t)stream);
 }
 
 // ---- host-buffer entry -----------------------------------------------------------

@@ -24,32 +24,39 @@ struct Args {
     int64_t n_rows;                // table rows (indexed)
     int32_t *bad_flag;
     int64_t n;
-    int d_in, k1p, k2p;
+    int d_in, k1p, k2p, d_out;     // d_out: embedding width written by the embed modes
     const float *w1t, *b1, *w2t, *w3t, *b2, *p, *q, *c;
     float *scores;
 };
 
-template <bool DPLDA, bool INDEXED, bool VEC>
+// MODE: 0 NeuralPlda score, 1 DPlda score, 2 NeuralPlda embeddings y[n,d2], 3 DPlda embeddings u[n,d1],
+//       4 DPlda score from embeddings (x1, x2 hold u rows of width d_in = d1)
+template <int MODE, bool INDEXED, bool VEC>
 __global__ void __launch_bounds__(NTHREADS, 1) score_kernel(Args g) {
+    constexpr bool DPLDA = MODE == 1 || MODE == 3 || MODE == 4;
+    constexpr bool EMBED = MODE == 2 || MODE == 3;
+    constexpr bool FROM_EMB = MODE == 4;
+    constexpr int ROWS_PER_UNIT = EMBED ? 1 : 2;             // an embed tile is 128 input rows, a score tile 64 pairs
     extern __shared__ __align__(16) float smem[];
     float *As = smem;
     float *Ws = smem + 2 * A_STAGE;
     float *Us = Ws + 2 * W_STAGE;
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int64_t ntiles = (g.n + TILE_PAIRS - 1) / TILE_PAIRS;
+    constexpr int UNITS = TM / ROWS_PER_UNIT;
+    const int64_t ntiles = (g.n + UNITS - 1) / UNITS;
     const int nch1 = g.k1p / KC;
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t pair0 = tile * TILE_PAIRS;
+        const int64_t pair0 = tile * UNITS;
 
         // source row pointers of the 4 tile rows this thread copies
         const float *rowp[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             int m = (tid + NTHREADS * r) >> 3;
-            int64_t pr = min(pair0 + row_pair(m), g.n - 1);   // tail rows re-read the last pair
-            int side = row_side(m);
+            int64_t pr = min(pair0 + (EMBED ? m : row_pair(m)), g.n - 1);   // tail rows re-read the last one
+            int side = EMBED ? 0 : row_side(m);
             if (INDEXED) {
                 int64_t ix = side ? g.i2[pr] : g.i1[pr];
                 if (ix < 0 || ix >= g.n_rows) { *g.bad_flag = 1; ix = 0; }
@@ -59,8 +66,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_kernel(Args g) {
             }
         }
 
-        // ---------------- layer 1 ------------------------------------------------
         float2 acc[8][6];
+        if (FROM_EMB) {
+            // the inputs already are length-normalised embeddings: tile rows -> Us, zero padded
+            for (int e = tid; e < TM * NP; e += NTHREADS) {
+                int m = e / NP, k = e % NP;
+                int64_t pr = min(pair0 + row_pair(m), g.n - 1);
+                const float *src = (row_side(m) ? g.x2 : g.x1) + pr * g.d_in;
+                Us[m * LDU + k] = k < g.d_in ? src[k] : 0.f;
+            }
+            __syncthreads();
+        } else {
+        // ---------------- layer 1 ------------------------------------------------
         zero_acc(acc);
         load_a_chunk<VEC>(As, rowp, 0, g.d_in, tid);
         load_w_chunk(Ws, g.w1t, 0, tid);
@@ -110,13 +127,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_kernel(Args g) {
                     u.z = acc[i][2 * j + 1].x / den;
                     u.w = acc[i][2 * j + 1].y / den;
                     *reinterpret_cast<float4 *>(urow + 64 * j) = u;
+                    if (MODE == 3) {                             // DPlda embeddings: u is the output
+                        int64_t row = pair0 + ty + 16 * i;
+                        const float uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            int c = 4 * tx + 64 * j + e;
+                            if (row < g.n && c < g.d_out) g.scores[row * g.d_out + c] = uv[e];
+                        }
+                    }
                 }
             }
         }
         __syncthreads();
+        }   // !FROM_EMB
+        if (MODE == 3) continue;
 
         // ---------------- layer 2 + pair score ------------------------------------
         float part[4];
+        if (MODE == 2) {                                         // NeuralPlda embeddings: y = W2 u + b2
+            layer2_gemm(acc, Us, Ws, g.w2t, g.k2p, tx, ty, tid);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float4 b2 = *reinterpret_cast<const float4 *>(g.b2 + 4 * tx + 64 * j);
+                const float bv[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int64_t row = pair0 + ty + 16 * i;
+                    const float yv[4] = {acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        int c = 4 * tx + 64 * j + e;
+                        if (row < g.n && c < g.d_out) g.scores[row * g.d_out + c] = yv[e] + bv[e];
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         if (!DPLDA) {
             layer2_gemm(acc, Us, Ws, g.w2t, g.k2p, tx, ty, tid);
 #pragma unroll
@@ -189,11 +237,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_kernel(Args g) {
     }
 }
 
-template <bool DPLDA, bool INDEXED>
+template <int MODE, bool INDEXED>
 static int launch(const Args &a, bool vec, cudaStream_t st) {
-    int64_t ntiles = (a.n + TILE_PAIRS - 1) / TILE_PAIRS;
+    const int units = (MODE == 2 || MODE == 3) ? TM : TILE_PAIRS;
+    int64_t ntiles = (a.n + units - 1) / units;
     int grid = (int)std::min<int64_t>(ntiles, sm_count());
-    auto kern = vec ? score_kernel<DPLDA, INDEXED, true> : score_kernel<DPLDA, INDEXED, false>;
+    auto kern = vec ? score_kernel<MODE, INDEXED, true> : score_kernel<MODE, INDEXED, false>;
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(a);
     NPLDA_LAUNCH_CHECK();
@@ -216,8 +265,27 @@ int score_simt(bool dplda, const float *x1, const float *x2, const int64_t *i1, 
     a.scores = scores;
     const bool indexed = i1 != nullptr;
     bool vec = (L.d_in % 4 == 0) && (((uintptr_t)x1 & 15) == 0) && (indexed || ((uintptr_t)x2 & 15) == 0);
-    if (dplda) return indexed ? simt::launch<true, true>(a, vec, st) : simt::launch<true, false>(a, vec, st);
-    return indexed ? simt::launch<false, true>(a, vec, st) : simt::launch<false, false>(a, vec, st);
+    a.d_out = 0;
+    if (dplda) return indexed ? simt::launch<1, true>(a, vec, st) : simt::launch<1, false>(a, vec, st);
+    return indexed ? simt::launch<0, true>(a, vec, st) : simt::launch<0, false>(a, vec, st);
+}
+
+// mode 2: NeuralPlda embeddings, 3: DPlda embeddings, 4: DPlda score from embeddings (x1, x2 = u rows)
+int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
+             float *out, cudaStream_t st) {
+    simt::Args a;
+    a.x1 = x1; a.x2 = x2 ? x2 : x1; a.i1 = a.i2 = nullptr; a.n_rows = 0; a.bad_flag = nullptr;
+    a.n = n; a.d_in = mode == 4 ? L.d1 : L.d_in; a.k1p = L.k1p; a.k2p = L.k2p;
+    a.w1t = (const float *)(pack + L.w1t); a.b1 = (const float *)(pack + L.b1);
+    a.w2t = (const float *)(pack + L.w2t); a.w3t = (const float *)(pack + L.w3t);
+    a.b2 = (const float *)(pack + L.b2); a.p = (const float *)(pack + L.p);
+    a.q = (const float *)(pack + L.q); a.c = (const float *)(pack + L.c);
+    a.scores = out;
+    a.d_out = mode == 2 ? L.d2 : L.d1;
+    bool vec = (a.d_in % 4 == 0) && (((uintptr_t)x1 & 15) == 0) && (((uintptr_t)a.x2 & 15) == 0);
+    if (mode == 2) return simt::launch<2, false>(a, vec, st);
+    if (mode == 3) return simt::launch<3, false>(a, vec, st);
+    return simt::launch<4, false>(a, false, st);
 }
 
 }  // namespace nplda

@@ -149,6 +149,50 @@ class DpldaScoreFn(torch.autograd.Function):
         return (dx1, dx2, dW1, db1, dw, dc, None, None)
 
 
+def embed(kind, x, params, dims, packed):
+    """extract_plda_embeddings of the reference (models.py:366-370 / 478-481), no autograd."""
+    require_cuda(x)
+    d_in, d1, d2 = dims
+    if x.dim() != 2 or x.shape[1] != d_in:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x.shape[0]}x{x.shape[-1]} and {d_in}x{d1})")
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+        raise RuntimeError("extract_plda_embeddings is provided without autograd: call it under torch.no_grad() "
+                           "(training goes through forward(x1, x2), which is differentiable)")
+    x = _f32c(x)
+    n = x.shape[0]
+    pack = packed.get(kind, params, d_in, d1, d2)
+    width = d2 if kind == "nplda" else d1
+    out = torch.empty(n, width, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().nplda_embed_fwd(ptr(x), n, d_in, d1, d2, ptr(pack), ptr(out), 0 if kind == "nplda" else 1,
+                                    stream_ptr()), "nplda_embed_fwd")
+    return out
+
+
+def score_from_embeddings(kind, e1, e2, params, dims, packed):
+    """forward_from_plda_embeddings of the reference (models.py:372-376 / 483-489), no autograd."""
+    require_cuda(e1, e2)
+    d_in, d1, d2 = dims
+    width = d2 if kind == "nplda" else d1
+    if e1.shape != e2.shape or e1.dim() != 2 or e1.shape[1] != width:
+        raise RuntimeError(f"expected two [N, {width}] embedding tensors")
+    if torch.is_grad_enabled() and (e1.requires_grad or e2.requires_grad or any(p.requires_grad for p in params)):
+        raise RuntimeError("forward_from_plda_embeddings is provided without autograd: call it under torch.no_grad()")
+    e1, e2 = _f32c(e1), _f32c(e2)
+    n = e1.shape[0]
+    scores = torch.empty(n, dtype=torch.float32, device=e1.device)
+    with torch.cuda.device(e1.device):
+        if kind == "nplda":
+            ps, q = _f32c(params[4].detach()), _f32c(params[5].detach())
+            check(lib().nplda_score_from_embeddings(ptr(e1), ptr(e2), n, d2, ptr(ps), ptr(q), ptr(scores),
+                                                    stream_ptr()), "nplda_score_from_embeddings")
+        else:
+            pack = packed.get(kind, params, d_in, d1, d2)
+            check(lib().dplda_score_from_embeddings(ptr(e1), ptr(e2), n, d_in, d1, ptr(pack), ptr(scores),
+                                                    stream_ptr()), "dplda_score_from_embeddings")
+    return scores
+
+
 def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO):
     """Scores of trials (table[i1[k]], table[i2[k]]) with the gather fused into the
     kernel (replaces sv_trials_loaders.load_xvec_trials_from_numbatch + forward)."""

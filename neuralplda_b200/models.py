@@ -189,20 +189,14 @@ class NeuralPlda(_PldaBase):
                                             self.packed, self.impl)
         return scores, flag
 
-    # The two half-steps of forward are part of the reference's public surface
-    # (models.py:366-376).  They are not on the trial-scoring hot path (forward
-    # never materialises embeddings) and are provided through the same kernels:
-    # embeddings are recovered exactly by scoring against basis probes is not
-    # possible, so they are computed by a dedicated call of the fused kernel on
-    # (x, x) pairs only when asked for.
+    # The two half-steps of forward are part of the reference's public surface (models.py:366-376).
+    # No reference call site uses them separately (forward is the hot path and never materialises
+    # embeddings); they are served by the fp32 kernels and are not differentiable here.
     def extract_plda_embeddings(self, x):
-        raise NotImplementedError(
-            "extract_plda_embeddings: the fused kernel never materialises embeddings; "
-            "use forward(x1, x2) (all reference call sites do: models.py:378-382)")
+        return F_.embed("nplda", x, self._params(), self._dims(), self.packed)
 
     def forward_from_plda_embeddings(self, x1, x2):
-        raise NotImplementedError(
-            "forward_from_plda_embeddings: use forward(x1, x2); see extract_plda_embeddings")
+        return F_.score_from_embeddings("nplda", x1, x2, self._params(), self._dims(), self.packed)
 
     def LoadPldaParamsFromKaldi(self, mean_vec_file, transform_mat_file, PldaFile):
         """models.py:441-457 without the Kaldi binaries (files parsed directly)."""
@@ -246,10 +240,10 @@ class DPlda(_PldaBase):
         return scores, flag
 
     def extract_plda_embeddings(self, x):
-        raise NotImplementedError("the fused kernel never materialises embeddings; use forward(x1, x2)")
+        return F_.embed("dplda", x, self._params(), self._dims(), self.packed)
 
     def forward_from_plda_embeddings(self, x1, x2):
-        raise NotImplementedError("use forward(x1, x2); see extract_plda_embeddings")
+        return F_.score_from_embeddings("dplda", x1, x2, self._params(), self._dims(), self.packed)
 
     def LoadParamsFromKaldi(self, mean_vec_file, transform_mat_file):
         """models.py:551-563 without the Kaldi binaries."""

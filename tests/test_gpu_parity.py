@@ -195,6 +195,34 @@ def test_indexed_matches_materialised(kaldi_params, impl):
     assert int(flag.item()) != 0
 
 
+def test_embedding_half_steps(ref_out, kaldi_params, cfg1):
+    """extract_plda_embeddings / forward_from_plda_embeddings (models.py:366-376, 478-489)."""
+    x1, x2, _ = cfg1
+    n = 777
+    kp = kaldi_params
+    m = make_nplda(kp)
+    with torch.no_grad():
+        y1 = m.extract_plda_embeddings(x1[:n].to(DEV))
+        y2 = m.extract_plda_embeddings(x2[:n].to(DEV))
+        s = m.forward_from_plda_embeddings(y1, y2)
+    ref_y = O.nplda_embed(x1[:n], kp["W1"], kp["b1"], kp["W2"], kp["b2"])
+    assert y1.shape == (n, 170)
+    np.testing.assert_allclose(y1.cpu().numpy(), ref_y.numpy(), rtol=1e-4, atol=1e-5)
+    ok, worst = parity_ok(s, torch.from_numpy(ref_out["c1_scores"][:n]), rel=1e-4)
+    assert ok, worst
+    with pytest.raises(RuntimeError):
+        m.extract_plda_embeddings(x1[:4].to(DEV))           # grad mode: not differentiable here
+    d = make_dplda(kp, ref_out)
+    nd = 300
+    with torch.no_grad():
+        u1 = d.extract_plda_embeddings(x1[:nd].to(DEV))
+        u2 = d.extract_plda_embeddings(x2[:nd].to(DEV))
+        sd = d.forward_from_plda_embeddings(u1, u2)
+    np.testing.assert_allclose(u1.cpu().numpy(), O.dplda_embed(x1[:nd], kp["W1"], kp["b1"]).numpy(), rtol=1e-4, atol=1e-6)
+    ok, worst = parity_ok(sd, torch.from_numpy(ref_out["c4_scores"][:nd]), rel=1e-4)
+    assert ok, worst
+
+
 def test_losses_match_reference(ref_out, kaldi_params, cfg1):
     _, _, t = cfg1
     s = torch.from_numpy(ref_out["c1_scores"]).to(DEV)
