@@ -79,7 +79,7 @@ struct Args {
     const uint8_t *w1img, *w2img;
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
     float *scores;
-    long long *trace;       // optional timeline buffer (env NPLDA_TC_TRACE), CTA 0 only
+    long long *trace;       // cycle-accounting buffer (env NPLDA_TC_PROF), CTA 0 only
     int dbg;                // bottleneck experiments (env NPLDA_TC_DEBUG): 1 no x loads, 2 no weight copies, 4 no MMAs
 };
 
@@ -109,10 +109,12 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
                  : "memory");
 }
 
-// timeline slots (CTA 0, tile TRACE_TILE): role * 64 + index
-constexpr int TRACE_TILE = 5;
-#define TRACE(role, idx) do { if (g.trace && blockIdx.x == 0) g.trace[(role) * 64 + (idx)] = clock64(); } while (0)
+// Cycle accounting (PROF instantiation only, env NPLDA_TC_PROF): every role keeps a running clock and
+// charges the time since the previous mark to a bucket; CTA 0 writes role * 16 + bucket at exit.
+#define PMARK(b) do { if (PROF) { const long long _t = clock64(); pacc[b] += _t - ptime; ptime = _t; } } while (0)
+#define PFLUSH(role) do { if (PROF && blockIdx.x == 0) for (int _b = 0; _b < 8; ++_b) g.trace[(role) * 16 + _b] = pacc[_b]; } while (0)
 
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -151,6 +153,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     constexpr uint32_t IDESC = make_idesc_bf16(128, NPAD);
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ptime = PROF ? clock64() : 0;
 
     if (warp < EPI_WARPS) {
         // =============================== EPILOGUE ===============================
@@ -209,11 +212,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
             const uint32_t taddr = tbase + d * NPAD;
             // ---- layer-1 accumulator: a = D + b1, |a|, bf16 hi/lo of a -> U (normalised after layer 2) ----
-            if (i == TRACE_TILE && tid == 0) TRACE(0, 0);
+            PMARK(5);
             mbar_wait(&d_full[d], par_d);
             tc_fence_after();
-            if (i == TRACE_TILE && tid == 0) TRACE(0, 1);
+            PMARK(0);
             mbar_wait(u_empty, (uint32_t)((i & 1) ^ 1));           // layer 2 of the previous tile has read U
+            PMARK(1);
             float ss[4] = {0.f, 0.f, 0.f, 0.f};
             const int cend = (g.dbg & 32) ? 0 : NPAD - 16;          // dbg 32: epilogue does (almost) no work
 #pragma unroll 1
@@ -239,11 +243,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             fence_proxy_async();      // U is read by tcgen05.mma (async proxy)
             tc_fence_before();        // our TMEM reads of D are done before Y overwrites it
             mbar_arrive(u_full);
-            if (i == TRACE_TILE && tid == 0) TRACE(0, 2);
+            PMARK(2);
             // ---- layer-2 accumulator: y = Y / |a| + b2, pair score ----
             mbar_wait(&y_full[d], par_d);
             tc_fence_after();
-            if (i == TRACE_TILE && tid == 0) TRACE(0, 3);
+            PMARK(3);
             float sc[2] = {0.f, 0.f};
 #pragma unroll 1
             for (int c0 = 0; c0 < cend; c0 += 32) {
@@ -262,13 +266,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             }
             tc_fence_before();
             mbar_arrive(&d_empty[d]);                               // D buffer free before the shuffles/store
-            if (i == TRACE_TILE && tid == 0) TRACE(0, 4);
+            PMARK(4);
             float s = sc[0] + sc[1];
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + pl;
             if (cq == 0 && pr < g.n) g.scores[pr] = s;
         }
+        if (warp == 0 && lane == 0) PFLUSH(0);
     } else if (warp < WARP_MMA) {
         // =============================== CONVERTERS ===============================
         // Two sets of 8 warps; set s handles stages it = s, s + 2, ...: one warp's chain of waits, LDS,
@@ -287,15 +292,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             // mbarrier parity waits are only unambiguous for a waiter that observes EVERY phase of a
             // barrier, so both sets wait for every stage's x_full in order and skip the other set's data.
             if ((it & 1) != cset) {
+                PMARK(5);
                 if (!(g.dbg & 1)) mbar_wait(&x_full[rx.stage], rx.phase);
+                PMARK(1);
                 continue;
             }
             const uint8_t *xs = Xs + rx.stage * X_STAGE;
-            const bool tr = (warp == EPI_WARPS || warp == EPI_WARPS + 8) && lane == 0 && it / g.nst1 == TRACE_TILE;
-            const int ts = (int)(it % g.nst1);
-            if (tr) TRACE(1, 3 * ts);
+            PMARK(5);
             if (!(g.dbg & 1)) mbar_wait(&x_full[rx.stage], rx.phase);
-            if (tr) TRACE(1, 3 * ts + 1);
+            PMARK(0);
             float4 a0, a1, b0, b1;
             if (g.dbg & 16) {                                       // dbg 16: no shared-memory reads
                 a0 = a1 = b0 = b1 = make_float4(1.f, 2.f, 3.f, (float)it);
@@ -312,8 +317,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             split_bf16x2(b0.x, b0.y, hi[2], lo[2]); split_bf16x2(b0.z, b0.w, hi[3], lo[3]);
             split_bf16x2(a1.x, a1.y, hi[4], lo[4]); split_bf16x2(a1.z, a1.w, hi[5], lo[5]);
             split_bf16x2(b1.x, b1.y, hi[6], lo[6]); split_bf16x2(b1.z, b1.w, hi[7], lo[7]);
+            if (PROF && hi[0] == 0x12345678u && lo[7] == 0x9abcdefu) g.scores[0] = 0.f;   // pin the conversion before the mark
+            PMARK(2);
             mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
             tc_fence_after();
+            PMARK(3);
             const uint32_t col = st_addr + ra.stage * A_STAGE_COLS;
             if (!(g.dbg & 8)) {                                     // dbg 8: no TMEM stores
                 tmem_st_16x256b_x2(col, hi);
@@ -330,8 +338,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[ra.stage]);
-            if (tr) TRACE(1, 3 * ts + 2);
+            PMARK(4);
         }
+        if ((warp == EPI_WARPS || warp == EPI_WARPS + CONV_WARPS) && lane == 0) PFLUSH(1 + cset);
     } else if (warp == WARP_MMA) {
         // =============================== MMA ISSUER ===============================
         // The whole warp runs this loop converged; only the tcgen05 instructions are issued by one elected
@@ -350,8 +359,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             // stage s, not after its commits.
             auto layer1 = [&](uint32_t dcol, int s_begin, int s_end) {
                 if (s_begin >= s_end) return;
+                PMARK(6);
                 mbar_wait(&a_full[ra.stage], ra.phase);
+                PMARK(1);
                 mbar_wait(&b_full[rb.stage], rb.phase);
+                PMARK(2);
                 for (int s = s_begin; s < s_end; ++s) {
                     tc_fence_after();
                     const uint32_t acol = tmem + A_COL0 + ra.stage * A_STAGE_COLS;
@@ -366,9 +378,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     Ring na = ra, nb = rb;
                     na.advance();
                     nb.advance();
+                    PMARK(3);
                     if (s + 1 < s_end) {
                         mbar_wait(&a_full[na.stage], na.phase);
+                        PMARK(1);
                         mbar_wait(&b_full[nb.stage], nb.phase);
+                        PMARK(2);
                     }
                     if (elect_one()) {
                         if (!skip_mma) {
@@ -383,6 +398,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     __syncwarp();
                     ra = na;
                     rb = nb;
+                    PMARK(3);
                 }
             };
             // Order per iteration: first half of layer 1 (tile i), layer 2 (tile i-1), second half of layer 1.
@@ -392,21 +408,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             for (int64_t i = 0; i <= T; ++i) {
                 const uint32_t dcol_i = tmem + (uint32_t)(i & 1) * NPAD;
                 cur_tile = i;
-                if (i == TRACE_TILE && lane == 0) TRACE(2, 60);
                 if (i < T) {
+                    PMARK(6);
                     mbar_wait(&d_empty[i & 1], (uint32_t)(((i >> 1) & 1) ^ 1));
                     tc_fence_after();
+                    PMARK(0);
                     layer1(dcol_i, 0, half);
                 }
                 if (i >= 1) {      // layer 2 of tile i - 1
                     const int64_t j = i - 1;
                     const int d = (int)(j & 1);
                     const uint32_t dcol = tmem + d * NPAD;
-                    if (i == TRACE_TILE && lane == 0) TRACE(2, 61);
+                    PMARK(6);
                     mbar_wait(u_full, (uint32_t)(j & 1));
                     tc_fence_after();
-                    if (i == TRACE_TILE && lane == 0) TRACE(2, 62);
+                    PMARK(4);
                     mbar_wait(&b_full[rb.stage], rb.phase);
+                    PMARK(2);
                     for (int ks = 0; ks < g.ksteps2; ks += 2) {
                         const int nst = min(2, g.ksteps2 - ks);
                         tc_fence_after();
@@ -422,7 +440,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                         __syncwarp();
                         Ring nb = rb;
                         nb.advance();
+                        PMARK(5);
                         if (ks + 2 < g.ksteps2) mbar_wait(&b_full[nb.stage], nb.phase);
+                        PMARK(2);
                         if (elect_one()) {
                             if (nst == 2 && !skip_mma) {
                                 const uint64_t bhi1 = bhi0 + (B_STEP >> 4);
@@ -441,7 +461,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                         mma_commit(u_empty);
                     }
                     __syncwarp();
-                    if (i == TRACE_TILE && lane == 0) TRACE(2, 63);
+                    PMARK(5);
                 }
                 if (i < T) {
                     layer1(dcol_i, half, g.nst1);
@@ -458,6 +478,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                 for (int k = 0; k < NBS; ++k) { mbar_wait(&b_empty[rb.stage], rb.phase ^ 1); rb.advance(); }
                 mbar_wait(u_empty, (uint32_t)((T & 1) ^ 1));
             }
+            PMARK(7);
+            if (lane == 0) PFLUSH(3);
         }
     } else if (warp == WARP_BLOAD) {
         // =============================== B LOADER ===============================
@@ -466,7 +488,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const int half = g.nst1 / 2;
             const bool skip_b = (g.dbg & 2) != 0;                  // dbg 2: arrive without copying the weights
             auto put = [&](const uint8_t *src, uint32_t bytes) {
+                PMARK(1);
                 mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
+                PMARK(0);
                 if (skip_b) {
                     mbar_arrive(&b_full[rb.stage]);
                 } else {
@@ -484,6 +508,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                 if (i < T)
                     for (int s = half; s < g.nst1; ++s) put(g.w1img + (size_t)s * B_STAGE, B_STAGE);
             }
+            PMARK(1);
+            PFLUSH(4);
         }
     } else {
         // =============================== X LOADER ===============================
@@ -492,7 +518,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             for (int64_t i = 0; i < T; ++i) {
                 const int row0 = (int)((blockIdx.x + i * gridDim.x) * TP);
                 for (int s = 0; s < g.nst1; ++s) {
+                    PMARK(1);
                     mbar_wait(&x_empty[rx.stage], rx.phase ^ 1);
+                    PMARK(0);
                     mbar_arrive_expect_tx(&x_full[rx.stage], X_STAGE);
                     uint8_t *dst = Xs + rx.stage * X_STAGE;
                     tma_load_2d(dst, &map1, s * KST, row0, &x_full[rx.stage]);      // rows past n are zero-filled
@@ -500,6 +528,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     rx.advance();
                 }
             }
+            PMARK(1);
+            PFLUSH(5);
         }
     }
 
@@ -613,25 +643,39 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
         a.dbg = e ? atoi(e) : 0;
     }
     a.trace = nullptr;
-    if (getenv("NPLDA_TC_TRACE")) {
-        NPLDA_CUDA_TRY(cudaMalloc(&a.trace, 3 * 64 * sizeof(long long)));
-        NPLDA_CUDA_TRY(cudaMemsetAsync(a.trace, 0, 3 * 64 * sizeof(long long), st));
+    const bool prof = getenv("NPLDA_TC_PROF") != nullptr;
+    if (prof) {
+        NPLDA_CUDA_TRY(cudaMalloc(&a.trace, 6 * 16 * sizeof(long long)));
+        NPLDA_CUDA_TRY(cudaMemsetAsync(a.trace, 0, 6 * 16 * sizeof(long long), st));
     }
     const int64_t ntiles = (n + tcg::TP - 1) / tcg::TP;
     const int grid = (int)std::min<int64_t>(ntiles, sm_count());
-    NPLDA_CUDA_TRY(cudaFuncSetAttribute(tcg::score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
-    tcg::score_tc_kernel<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
+    auto kern = prof ? tcg::score_tc_kernel<true> : tcg::score_tc_kernel<false>;
+    NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
+    kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
     NPLDA_LAUNCH_CHECK();
-    if (a.trace) {   // debug only: synchronises
-        long long h[3 * 64];
+    if (prof) {   // debug only: synchronises
+        long long h[6 * 16];
         NPLDA_CUDA_TRY(cudaStreamSynchronize(st));
         NPLDA_CUDA_TRY(cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(a.trace);
-        long long t0 = h[2 * 64 + 60];
-        printf("[trace] tile %d of CTA 0, cycles relative to MMA-thread iteration start\n", tcg::TRACE_TILE);
-        printf("[trace] MMA: iter_start 0, L2 wait_u start %lld done %lld, L2 issued %lld\n", h[2*64+61]-t0, h[2*64+62]-t0, h[2*64+63]-t0);
-        for (int s2 = 0; s2 < 16; ++s2) printf("[trace] MMA st %2d: wait_a start %6lld got_a %6lld issued+committed %6lld | CONV st %2d: start %6lld got_x %6lld a_full_arrive %6lld\n", s2, h[2*64+3*s2]-t0, h[2*64+3*s2+1]-t0, h[2*64+3*s2+2]-t0, s2, h[64+3*s2]-t0, h[64+3*s2+1]-t0, h[64+3*s2+2]-t0);
-        printf("[trace] EPI: wait_d start %lld got_d %lld u_full_arrive %lld got_y %lld d_empty_arrive %lld\n", h[0]-t0, h[1]-t0, h[2]-t0, h[3]-t0, h[4]-t0);
+        static const char *names[6][8] = {
+            {"wait d_full", "wait u_empty", "pass 1", "wait y_full", "pass 2", "tail+store", "", ""},
+            {"wait x_full", "wait x_full (other set)", "lds+convert", "wait a_empty", "st+st_wait+arrive", "loop", "", ""},
+            {"wait x_full", "wait x_full (other set)", "lds+convert", "wait a_empty", "st+st_wait+arrive", "loop", "", ""},
+            {"wait d_empty", "wait a_full", "wait b_full", "L1 issue+commit", "wait u_full", "L2 issue+commit", "other", "drain"},
+            {"wait b_empty", "issue", "", "", "", "", "", ""},
+            {"wait x_empty", "issue", "", "", "", "", "", ""}};
+        static const char *roles[6] = {"EPI w0", "CONV set0", "CONV set1", "MMA", "BLOAD", "XLOAD"};
+        for (int r = 0; r < 6; ++r) {
+            long long tot = 0;
+            for (int b = 0; b < 8; ++b) tot += h[r * 16 + b];
+            printf("[prof] %-9s total %9lld cyc:", roles[r], tot);
+            for (int b = 0; b < 8; ++b)
+                if (names[r][b][0]) printf("  %s %.1f%%", names[r][b], tot ? 100.0 * h[r * 16 + b] / tot : 0.0);
+            printf("\n");
+        }
+        fflush(stdout);
     }
     return NPLDA_OK;
 }
