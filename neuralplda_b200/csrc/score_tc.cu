@@ -284,8 +284,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         const int pl = q * 16 + h * 8 + rsub;                    // pair within the tile = row of both x boxes
         const uint32_t st_addr = tmem + ((uint32_t)(q * 32 + h * 16) << 16) + A_COL0;
         // 128-byte swizzle of the x boxes: 16-byte chunk c of row r sits at chunk (c ^ (r & 7))
-        const int off0 = pl * 128 + ((cq ^ rsub) << 4);          // k-step 0: chunks 0-3
-        const int off1 = pl * 128 + (((4 + cq) ^ rsub) << 4);    // k-step 1: chunks 4-7
+        // Odd rows fetch their two chunks in the opposite order: within a quarter-warp (2 rows x 4 lanes)
+        // the even row then reads bank half (rsub & 4) and the odd row the other half.  Fetching chunk
+        // cq in both rows put both on the same 16 banks (ncu: 8 instead of 4 wavefronts per LDS.128).
+        const bool odd = (rsub & 1) != 0;
+        const int offk0 = pl * 128 + ((cq ^ rsub) << 4);         // k-step 0: chunks 0-3
+        const int offk1 = pl * 128 + (((4 + cq) ^ rsub) << 4);   // k-step 1: chunks 4-7
+        const int off0 = odd ? offk1 : offk0, off1 = odd ? offk0 : offk1;
         const int64_t total = T * g.nst1;
         Ring rx(NX), ra(NA);
         for (int64_t it = 0; it < total; ++it, rx.advance(), ra.advance()) {
@@ -312,6 +317,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             }
             // registers of tcgen05.st.16x256b.x2: r0,r1 -> (row, cols 2j,2j+1)  r2,r3 -> (row+8, same cols);
             // r4..r7 the same for the next 8 columns (k + 16)
+            if (odd) { float4 t = a0; a0 = a1; a1 = t; t = b0; b0 = b1; b1 = t; }
             uint32_t hi[8], lo[8];
             split_bf16x2(a0.x, a0.y, hi[0], lo[0]); split_bf16x2(a0.z, a0.w, hi[1], lo[1]);
             split_bf16x2(b0.x, b0.y, hi[2], lo[2]); split_bf16x2(b0.z, b0.w, hi[3], lo[3]);
