@@ -35,9 +35,14 @@ extern "C" {
 #define NPLDA_ERR_NO_DEVICE (-4)      /* no sm_100 device / kernel image not loadable        */
 
 /* kernel selection for the score kernels */
-#define NPLDA_IMPL_AUTO 0   /* tcgen05 path when the shape allows, else SIMT */
+#define NPLDA_IMPL_AUTO 0   /* NPLDA_IMPL_TC when the shape allows, else SIMT */
 #define NPLDA_IMPL_SIMT 1   /* fp32 FFMA2 register-tiled kernel (any supported shape) */
-#define NPLDA_IMPL_TC 2     /* tcgen05 split-bf16 tensor-core kernel (error if shape unsupported) */
+#define NPLDA_IMPL_TC 2     /* tcgen05 kernel, both layers as split bf16 (hi*hi + lo*hi + hi*lo); error if shape unsupported */
+#define NPLDA_IMPL_TC_F8 3  /* tcgen05 kernel, layer 1 as fp16*fp16 + two e4m3*e4m3 correction products on the same
+                               accumulator (same MAC count, 2/3 of the MMA instructions).  Inputs outside the range the
+                               e4m3 terms cover (typical |x| in [2^-3, 2^8)) are detected on the device and the call is
+                               recomputed by the NPLDA_IMPL_TC kernel on the same stream, without a host round trip.
+                               Opt-in: measured no faster than NPLDA_IMPL_TC on B200. */
 
 /* loss ids, matching the reference's case-sensitive `lossfn` strings (models.py:395-399) */
 #define NPLDA_LOSS_SOFTCDET 0      /* 'SoftCdet'      */
@@ -111,6 +116,25 @@ int nplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *i
 int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *idx1,
                             const int64_t *idx2, int64_t n, int d_in, int d1, const void *pack,
                             float *scores, int32_t *bad_index_flag, int impl, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Trial-list scoring with every utterance transformed ONCE.
+ * Replaces the per-batch gather + double forward of the scoring loop
+ * (scorefile_generator.py:29-36 / 46-53 with sv_trials_loaders.py:418-437 and
+ * models.py:378-382 / 491-495) for a trial list over a device-resident x-vector
+ * table: both models' scores split as S(i,j) = r[i] + r[j] + A[i] . B[j] with
+ * per-utterance rows (NeuralPlda: A = y, B = 2 P_sqrt^2 y, r = sum Q y^2;
+ * DPlda: A = u, B = (Wb + Wb^T) u, r = u^T Ww u + ws.u + c/2).
+ * nplda_table_prepare: table [n_rows, d_in] fp32 -> rowtab (nplda_rowtab_bytes(n_rows)
+ * bytes, caller-owned); re-run when the table or the parameters change.
+ * nplda_score_pairs: scores[t] = S(idx1[t], idx2[t]); indices outside [0, n_rows)
+ * set *bad_index_flag and score 0, never a fault.  Layer widths up to 175.
+ * ------------------------------------------------------------------------- */
+int64_t nplda_rowtab_bytes(int64_t n_rows);
+int nplda_table_prepare(const float *table, int64_t n_rows, int d_in, int d1, int d2, const void *pack,
+                        int is_dplda, float *rowtab, void *stream);
+int nplda_score_pairs(const float *rowtab, int64_t n_rows, const int64_t *idx1, const int64_t *idx2,
+                      int64_t n, float *scores, int32_t *bad_index_flag, void *stream);
 
 /* ---------------------------------------------------------------------------
  * K2: loss / detection-cost accumulators.

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnplda.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8 = 0, 1, 2, 3
 LOSS_SOFTCDET, LOSS_CROSSENTROPY = 0, 1
 MAX_BETAS = 8
 
@@ -43,6 +43,9 @@ SIGNATURES = {
                                         c_vp, c_int, c_vp]),
     "dplda_score_fwd_indexed": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
                                         c_int, c_vp]),
+    "nplda_rowtab_bytes": (c_i64, [c_i64]),
+    "nplda_table_prepare": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
+    "nplda_score_pairs": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nplda_embed_fwd": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "nplda_score_from_embeddings": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "dplda_score_from_embeddings": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),

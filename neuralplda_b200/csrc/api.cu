@@ -28,10 +28,10 @@ int score_simt(bool dplda, const float *x1, const float *x2, const int64_t *i1, 
 bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed);   // score_tc.cu
 int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2,
              int64_t n_rows, int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack,
-             float *scores, cudaStream_t st);   // score_tc.cu
+             float *scores, int mode, cudaStream_t st);   // score_tc.cu
 
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
-             float *out, cudaStream_t st);   // score_simt.cu
+             float *out, int64_t ld_out, cudaStream_t st);   // score_simt.cu
 
 // S = sum_k Q y1^2 + Q y2^2 + 2 P_sqrt^2 y1 y2 from materialised embeddings (models.py:372-376): one warp per pair
 __global__ void __launch_bounds__(256) score_from_emb_kernel(const float *__restrict__ y1, const float *__restrict__ y2,
@@ -57,16 +57,18 @@ static int score_dispatch(bool dplda, const float *x1, const float *x2, const in
     if (n < 0 || !pack || (n > 0 && (!x1 || !scores))) return NPLDA_ERR_BAD_ARG;
     if (indexed && (!i1 || !i2 || !bad_flag || n_rows <= 0)) return NPLDA_ERR_BAD_ARG;
     if (!indexed && n > 0 && !x2) return NPLDA_ERR_BAD_ARG;
-    if (impl != NPLDA_IMPL_AUTO && impl != NPLDA_IMPL_SIMT && impl != NPLDA_IMPL_TC) return NPLDA_ERR_BAD_ARG;
+    if (impl != NPLDA_IMPL_AUTO && impl != NPLDA_IMPL_SIMT && impl != NPLDA_IMPL_TC && impl != NPLDA_IMPL_TC_F8)
+        return NPLDA_ERR_BAD_ARG;
     if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n == 0) return NPLDA_OK;
     PackLayout L = make_pack_layout(d_in, d1, d2);
     cudaStream_t st = (cudaStream_t)stream;
     const bool aligned = (((uintptr_t)x1 & 15) == 0) && (indexed || ((uintptr_t)x2 & 15) == 0);
     const bool tc_ok = tc_shape_ok(dplda, L, indexed) && aligned;
-    if (impl == NPLDA_IMPL_TC && !tc_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
-    if (impl == NPLDA_IMPL_TC || (impl == NPLDA_IMPL_AUTO && tc_ok))
-        return score_tc(dplda, x1, x2, i1, i2, n_rows, bad_flag, n, L, (const char *)pack, scores, st);
+    if ((impl == NPLDA_IMPL_TC || impl == NPLDA_IMPL_TC_F8) && !tc_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (impl == NPLDA_IMPL_TC || impl == NPLDA_IMPL_TC_F8 || (impl == NPLDA_IMPL_AUTO && tc_ok))
+        return score_tc(dplda, x1, x2, i1, i2, n_rows, bad_flag, n, L, (const char *)pack, scores,
+                        impl == NPLDA_IMPL_TC_F8 ? 1 : 0, st);
     return score_simt(dplda, x1, x2, i1, i2, n_rows, bad_flag, n, L, (const char *)pack, scores, st);
 }
 
@@ -123,7 +125,7 @@ extern "C" int nplda_embed_fwd(const float *x, int64_t n, int d_in, int d1, int 
     if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n == 0) return NPLDA_OK;
     PackLayout L = make_pack_layout(d_in, d1, d2);
-    return simt_aux(is_dplda ? 3 : 2, x, nullptr, n, L, (const char *)pack, emb, (cudaStream_t)stream);
+    return simt_aux(is_dplda ? 3 : 2, x, nullptr, n, L, (const char *)pack, emb, 0, (cudaStream_t)stream);
 }
 
 extern "C" int nplda_score_from_embeddings(const float *y1, const float *y2, int64_t n, int d2,
@@ -142,7 +144,7 @@ extern "C" int dplda_score_from_embeddings(const float *u1, const float *u2, int
     if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n == 0) return NPLDA_OK;
     PackLayout L = make_pack_layout(d_in, d1, d1);
-    return simt_aux(4, u1, u2, n, L, (const char *)pack, scores, (cudaStream_t)stream);
+    return simt_aux(4, u1, u2, n, L, (const char *)pack, scores, 0, (cudaStream_t)stream);
 }
 
 // ---- host-buffer entry -----------------------------------------------------------

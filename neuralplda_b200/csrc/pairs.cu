@@ -1,0 +1,146 @@
+// Trial-list scoring with every utterance transformed ONCE.
+//
+// The reference gathers [B,512] x-vector pairs per batch and pushes both sides through the two affine
+// layers again for every trial (sv_trials_loaders.py:418-437 + models.py:378-382).  A trial list over U
+// unique utterances only needs U transforms: both models' scores split into per-utterance terms plus one
+// 170-long dot product per trial,
+//     S(i, j) = r[i] + r[j] + A[i] . B[j]
+//   NeuralPlda (models.py:372-376):  y = W2 normalize(W1 x + b1) + b2,  A = y,  B = 2 P_sqrt^2 * y,  r = sum Q y^2
+//   DPlda      (models.py:483-489):  u = normalize(W1 x + b1),          A = u,  B = (Wb + Wb^T) u,
+//                                    r = u^T Ww u + ws . u + c / 2
+// nplda_table_prepare builds the row table [n_rows][2 * ROW_LD] = { A (ROW_LD floats, r stored in A[ROW_LD-1]) |
+// B (ROW_LD floats) } with the fp32 SIMT embed kernel; nplda_score_pairs streams the index pairs (16 B per
+// trial from HBM) and gathers two 704-byte rows per trial, which stay in L2 for tables up to ~80 k utterances.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace nplda {
+
+int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
+             float *out, int64_t ld_out, cudaStream_t st);   // score_simt.cu
+
+constexpr int ROW_LD = 176;              // floats per half row (width <= 175; the last float of A holds r)
+constexpr int ROW_FLOATS = 2 * ROW_LD;
+
+// one warp per utterance: B = 2 P y, r = sum Q y^2 (y already sits in the A half)
+__global__ void __launch_bounds__(256) rowtab_nplda_kernel(float *__restrict__ rowtab, int64_t n_rows, int d,
+                                                           const float *__restrict__ p, const float *__restrict__ q) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = w0; r < n_rows; r += nw) {
+        float *A = rowtab + r * ROW_FLOATS, *B = A + ROW_LD;
+        float acc = 0.f;
+        for (int k = lane; k < ROW_LD; k += 32) {
+            const float y = k < d ? A[k] : 0.f;
+            if (k >= d && k < ROW_LD - 1) A[k] = 0.f;
+            B[k] = k < d ? 2.f * p[k] * y : 0.f;
+            acc = fmaf(k < d ? q[k] : 0.f, y * y, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) A[ROW_LD - 1] = acc;
+    }
+}
+
+// one CTA per utterance: B = (Wb + Wb^T) u, r = u^T Ww u + ws . u + c / 2.  wwt[k][n] = Ww[n][k], wbt[k][n] = Wb[n][k].
+__global__ void __launch_bounds__(NP) rowtab_dplda_kernel(float *__restrict__ rowtab, int64_t n_rows, int d,
+                                                          const float *__restrict__ wwt, const float *__restrict__ wbt,
+                                                          const float *__restrict__ ws, const float *__restrict__ c) {
+    __shared__ float u[NP];
+    __shared__ float red[NP / 32];
+    const int n = threadIdx.x;
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        float *A = rowtab + r * ROW_FLOATS, *B = A + ROW_LD;
+        __syncthreads();
+        u[n] = n < d ? A[n] : 0.f;
+        __syncthreads();
+        float pm = 0.f, ww = 0.f;
+        if (n < d) {
+            for (int k = 0; k < d; ++k) {
+                pm = fmaf(wbt[(int64_t)k * NP + n] + wbt[(int64_t)n * NP + k], u[k], pm);
+                ww = fmaf(wwt[(int64_t)k * NP + n], u[k], ww);
+            }
+        }
+        float part = n < d ? u[n] * (ww + ws[n]) : 0.f;          // u_n (Ww u)_n + ws_n u_n
+        part = warp_sum(part);
+        if ((n & 31) == 0) red[n >> 5] = part;
+        if (n < ROW_LD) B[n] = n < d ? pm : 0.f;
+        if (n >= d && n < ROW_LD - 1) A[n] = 0.f;
+        __syncthreads();
+        if (n == 0) {
+            float tot = 0.5f * c[0];
+            for (int w = 0; w < NP / 32; ++w) tot += red[w];
+            A[ROW_LD - 1] = tot;
+        }
+    }
+}
+
+// one warp per trial: S = r[i] + r[j] + A[i] . B[j]; 44 float4 per half row = lanes 0..31 + lanes 0..11
+__global__ void __launch_bounds__(256) score_pairs_kernel(const float *__restrict__ rowtab, int64_t n_rows,
+                                                          const int64_t *__restrict__ i1, const int64_t *__restrict__ i2,
+                                                          int64_t n, float *__restrict__ scores, int32_t *bad_flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = w0; t < n; t += nw) {
+        int64_t a = i1[t], b = i2[t];
+        if (a < 0 || a >= n_rows || b < 0 || b >= n_rows) {       // reported, never a fault
+            if (lane == 0) { *bad_flag = 1; scores[t] = 0.f; }
+            continue;
+        }
+        const float4 *A = reinterpret_cast<const float4 *>(rowtab + a * ROW_FLOATS);
+        const float4 *B = reinterpret_cast<const float4 *>(rowtab + b * ROW_FLOATS + ROW_LD);
+        const float4 x = A[lane], y = B[lane];
+        float acc = x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        if (lane < ROW_LD / 4 - 32) {
+            float4 x2 = A[32 + lane];
+            const float4 y2 = B[32 + lane];
+            if (lane == ROW_LD / 4 - 33) x2.w = 0.f;              // A[ROW_LD - 1] is r, not part of the dot product
+            acc += x2.x * y2.x + x2.y * y2.y + x2.z * y2.z + x2.w * y2.w;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) scores[t] = acc + rowtab[a * ROW_FLOATS + ROW_LD - 1] + rowtab[b * ROW_FLOATS + ROW_LD - 1];
+    }
+}
+
+}  // namespace nplda
+
+using namespace nplda;
+
+extern "C" int64_t nplda_rowtab_bytes(int64_t n_rows) {
+    if (n_rows < 0) return NPLDA_ERR_BAD_ARG;
+    return n_rows * ROW_FLOATS * (int64_t)sizeof(float);
+}
+
+extern "C" int nplda_table_prepare(const float *table, int64_t n_rows, int d_in, int d1, int d2, const void *pack,
+                                   int is_dplda, float *rowtab, void *stream) {
+    if (n_rows < 0 || !pack || (n_rows > 0 && (!table || !rowtab))) return NPLDA_ERR_BAD_ARG;
+    if (is_dplda) d2 = d1;
+    if (!dims_supported(d_in, d1, d2) || d1 >= ROW_LD || d2 >= ROW_LD) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n_rows == 0) return NPLDA_OK;
+    PackLayout L = make_pack_layout(d_in, d1, d2);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char *pk = (const char *)pack;
+    int rc = simt_aux(is_dplda ? 3 : 2, table, nullptr, n_rows, L, pk, rowtab, ROW_FLOATS, st);
+    if (rc != NPLDA_OK) return rc;
+    if (is_dplda) {
+        const int grid = (int)std::min<int64_t>(n_rows, 8 * (int64_t)sm_count());
+        rowtab_dplda_kernel<<<grid, NP, 0, st>>>(rowtab, n_rows, d1, (const float *)(pk + L.w2t), (const float *)(pk + L.w3t),
+                                                 (const float *)(pk + L.b2), (const float *)(pk + L.c));
+    } else {
+        const int grid = (int)std::min<int64_t>((n_rows + 7) / 8, 8 * (int64_t)sm_count());
+        rowtab_nplda_kernel<<<grid, 256, 0, st>>>(rowtab, n_rows, d2, (const float *)(pk + L.p), (const float *)(pk + L.q));
+    }
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
+}
+
+extern "C" int nplda_score_pairs(const float *rowtab, int64_t n_rows, const int64_t *idx1, const int64_t *idx2, int64_t n,
+                                 float *scores, int32_t *bad_index_flag, void *stream) {
+    if (n < 0 || n_rows < 0 || (n > 0 && (!rowtab || !idx1 || !idx2 || !scores || !bad_index_flag))) return NPLDA_ERR_BAD_ARG;
+    if (n == 0) return NPLDA_OK;
+    if (n_rows == 0) return NPLDA_ERR_BAD_ARG;
+    const int grid = (int)std::min<int64_t>((n + 7) / 8, 16 * (int64_t)sm_count());
+    score_pairs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rowtab, n_rows, idx1, idx2, n, scores, bad_index_flag);
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
+}

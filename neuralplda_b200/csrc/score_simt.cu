@@ -25,6 +25,7 @@ struct Args {
     int32_t *bad_flag;
     int64_t n;
     int d_in, k1p, k2p, d_out;     // d_out: embedding width written by the embed modes
+    int64_t ld_out;                // row stride of the embedding output (floats)
     const float *w1t, *b1, *w2t, *w3t, *b2, *p, *q, *c;
     float *scores;
 };
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_kernel(Args g) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             int c = 4 * tx + 64 * j + e;
-                            if (row < g.n && c < g.d_out) g.scores[row * g.d_out + c] = uv[e];
+                            if (row < g.n && c < g.d_out) g.scores[row * g.ld_out + c] = uv[e];
                         }
                     }
                 }
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_kernel(Args g) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         int c = 4 * tx + 64 * j + e;
-                        if (row < g.n && c < g.d_out) g.scores[row * g.d_out + c] = yv[e] + bv[e];
+                        if (row < g.n && c < g.d_out) g.scores[row * g.ld_out + c] = yv[e] + bv[e];
                     }
                 }
             }
@@ -265,14 +266,14 @@ int score_simt(bool dplda, const float *x1, const float *x2, const int64_t *i1, 
     a.scores = scores;
     const bool indexed = i1 != nullptr;
     bool vec = (L.d_in % 4 == 0) && (((uintptr_t)x1 & 15) == 0) && (indexed || ((uintptr_t)x2 & 15) == 0);
-    a.d_out = 0;
+    a.d_out = 0; a.ld_out = 0;
     if (dplda) return indexed ? simt::launch<1, true>(a, vec, st) : simt::launch<1, false>(a, vec, st);
     return indexed ? simt::launch<0, true>(a, vec, st) : simt::launch<0, false>(a, vec, st);
 }
 
 // mode 2: NeuralPlda embeddings, 3: DPlda embeddings, 4: DPlda score from embeddings (x1, x2 = u rows)
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
-             float *out, cudaStream_t st) {
+             float *out, int64_t ld_out, cudaStream_t st) {
     simt::Args a;
     a.x1 = x1; a.x2 = x2 ? x2 : x1; a.i1 = a.i2 = nullptr; a.n_rows = 0; a.bad_flag = nullptr;
     a.n = n; a.d_in = mode == 4 ? L.d1 : L.d_in; a.k1p = L.k1p; a.k2p = L.k2p;
@@ -282,6 +283,7 @@ int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLa
     a.q = (const float *)(pack + L.q); a.c = (const float *)(pack + L.c);
     a.scores = out;
     a.d_out = mode == 2 ? L.d2 : L.d1;
+    a.ld_out = ld_out > 0 ? ld_out : a.d_out;
     bool vec = (a.d_in % 4 == 0) && (((uintptr_t)x1 & 15) == 0) && (((uintptr_t)a.x2 & 15) == 0);
     if (mode == 2) return simt::launch<2, false>(a, vec, st);
     if (mode == 3) return simt::launch<3, false>(a, vec, st);

@@ -27,10 +27,14 @@
 //                         linear layer 2).  Pass 2: y = Y/|a| + b2, S = sum Q y1^2 + Q y2^2 + 2 P y1 y2,
 //                         two shuffles per pair, one 4-byte store per pair.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -76,8 +80,12 @@ struct Args {
     int64_t n;
     int nst1;               // layer-1 stages  = d_in / 32
     int ksteps2;            // layer-2 K steps = round_up(d1, 16) / 16
-    const uint8_t *w1img, *w2img;
+    const uint8_t *w1img, *w2img;   // MODE 1: w1img is the fp16 + 2 x e4m3 image
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
+    const float *hdr;       // MODE 1: hdr[0] = 2^-(9 + gw), the scale that undoes the weight pre-scaling
+    int *guard;             // MODE 1: guard[0] set when an input leaves the range the e4m3 terms cover; MODE 0 with
+                            //         guard != nullptr: run only if guard[0] is set (fallback pass), then clear it
+
     float *scores;
     long long *trace;       // cycle-accounting buffer (env NPLDA_TC_PROF), CTA 0 only
     int dbg;                // bottleneck experiments (env NPLDA_TC_DEBUG): 1 no x loads, 2 no weight copies, 4 no MMAs
@@ -102,6 +110,40 @@ __device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_
                  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st_16x256b_x1(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+// kind::f8f6f4 with the A operand in tensor memory (four e4m3 per 32-bit cell), K = 32 per instruction
+__device__ __forceinline__ void mma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D fp32, A/B format code fa/fb (kind::f16: 0 = fp16, 1 = bf16; kind::f8f6f4: 0 = e4m3), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_fmt(int fa, int fb, int M, int N) {
+    return (1u << 4) | ((uint32_t)fa << 7) | ((uint32_t)fb << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MODE 1 split of one fp32 value: hi = v rounded to 11 significant bits (exactly representable in fp16
+// inside its normal range), l9 = (v - hi) * 2^9 for the e4m3 correction operand.
+__device__ __forceinline__ void split_f16(float v, float &hi, float &l9) {
+    hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    l9 = (v - hi) * 512.f;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {   // a -> low half
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {   // a -> byte 0
+    uint32_t lo, hi;
+    asm("{\n.reg .b16 t;\ncvt.rn.satfinite.e4m3x2.f32 t, %1, %2;\ncvt.u32.u16 %0, t;\n}\n" : "=r"(lo) : "f"(b), "f"(a));
+    asm("{\n.reg .b16 t;\ncvt.rn.satfinite.e4m3x2.f32 t, %1, %2;\ncvt.u32.u16 %0, t;\n}\n" : "=r"(hi) : "f"(d), "f"(c));
+    return lo | (hi << 16);
+}
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -114,7 +156,14 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
 #define PMARK(b) do { if (PROF) { const long long _t = clock64(); pacc[b] += _t - ptime; ptime = _t; } } while (0)
 #define PFLUSH(role) do { if (PROF && blockIdx.x == 0) for (int _b = 0; _b < 8; ++_b) g.trace[(role) * 16 + _b] = pacc[_b]; } while (0)
 
-template <bool PROF>
+// MODE 0: bf16x3 (both layers).  MODE 1: layer 1 as fp16 x fp16 + e4m3 x e4m3 + e4m3 x e4m3 (see the pack
+// kernel for the scaling), layer 2 bf16x3.
+// Waits of the roles off the critical path.  Measured on B200: neither the suspend-time hint of try_wait nor a
+// nanosleep back-off between polls changes the issued-instruction count or the kernel time (a try_wait that
+// fails already parks the warp for ~60 cycles), so these are plain polling waits.
+#define WAIT_OFFPATH(bar, par) mbar_wait(bar, par)
+
+template <bool PROF, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -132,7 +181,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (g.n + TP - 1) / TP;
-    const int64_t T = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    int64_t T = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (MODE == 0 && g.guard != nullptr && *reinterpret_cast<volatile int *>(g.guard) == 0) T = 0;   // fallback pass not needed
 
     // ---- one-time setup ----
     for (int i = tid; i < NPAD; i += NTHREADS) {
@@ -153,6 +203,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     constexpr uint32_t IDESC = make_idesc_bf16(128, NPAD);
+    constexpr uint32_t IDESC_F16 = make_idesc_fmt(0, 0, 128, NPAD), IDESC_E4M3 = make_idesc_fmt(0, 0, 128, NPAD);
+    const float s1 = MODE == 1 ? g.hdr[0] : 1.f;
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ptime = PROF ? clock64() : 0;
 
     if (warp < EPI_WARPS) {
@@ -171,10 +223,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
 
         auto pass1 = [&](const uint32_t (&v)[8], int c0, float (&ss)[4]) {
             const float2 ba = b1s[(c0 >> 1) + cq], bb = b1s[(c0 >> 1) + 4 + cq];
-            const float a00 = __uint_as_float(v[0]) + ba.x, a01 = __uint_as_float(v[1]) + ba.y;
-            const float a10 = __uint_as_float(v[2]) + ba.x, a11 = __uint_as_float(v[3]) + ba.y;
-            const float a02 = __uint_as_float(v[4]) + bb.x, a03 = __uint_as_float(v[5]) + bb.y;
-            const float a12 = __uint_as_float(v[6]) + bb.x, a13 = __uint_as_float(v[7]) + bb.y;
+            const float a00 = fmaf(__uint_as_float(v[0]), s1, ba.x), a01 = fmaf(__uint_as_float(v[1]), s1, ba.y);
+            const float a10 = fmaf(__uint_as_float(v[2]), s1, ba.x), a11 = fmaf(__uint_as_float(v[3]), s1, ba.y);
+            const float a02 = fmaf(__uint_as_float(v[4]), s1, bb.x), a03 = fmaf(__uint_as_float(v[5]), s1, bb.y);
+            const float a12 = fmaf(__uint_as_float(v[6]), s1, bb.x), a13 = fmaf(__uint_as_float(v[7]), s1, bb.y);
             ss[0] = fmaf(a00, a00, ss[0]); ss[1] = fmaf(a01, a01, ss[1]);
             ss[0] = fmaf(a02, a02, ss[0]); ss[1] = fmaf(a03, a03, ss[1]);
             ss[2] = fmaf(a10, a10, ss[2]); ss[3] = fmaf(a11, a11, ss[3]);
@@ -213,10 +265,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const uint32_t taddr = tbase + d * NPAD;
             // ---- layer-1 accumulator: a = D + b1, |a|, bf16 hi/lo of a -> U (normalised after layer 2) ----
             PMARK(5);
-            mbar_wait(&d_full[d], par_d);
+            WAIT_OFFPATH(&d_full[d], par_d);
             tc_fence_after();
             PMARK(0);
-            mbar_wait(u_empty, (uint32_t)((i & 1) ^ 1));           // layer 2 of the previous tile has read U
+            WAIT_OFFPATH(u_empty, (uint32_t)((i & 1) ^ 1));        // layer 2 of the previous tile has read U
             PMARK(1);
             float ss[4] = {0.f, 0.f, 0.f, 0.f};
             const int cend = (g.dbg & 32) ? 0 : NPAD - 16;          // dbg 32: epilogue does (almost) no work
@@ -245,7 +297,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             mbar_arrive(u_full);
             PMARK(2);
             // ---- layer-2 accumulator: y = Y / |a| + b2, pair score ----
-            mbar_wait(&y_full[d], par_d);
+            WAIT_OFFPATH(&y_full[d], par_d);
             tc_fence_after();
             PMARK(3);
             float sc[2] = {0.f, 0.f};
@@ -293,18 +345,32 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         const int off0 = odd ? offk1 : offk0, off1 = odd ? offk0 : offk1;
         const int64_t total = T * g.nst1;
         Ring rx(NX), ra(NA);
+        float amax = 0.f;       // MODE 1 range guard: largest |x| this thread saw in the current tile
+        int stage_in_tile = 0;
+        int64_t tile_i = 0;
         for (int64_t it = 0; it < total; ++it, rx.advance(), ra.advance()) {
+            // MODE 1 range guard, evaluated after the last stage of every tile: both converter sets count
+            // stages and each checks the values it converted (its pair's two rows, 8 columns of every other
+            // stage).  The e4m3 terms need typical |x| in about [2^-3, 2^8); outside that, the call is flagged and
+            // the bf16x3 pass that follows on the stream recomputes it.
+            const bool tile_end = MODE == 1 && ++stage_in_tile == g.nst1;
+            auto guard_check = [&]() {
+                const int64_t pr = (blockIdx.x + tile_i * gridDim.x) * TP + pl;
+                if (pr < g.n && (amax < 0.25f || amax >= 256.f)) *reinterpret_cast<volatile int *>(g.guard) = 1;
+                amax = 0.f; stage_in_tile = 0; ++tile_i;
+            };
             // mbarrier parity waits are only unambiguous for a waiter that observes EVERY phase of a
             // barrier, so both sets wait for every stage's x_full in order and skip the other set's data.
             if ((it & 1) != cset) {
                 PMARK(5);
-                if (!(g.dbg & 1)) mbar_wait(&x_full[rx.stage], rx.phase);
+                if (!(g.dbg & 1)) WAIT_OFFPATH(&x_full[rx.stage], rx.phase);
                 PMARK(1);
+                if (tile_end) guard_check();
                 continue;
             }
             const uint8_t *xs = Xs + rx.stage * X_STAGE;
             PMARK(5);
-            if (!(g.dbg & 1)) mbar_wait(&x_full[rx.stage], rx.phase);
+            if (!(g.dbg & 1)) WAIT_OFFPATH(&x_full[rx.stage], rx.phase);
             PMARK(0);
             float4 a0, a1, b0, b1;
             if (g.dbg & 16) {                                       // dbg 16: no shared-memory reads
@@ -319,19 +385,43 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             // r4..r7 the same for the next 8 columns (k + 16)
             if (odd) { float4 t = a0; a0 = a1; a1 = t; t = b0; b0 = b1; b1 = t; }
             uint32_t hi[8], lo[8];
-            split_bf16x2(a0.x, a0.y, hi[0], lo[0]); split_bf16x2(a0.z, a0.w, hi[1], lo[1]);
-            split_bf16x2(b0.x, b0.y, hi[2], lo[2]); split_bf16x2(b0.z, b0.w, hi[3], lo[3]);
-            split_bf16x2(a1.x, a1.y, hi[4], lo[4]); split_bf16x2(a1.z, a1.w, hi[5], lo[5]);
-            split_bf16x2(b1.x, b1.y, hi[6], lo[6]); split_bf16x2(b1.z, b1.w, hi[7], lo[7]);
+            if (MODE == 1) {
+                // hi[0..7]: fp16 of x (same register layout as the bf16 path); lo[0..3]: e4m3 of (x - hi) * 2^9,
+                // lo[4..7]: e4m3 of x.  One e4m3 register = K slots 8 cq + {0..3} (k-step 0 chunk) or + {4..7}
+                // (k-step 1 chunk): the weight image uses the same slot permutation.
+                const float v[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float h[16], l[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { split_f16(v[j], h[j], l[j]); amax = fmaxf(amax, fabsf(v[j])); }
+                hi[0] = pack_f16x2(h[0], h[1]); hi[1] = pack_f16x2(h[2], h[3]);       // side 0, k-step 0
+                hi[2] = pack_f16x2(h[8], h[9]); hi[3] = pack_f16x2(h[10], h[11]);     // side 1, k-step 0
+                hi[4] = pack_f16x2(h[4], h[5]); hi[5] = pack_f16x2(h[6], h[7]);       // side 0, k-step 1
+                hi[6] = pack_f16x2(h[12], h[13]); hi[7] = pack_f16x2(h[14], h[15]);   // side 1, k-step 1
+                lo[0] = pack_e4m3x4(l[0], l[1], l[2], l[3]); lo[1] = pack_e4m3x4(l[4], l[5], l[6], l[7]);
+                lo[2] = pack_e4m3x4(l[8], l[9], l[10], l[11]); lo[3] = pack_e4m3x4(l[12], l[13], l[14], l[15]);
+                lo[4] = pack_e4m3x4(v[0], v[1], v[2], v[3]); lo[5] = pack_e4m3x4(v[4], v[5], v[6], v[7]);
+                lo[6] = pack_e4m3x4(v[8], v[9], v[10], v[11]); lo[7] = pack_e4m3x4(v[12], v[13], v[14], v[15]);
+            } else {
+                split_bf16x2(a0.x, a0.y, hi[0], lo[0]); split_bf16x2(a0.z, a0.w, hi[1], lo[1]);
+                split_bf16x2(b0.x, b0.y, hi[2], lo[2]); split_bf16x2(b0.z, b0.w, hi[3], lo[3]);
+                split_bf16x2(a1.x, a1.y, hi[4], lo[4]); split_bf16x2(a1.z, a1.w, hi[5], lo[5]);
+                split_bf16x2(b1.x, b1.y, hi[6], lo[6]); split_bf16x2(b1.z, b1.w, hi[7], lo[7]);
+            }
             if (PROF && hi[0] == 0x12345678u && lo[7] == 0x9abcdefu) g.scores[0] = 0.f;   // pin the conversion before the mark
             PMARK(2);
-            mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
+            WAIT_OFFPATH(&a_empty[ra.stage], ra.phase ^ 1);
             tc_fence_after();
             PMARK(3);
             const uint32_t col = st_addr + ra.stage * A_STAGE_COLS;
             if (!(g.dbg & 8)) {                                     // dbg 8: no TMEM stores
                 tmem_st_16x256b_x2(col, hi);
-                tmem_st_16x256b_x2(col + 16, lo);
+                if (MODE == 1) {
+                    const uint32_t e0[4] = {lo[0], lo[1], lo[2], lo[3]}, e1[4] = {lo[4], lo[5], lo[6], lo[7]};
+                    tmem_st_16x256b_x1(col + 16, e0);
+                    tmem_st_16x256b_x1(col + 24, e1);
+                } else {
+                    tmem_st_16x256b_x2(col + 16, lo);
+                }
             } else if (hi[0] == 0x12345678u && lo[7] == 0x9abcdefu) {
                 g.scores[0] = 0.f;                                  // keep the conversion alive
             }
@@ -344,6 +434,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[ra.stage]);
+            if (tile_end) guard_check();
             PMARK(4);
         }
         if ((warp == EPI_WARPS || warp == EPI_WARPS + CONV_WARPS) && lane == 0) PFLUSH(1 + cset);
@@ -376,9 +467,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     const uint32_t bs = b_base + rb.stage * B_STAGE;
                     const uint64_t bhi0 = make_smem_desc(bs, KCH_B, 128);
                     if (elect_one() && !skip_mma) {
-                        mma_ts(dcol, acol, bhi0, IDESC, s != 0);
-                        mma_ts(dcol, acol + 16, bhi0, IDESC, 1);
-                        mma_ts(dcol, acol, bhi0 + ((2 * KCH_B) >> 4), IDESC, 1);
+                        if (MODE == 1) {        // fp16 x fp16, K steps 0 and 1
+                            mma_ts(dcol, acol, bhi0, IDESC_F16, s != 0);
+                            mma_ts(dcol, acol + 8, bhi0 + ((2 * KCH_B) >> 4), IDESC_F16, 1);
+                        } else {
+                            mma_ts(dcol, acol, bhi0, IDESC, s != 0);
+                            mma_ts(dcol, acol + 16, bhi0, IDESC, 1);
+                            mma_ts(dcol, acol, bhi0 + ((2 * KCH_B) >> 4), IDESC, 1);
+                        }
                     }
                     __syncwarp();
                     Ring na = ra, nb = rb;
@@ -394,9 +490,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     if (elect_one()) {
                         if (!skip_mma) {
                             const uint64_t bhi1 = bhi0 + (B_STEP >> 4);
-                            mma_ts(dcol, acol + 8, bhi1, IDESC, 1);
-                            mma_ts(dcol, acol + 24, bhi1, IDESC, 1);
-                            mma_ts(dcol, acol + 8, bhi1 + ((2 * KCH_B) >> 4), IDESC, 1);
+                            if (MODE == 1) {    // e4m3((x - hi) 2^9) x e4m3(Wh 2^-9)  and  e4m3(x) x e4m3(Wl), K = 32 each
+                                mma_f8_ts(dcol, acol + 16, bhi1, IDESC_E4M3, 1);
+                                mma_f8_ts(dcol, acol + 24, bhi1 + ((2 * KCH_B) >> 4), IDESC_E4M3, 1);
+                            } else {
+                                mma_ts(dcol, acol + 8, bhi1, IDESC, 1);
+                                mma_ts(dcol, acol + 24, bhi1, IDESC, 1);
+                                mma_ts(dcol, acol + 8, bhi1 + ((2 * KCH_B) >> 4), IDESC, 1);
+                            }
                         }
                         mma_commit(&a_empty[ra.stage]);
                         mma_commit(&b_empty[rb.stage]);
@@ -493,17 +594,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             Ring rb(NBS);
             const int half = g.nst1 / 2;
             const bool skip_b = (g.dbg & 2) != 0;                  // dbg 2: arrive without copying the weights
+            int nput = 0;
             auto put = [&](const uint8_t *src, uint32_t bytes) {
                 PMARK(1);
-                mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
+                WAIT_OFFPATH(&b_empty[rb.stage], rb.phase ^ 1);
                 PMARK(0);
-                if (skip_b) {
+                if (skip_b && nput >= NBS) {              // the ring keeps the real weights of its first NBS stages
                     mbar_arrive(&b_full[rb.stage]);
                 } else {
                     mbar_arrive_expect_tx(&b_full[rb.stage], bytes);
                     bulk_g2s(Bs + rb.stage * B_STAGE, src, bytes, &b_full[rb.stage]);
                 }
                 rb.advance();
+                ++nput;
             };
             for (int64_t i = 0; i <= T; ++i) {
                 if (i < T)
@@ -525,7 +628,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                 const int row0 = (int)((blockIdx.x + i * gridDim.x) * TP);
                 for (int s = 0; s < g.nst1; ++s) {
                     PMARK(1);
-                    mbar_wait(&x_empty[rx.stage], rx.phase ^ 1);
+                    WAIT_OFFPATH(&x_empty[rx.stage], rx.phase ^ 1);
                     PMARK(0);
                     mbar_arrive_expect_tx(&x_full[rx.stage], X_STAGE);
                     uint8_t *dst = Xs + rx.stage * X_STAGE;
@@ -543,6 +646,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == WARP_MMA) tmem_dealloc(tmem, 512);
+    if (MODE == 0 && g.guard != nullptr && T > 0 && tid == 0) {
+        // fallback pass: every CTA read guard[0] when it started; the last one to finish clears the slot
+        __threadfence();
+        if (atomicAdd(g.guard + 1, 1) == (int)min((int64_t)gridDim.x, ntiles) - 1) { g.guard[1] = 0; g.guard[0] = 0; }
+    }
 }
 
 // ---- weight images --------------------------------------------------------------------------
@@ -568,6 +676,62 @@ __global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ks
 }
 
 static int64_t image_bytes(int ksteps) { return (int64_t)ksteps * B_STEP; }
+
+// ---- MODE 1 weight image (layer 1) ------------------------------------------------------------
+// With gw chosen so that max|W| 2^gw is in [32, 64):  W' = W 2^(gw+9) = Wh + Wl, Wh = fp16(W') (|Wh| < 2^15).
+//   x W' = xh Wh + (xl 2^9)(Wh 2^-9) + xh Wl + O(2^-22),   xh = fp16(x), xl = x - xh
+// The first product runs as kind::f16, the other two as kind::f8f6f4 with every operand in e4m3:
+// |xl 2^9| <= |x| / 4, |Wh 2^-9| < 64, |Wl| <= 2^-11 |W'| < 16.  The accumulator holds x W 2^(gw+9); the epilogue
+// multiplies by hdr[0] = 2^-(gw+9).
+// Stage s (K = [32 s, 32 s + 32)) of the image, 8 chunks of 22 core matrices (KCH_B bytes each):
+//   [fp16 k 0-7][fp16 k 8-15][fp16 k 16-23][fp16 k 24-31][e4m3 Wh 2^-9 slots 0-15][slots 16-31][e4m3 Wl slots 0-15][slots 16-31]
+// e4m3 slot t holds k = 4 (t >> 3) + (t & 3) + 16 ((t >> 2) & 1): the order in which a converter thread's two
+// 16-byte loads land in one tcgen05.st.16x256b register pair.
+__global__ void tc_absmax_kernel(const float *__restrict__ W, int64_t count, float *__restrict__ hdr) {
+    __shared__ float red[32];
+    float m = 0.f;
+    for (int64_t e = threadIdx.x; e < count; e += blockDim.x) m = fmaxf(m, fabsf(W[e]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+        int gw = 0;
+        if (m > 0.f && m < 3.0e38f) {
+            int e;
+            frexpf(m, &e);          // m = f 2^e, f in [0.5, 1)  ->  m 2^(6 - e) in [32, 64)
+            gw = 6 - e;
+        }
+        gw = max(-100, min(100, gw));
+        hdr[0] = exp2f((float)-(gw + 9));   // epilogue scale
+        hdr[1] = exp2f((float)(gw + 9));    // W -> W'
+    }
+}
+
+__global__ void tc_pack_mixed_kernel(const float *__restrict__ W, int N, int K, int nstages, const float *__restrict__ hdr,
+                                     uint8_t *__restrict__ img) {
+    const float up = hdr[1];
+    const int64_t total = (int64_t)nstages * NPAD * 32;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(e & 31);
+        const int n = (int)((e >> 5) % NPAD);
+        const int s = (int)((e >> 5) / NPAD);
+        const int k = s * 32 + kk;
+        const float w = (n < N && k < K) ? W[(int64_t)n * K + k] * up : 0.f;
+        const __half wh = __float2half_rn(w);
+        const float whf = __half2float(wh);
+        uint8_t *st = img + (size_t)s * B_STAGE;
+        const size_t row = (size_t)(n >> 3) * 128 + (n & 7) * 16;
+        *reinterpret_cast<__half *>(st + (size_t)(kk >> 3) * KCH_B + row + (kk & 7) * 2) = wh;
+        // slot of k within the stage: inverse of k = 4 (t >> 3) + (t & 3) + 16 ((t >> 2) & 1)
+        const int t = ((kk & 15) >> 2) * 8 + ((kk >> 4) & 1) * 4 + (kk & 3);
+        const size_t off8 = (size_t)(t >> 4) * KCH_B + row + (t & 15);
+        st[4 * KCH_B + off8] = (uint8_t)__nv_cvt_float_to_fp8(whf * (1.f / 512.f), __NV_SATFINITE, __NV_E4M3);
+        st[6 * KCH_B + off8] = (uint8_t)__nv_cvt_float_to_fp8(w - whf, __NV_SATFINITE, __NV_E4M3);
+    }
+}
+static int64_t mixed_image_bytes(int d_in) { return (int64_t)(d_in / KST) * B_STAGE; }
+constexpr int HDR_BYTES = 256;
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -604,7 +768,8 @@ static bool tc_dims_ok(int d_in, int d1, int d2) {
 
 int64_t tc_image_bytes(int d_in, int d1, int d2) {
     if (!tc_dims_ok(d_in, d1, d2)) return 0;
-    return tcg::image_bytes(d_in / 16) + tcg::image_bytes(round_up(d1, 16) / 16) + 512;
+    return tcg::image_bytes(d_in / 16) + tcg::image_bytes(round_up(d1, 16) / 16) + 512 + tcg::mixed_image_bytes(d_in) +
+           tcg::HDR_BYTES + 256;
 }
 
 bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed) {
@@ -621,6 +786,12 @@ int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float
     NPLDA_LAUNCH_CHECK();
     tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(W2, L.d2, L.d1, round_up(L.d1, 16) / 16, img2);
     NPLDA_LAUNCH_CHECK();
+    uint8_t *img1m = img2 + (tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256;
+    float *hdr = (float *)(img1m + tcg::mixed_image_bytes(L.d_in));
+    tcg::tc_absmax_kernel<<<1, 1024, 0, st>>>(W1, (int64_t)L.d1 * L.d_in, hdr);
+    NPLDA_LAUNCH_CHECK();
+    tcg::tc_pack_mixed_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / tcg::KST, hdr, img1m);
+    NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }
 
@@ -629,8 +800,41 @@ int tc_pack_dplda(const float *, const float *, const float *, const float *, co
     return NPLDA_OK;   // DPlda scores run on the SIMT kernel (tc_shape_ok is false for it)
 }
 
+// Range-guard slots of the mixed-precision path: a per-device ring of {flag, counter} pairs in device memory,
+// allocated on first use (the one allocation this library keeps; 8 KB).  A call takes the next slot, the
+// mixed kernel raises slot[0] when an input is out of range, the bf16x3 pass that follows on the same stream
+// runs only if it is raised and clears it.  Slots are zero between calls.
+static int *guard_slot() {
+    static int *ring[64] = {nullptr};
+    static std::atomic<unsigned> ticket{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ring[dev]) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ring[dev]) {
+            int *p = nullptr;
+            if (cudaMalloc(&p, 1024 * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+            if (cudaMemset(p, 0, 1024 * 2 * sizeof(int)) != cudaSuccess) { cudaFree(p); return nullptr; }
+            ring[dev] = p;
+        }
+    }
+    return ring[dev] + 2 * (ticket.fetch_add(1, std::memory_order_relaxed) & 1023u);
+}
+
+template <bool PROF, int MODE>
+static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Args &a, int grid, cudaStream_t st) {
+    auto kern = tcg::score_tc_kernel<PROF, MODE>;
+    NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
+    kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
+}
+
+// mode 0: bf16x3 kernel.  mode 1: fp16 + 2 x e4m3 kernel for layer 1, then the bf16x3 kernel as a guarded
+// fallback pass (a no-op launch unless the range guard fired).
 int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2, int64_t n_rows,
-             int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack, float *scores, cudaStream_t st) {
+             int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack, float *scores, int mode, cudaStream_t st) {
     (void)i2; (void)n_rows; (void)bad_flag;
     if (dplda || i1 || !tc_dims_ok(L.d_in, L.d1, L.d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n >= (int64_t)1 << 31) return NPLDA_ERR_UNSUPPORTED_DIM;   // TMA row coordinates are int32
@@ -639,14 +843,20 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
     tcg::Args a;
     a.x1 = x1; a.x2 = x2; a.n = n;
     a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
-    a.w1img = (const uint8_t *)pack + L.tc;
-    a.w2img = a.w1img + (tcg::image_bytes(L.d_in / 16) + 255) / 256 * 256;
+    const uint8_t *img1 = (const uint8_t *)pack + L.tc;
+    const uint8_t *img2 = img1 + (tcg::image_bytes(L.d_in / 16) + 255) / 256 * 256;
+    const uint8_t *img1m = img2 + (tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256;
+    a.w1img = img1; a.w2img = img2;
+    a.hdr = (const float *)(img1m + tcg::mixed_image_bytes(L.d_in));
+    a.guard = nullptr;
     a.b1 = (const float *)(pack + L.b1); a.b2 = (const float *)(pack + L.b2);
     a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.q);
     a.scores = scores;
     {
         const char *e = getenv("NPLDA_TC_DEBUG");
         a.dbg = e ? atoi(e) : 0;
+        const char *m = getenv("NPLDA_TC_MODE");       // experiments: force 0 (bf16x3) or 1 (mixed)
+        if (m) mode = atoi(m) != 0;
     }
     a.trace = nullptr;
     const bool prof = getenv("NPLDA_TC_PROF") != nullptr;
@@ -656,10 +866,22 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
     }
     const int64_t ntiles = (n + tcg::TP - 1) / tcg::TP;
     const int grid = (int)std::min<int64_t>(ntiles, sm_count());
-    auto kern = prof ? tcg::score_tc_kernel<true> : tcg::score_tc_kernel<false>;
-    NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
-    kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
-    NPLDA_LAUNCH_CHECK();
+    int rc;
+    if (mode == 1) {
+        int *slot = guard_slot();
+        if (!slot) return NPLDA_ERR_NO_DEVICE;
+        tcg::Args am = a;
+        am.w1img = img1m; am.guard = slot;
+        rc = prof ? launch_tc<true, 1>(m1, m2, am, grid, st) : launch_tc<false, 1>(m1, m2, am, grid, st);
+        if (rc != NPLDA_OK) return rc;
+        a.guard = slot;
+        tcg::Args af = a;
+        af.trace = nullptr;
+        rc = launch_tc<false, 0>(m1, m2, af, grid, st);
+    } else {
+        rc = prof ? launch_tc<true, 0>(m1, m2, a, grid, st) : launch_tc<false, 0>(m1, m2, a, grid, st);
+    }
+    if (rc != NPLDA_OK) return rc;
     if (prof) {   // debug only: synchronises
         long long h[6 * 16];
         NPLDA_CUDA_TRY(cudaStreamSynchronize(st));

@@ -47,7 +47,30 @@ class PackedWeights:
                                                   self.buf.numel(), stream_ptr())
             check(rc, "pack_weights")
             self.key = key
+            self.rowtab_key = None          # per-utterance rows depend on the parameters
         return self.buf
+
+    rowtab = None
+    rowtab_key = None
+
+    def rowtab_valid(self, table):
+        return self.rowtab_key == (table.data_ptr(), table._version, tuple(table.shape), self.key)
+
+    def get_rowtab(self, kind, table, params, d_in, d1, d2):
+        """Per-utterance score operands of `table` (nplda_table_prepare), rebuilt only when the table or a
+        parameter changed."""
+        pack = self.get(kind, params, d_in, d1, d2)
+        key = (table.data_ptr(), table._version, tuple(table.shape), self.key)
+        if key != self.rowtab_key:
+            n_rows = table.shape[0]
+            nbytes = lib().nplda_rowtab_bytes(n_rows)
+            if self.rowtab is None or self.rowtab.numel() * 4 < nbytes or self.rowtab.device != table.device:
+                self.rowtab = torch.empty(max(1, nbytes // 4), dtype=torch.float32, device=table.device)
+            with torch.cuda.device(table.device):
+                check(lib().nplda_table_prepare(ptr(table), n_rows, d_in, d1, d2, ptr(pack), 0 if kind == "nplda" else 1,
+                                                ptr(self.rowtab), stream_ptr()), "nplda_table_prepare")
+            self.rowtab_key = key
+        return self.rowtab
 
 
 def _check_pair_inputs(x1, x2, d_in):
@@ -193,9 +216,12 @@ def score_from_embeddings(kind, e1, e2, params, dims, packed):
     return scores
 
 
-def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO):
-    """Scores of trials (table[i1[k]], table[i2[k]]) with the gather fused into the
-    kernel (replaces sv_trials_loaders.load_xvec_trials_from_numbatch + forward)."""
+def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO, embed_once=None):
+    """Scores of trials (table[i1[k]], table[i2[k]]) (replaces sv_trials_loaders.load_xvec_trials_from_numbatch
+    + forward).  Two device paths: `embed_once` transforms every table row once (nplda_table_prepare, cached
+    per table / parameter version) and scores a trial as r[i] + r[j] + A[i].B[j] (nplda_score_pairs); the other
+    fuses the gather into the full score kernel and recomputes both sides per trial.  Default: embed once when
+    the row table is already valid or the table has at most twice as many rows as this call has trials."""
     require_cuda(table, i1, i2)
     d_in, d1, d2 = dims
     if table.dim() != 2 or table.shape[1] != d_in:
@@ -210,6 +236,14 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
     pack = packed.get(kind, params, d_in, d1, d2)
     scores = torch.empty(n, dtype=torch.float32, device=dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if embed_once is None:
+        embed_once = max(d1, d2) < 176 and table.shape[0] > 0 and (packed.rowtab_valid(table) or table.shape[0] <= 2 * n)
+    if embed_once:
+        rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
+        with torch.cuda.device(dev):
+            check(lib().nplda_score_pairs(ptr(rowtab), table.shape[0], ptr(i1), ptr(i2), n, ptr(scores), ptr(flag),
+                                          stream_ptr()), "nplda_score_pairs")
+        return scores, flag
     with torch.cuda.device(dev):
         if kind == "nplda":
             rc = lib().nplda_score_fwd_indexed(ptr(table), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1, d2,

@@ -181,12 +181,13 @@ class NeuralPlda(_PldaBase):
     def forward(self, x1, x2):
         return F_.NpldaScoreFn.apply(x1, x2, *self._params(), self.packed, self.impl)
 
-    def forward_indexed(self, table, idx1, idx2):
-        """Scores for trials given as row indices into a device-resident x-vector
-        table (no gradient); the gather is fused into the score kernel."""
+    def forward_indexed(self, table, idx1, idx2, embed_once=None):
+        """Scores for trials given as row indices into a device-resident x-vector table (no gradient).
+        Every table row is transformed once and cached (F_.score_indexed); `embed_once=False` forces the
+        kernel that gathers and recomputes both sides per trial."""
         with torch.no_grad():
             scores, flag = F_.score_indexed("nplda", table, idx1, idx2, self._params(), self._dims(),
-                                            self.packed, self.impl)
+                                            self.packed, self.impl, embed_once)
         return scores, flag
 
     # The two half-steps of forward are part of the reference's public surface (models.py:366-376).
@@ -233,10 +234,10 @@ class DPlda(_PldaBase):
     def forward(self, x1, x2):
         return F_.DpldaScoreFn.apply(x1, x2, *self._params(), self.packed, self.impl)
 
-    def forward_indexed(self, table, idx1, idx2):
+    def forward_indexed(self, table, idx1, idx2, embed_once=None):
         with torch.no_grad():
             scores, flag = F_.score_indexed("dplda", table, idx1, idx2, self._params(), self._dims(),
-                                            self.packed, self.impl)
+                                            self.packed, self.impl, embed_once)
         return scores, flag
 
     def extract_plda_embeddings(self, x):

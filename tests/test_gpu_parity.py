@@ -103,6 +103,36 @@ def test_tc_kernel_is_selected_and_deterministic(kaldi_params, cfg1):
         m3(torch.zeros(4, 100, device=DEV), torch.zeros(4, 100, device=DEV))
 
 
+def test_tc_f8_mode_parity_and_range_guard(ref_out, kaldi_params, cfg1):
+    """IMPL_TC_F8 (layer 1 as fp16*fp16 + two e4m3*e4m3 products on one accumulator): 1e-4 parity on the golden
+    10k config and on ragged sizes; inputs outside the range the e4m3 terms cover must be recomputed on the
+    device by the bf16x3 kernel (bit-identical to IMPL_TC), and a later in-range call must again take the fp8 path
+    (the guard slot is cleared)."""
+    x1, x2, _ = cfg1
+    a, b = x1.to(DEV), x2.to(DEV)
+    m = make_nplda(kaldi_params, npl.IMPL_TC_F8)
+    mt = make_nplda(kaldi_params, npl.IMPL_TC)
+    with torch.no_grad():
+        s = m(a, b)
+        ok, worst = parity_ok(s, torch.from_numpy(ref_out["c1_scores"]), rel=1e-4)
+        assert ok, worst
+        assert not torch.equal(s, mt(a, b))                      # it really is the other arithmetic
+        kp = kaldi_params
+        for n in (1, 63, 65, 1000, 4097):
+            ref = O.nplda_score(x1[:n], x2[:n], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+            np.testing.assert_allclose(m(a[:n], b[:n]).cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-4)
+        for scale in (1e-3, 300.0):                                # out of range -> guarded fallback pass
+            got, want = m(a * scale, b * scale), mt(a * scale, b * scale)
+            assert torch.equal(got, want), scale
+            ref = O.nplda_score(x1 * scale, x2 * scale, kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+            ok, worst = parity_ok(got, ref, rel=1e-4)
+            assert ok, (scale, worst)
+        one_bad = a.clone(); one_bad[777, 5] = 1.0e4                 # a single out-of-range element flags the call
+        assert torch.equal(m(one_bad, b), mt(one_bad, b))
+        again = m(a, b)                                            # guard cleared: fp8 path again, same bits as before
+        assert torch.equal(again, s)
+
+
 def test_empty_input(kaldi_params):
     m = make_nplda(kaldi_params)
     with torch.no_grad():
@@ -177,7 +207,7 @@ def test_indexed_matches_materialised(kaldi_params, impl):
     m = make_nplda(kaldi_params, impl)
     t = table.to(DEV)
     with torch.no_grad():
-        s_idx, flag = m.forward_indexed(t, i1.to(DEV), i2.to(DEV))
+        s_idx, flag = m.forward_indexed(t, i1.to(DEV), i2.to(DEV), embed_once=False)   # gather fused into the score kernel
         s_mat = m(t[i1.to(DEV)], t[i2.to(DEV)])
     assert int(flag.item()) == 0
     if impl == npl.IMPL_SIMT:       # same kernel, same arithmetic: bit-identical
@@ -191,8 +221,54 @@ def test_indexed_matches_materialised(kaldi_params, impl):
     assert ok, worst
     bad = i1.clone(); bad[5] = 10 ** 6
     with torch.no_grad():
-        _, flag = m.forward_indexed(t, bad.to(DEV), i2.to(DEV))
+        _, flag = m.forward_indexed(t, bad.to(DEV), i2.to(DEV), embed_once=False)
     assert int(flag.item()) != 0
+
+
+@pytest.mark.parametrize("kind", ["nplda", "dplda"])
+def test_embed_once_trial_list_scoring(ref_out, kaldi_params, kind):
+    """every utterance of the table transformed once (nplda_table_prepare), trials scored as
+    r[i] + r[j] + A[i].B[j] (nplda_score_pairs).  Against the oracle on the gathered pairs, both models; the
+    cached row table must follow parameter updates and in-place table updates; bad indices are flagged."""
+    kp = kaldi_params
+    table, i1, i2, _ = O.synth_grid(61, 83, 17, seed=1004, mean=kp["mean"])
+    if kind == "nplda":
+        m = make_nplda(kp)
+        oracle = lambda tb: O.nplda_score(tb[i1], tb[i2], *[m.state_dict()[k].cpu() for k in (
+            "centering_and_LDA.weight", "centering_and_LDA.bias", "centering_and_wccn_plda.weight",
+            "centering_and_wccn_plda.bias", "P_sqrt", "Q")])
+    else:
+        m = make_dplda(kp, ref_out)
+        oracle = lambda tb: O.dplda_score(tb[i1], tb[i2], *[m.state_dict()[k].cpu() for k in (
+            "centering_and_LDA.weight", "centering_and_LDA.bias", "logistic_regres.weight", "logistic_regres.bias")])
+    t, a, b = table.to(DEV), i1.to(DEV), i2.to(DEV)
+    launches0 = _lib.launch_count()
+    s, flag = m.forward_indexed(t, a, b)                       # default: table has fewer rows than trials -> embed once
+    assert int(flag.item()) == 0 and s.shape == (i1.numel(),)
+    ok, worst = parity_ok(s, oracle(table), rel=1e-4)
+    assert ok, worst
+    used = _lib.launch_count() - launches0
+    s2, _ = m.forward_indexed(t, a[:100], b[:100])               # cached rows: one kernel, same bits
+    assert _lib.launch_count() - launches0 == used + 1
+    assert torch.equal(s2, s[:100])
+    s_fused, _ = m.forward_indexed(t, a, b, embed_once=False)    # the per-trial kernel agrees
+    ok, worst = parity_ok(s, s_fused.cpu(), rel=1e-4)
+    assert ok, worst
+    with torch.no_grad():                                        # parameter update -> rows rebuilt
+        m.centering_and_LDA.bias.add_(0.05)
+    s3, _ = m.forward_indexed(t, a, b)
+    ok, worst = parity_ok(s3, oracle(table), rel=1e-4)
+    assert ok, worst
+    assert not torch.equal(s3, s)
+    t.mul_(1.01)                                                 # in-place table update -> rows rebuilt
+    s4, _ = m.forward_indexed(t, a, b)
+    ok, worst = parity_ok(s4, oracle(t.cpu()), rel=1e-4)
+    assert ok, worst
+    bad = i2.clone(); bad[7] = -3
+    _, flag = m.forward_indexed(t, a, bad.to(DEV))
+    assert int(flag.item()) != 0
+    s0, _ = m.forward_indexed(t, a[:0], b[:0])
+    assert s0.shape == (0,)
 
 
 def test_embedding_half_steps(ref_out, kaldi_params, cfg1):

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) probe(Imgs im, float *D, long long *cyc, 
         tmem_st_wait();
     }
     tc_fence_before(); __syncthreads(); tc_fence_after();
-    if (tid == 0) {
+    if (tid == 0 && which < 10) {
         const uint32_t id16 = make_idesc(0, 0, M, N);            // kind::f16: 0 = F16
         const uint32_t id8 = make_idesc(fmt8, fmt8, M, N);       // kind::f8f6f4: 0 = E4M3, 1 = E5M2
         const uint64_t b16d = make_smem_desc(smem_addr(B16), LBO_B, 128), b8d = make_smem_desc(smem_addr(B8), LBO_B, 128);
@@ -84,6 +84,40 @@ __global__ void __launch_bounds__(128) probe(Imgs im, float *D, long long *cyc, 
         mma_commit(&bar);
         mbar_wait(&bar, 0);
         cyc[0] = clock64() - t0;
+    }
+    if (warp == 1 && which >= 10) {
+        // "stage" pattern of the score kernel's MMA warp: converged warp, elected issue, two satisfied barrier
+        // waits in the middle, two commits at the end.  which = 10: 6 bf16-style MMAs, 11: 2 f16 + 2 f8 MMAs,
+        // 12: no MMAs, 13: 6 MMAs without waits/commits, 14: 2+2 without waits/commits
+        __shared__ uint64_t bw[2], bc[2];
+        if ((tid & 31) == 0) { mbar_init(&bw[0], 1); mbar_init(&bw[1], 1); mbar_init(&bc[0], 1); mbar_init(&bc[1], 1); mbar_fence_init(); }
+        __syncwarp();
+        const uint32_t id16 = make_idesc(0, 0, M, N), id8 = make_idesc(0, 0, M, N);
+        const uint64_t b16d = make_smem_desc(smem_addr(B16), LBO_B, 128), b8d = make_smem_desc(smem_addr(B8), LBO_B, 128);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            tc_fence_after();
+            if (elect_one()) {
+                if (which == 10 || which == 13) { mma_ts(tmem, a16t, b16d, id16, 1); mma_ts(tmem, a16t + 8, b16d, id16, 1); mma_ts(tmem, a16t, b16d + ((2 * LBO_B) >> 4), id16, 1); }
+                if (which == 11 || which == 14) { mma_ts(tmem, a16t, b16d, id16, 1); mma_ts(tmem, a16t + 8, b16d + ((2 * LBO_B) >> 4), id16, 1); }
+            }
+            __syncwarp();
+            if (which <= 12 || which == 15) { mbar_wait(&bw[0], 1); mbar_wait(&bw[1], 1); }
+            if (elect_one()) {
+                if (which == 10 || which == 13) { mma_ts(tmem, a16t + 8, b16d, id16, 1); mma_ts(tmem, a16t, b16d, id16, 1); mma_ts(tmem, a16t + 8, b16d + ((2 * LBO_B) >> 4), id16, 1); }
+                if (which == 11 || which == 14) { mma_f8_ts(tmem, a8t, b8d, id8, 1); mma_f8_ts(tmem, a8t, b8d, id8, 1); }
+                if (which <= 12 || which == 16) { mma_commit(&bc[0]); mma_commit(&bc[1]); }
+                if (which == 17 || which == 18) mma_commit(&bc[0]);
+                if (which == 19) { mma_ts(tmem, a16t, b16d, id16, 1); mma_commit(&bc[0]); mma_ts(tmem, a16t, b16d, id16, 1); mma_commit(&bc[1]); }
+                if (which == 20) { mma_ts(tmem, a16t, b16d, id16, 1); mma_ts(tmem, a16t, b16d, id16, 1); mma_commit(&bc[0]); }
+            }
+            __syncwarp();
+            if (which == 18) { mbar_wait(&bc[0], it & 1); }      // wait for the commit's arrival every iteration
+        }
+        if (elect_one()) mma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        if ((tid & 31) == 0) cyc[0] = clock64() - t0;
     }
     __syncthreads();
     tc_fence_after();
@@ -157,6 +191,13 @@ int main() {
                        ts ? "tmem" : "smem", which, cudaGetErrorString(e), bad, worst);
                 bad_total += bad;
                 if (e != cudaSuccess) return 2;
+            }
+        if (fmt8 == 0)
+            for (int which = 10; which <= 20; ++which) {
+                const int iters = 2000;
+                probe<<<1, 128, smem>>>(im, dD, dc, 1, 0, which, iters);
+                long long h; cudaMemcpy(&h, dc, 8, cudaMemcpyDeviceToHost);
+                printf("stage pattern which=%d (10: 6 MMAs+2 waits+2 commits, 11: 2 f16+2 f8 +waits+commits, 12: waits+commits only, 13: 6 MMAs only, 14: 2+2 only, 15: 2 waits only, 16: 2 commits only, 17: 1 commit, 18: 1 commit + wait for it, 19: mma,commit,mma,commit, 20: 2 mma + 1 commit): %.0f cycles per stage [%s]\n", which, (double)h / iters, cudaGetErrorString(cudaGetLastError()));
             }
         if (fmt8 == 0)
             for (int ts = 0; ts < 2; ++ts)

@@ -41,13 +41,14 @@ __global__ void __launch_bounds__(128) k(int N, int ts, int nacc, int iters, lon
 int main() {
     long long *out; cudaMalloc(&out, 8);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    for (int grid : {1, 16, 74, 148})
     for (int N : {176})
         for (int ts = 0; ts < 2; ++ts)
-            for (int mode = 0; mode < 4; ++mode) {
+            for (int mode = 0; mode < 4; mode += 3) {
                 const int iters = 1998;
-                k<<<148, 128, 64 * 1024>>>(N, ts, 1, iters, out, mode);
+                k<<<grid, 128, 64 * 1024>>>(N, ts, 1, iters, out, mode);
                 long long h; cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
-                printf("N=%3d %s mode=%d (1: commit/6 MMAs, 2: two satisfied waits/6 MMAs): %.1f cycles/MMA, %.0f cycles per group of 6  [%s]\n", N, ts ? "TS" : "SS", mode, (double)h / iters, 6.0 * h / iters, cudaGetErrorString(cudaGetLastError()));
+                printf("grid %3d N=%3d %s mode=%d (1: commit/6 MMAs, 2: two satisfied waits/6 MMAs): %.1f cycles/MMA, %.0f cycles per group of 6  [%s]\n", grid, N, ts ? "TS" : "SS", mode, (double)h / iters, 6.0 * h / iters, cudaGetErrorString(cudaGetLastError()));
             }
     return 0;
 }
