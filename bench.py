@@ -49,6 +49,16 @@ def kaldi_params():
     return {k: torch.from_numpy(z[k].copy()) for k in z.files}
 
 
+def measured_traffic():
+    """DRAM bytes per K1 launch from the committed `ncu --set full` capture of this workload (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(p):
+        t = json.load(open(p))
+        if t.get("pairs") == PAIRS_PER_GPU:
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -119,9 +129,11 @@ def synth_on_device(n, seed, mean, dev):
     return x1, x2, tgt.float()
 
 
-def cpu_forward_timing(kp, n_chunks, repeats, threads=None):
+def cpu_forward_timing(kp, n_chunks, repeats, threads=None, min_seconds=0.0):
     """The reference's CPU forward restated by the oracle, in chunks of 102,400
-    pairs as scorefile_generator.py scores, under no_grad, all host threads."""
+    pairs as scorefile_generator.py scores, under no_grad, all host threads.
+    Repeats passes of `n_chunks` chunks until `repeats` passes are done AND at least
+    `min_seconds` of CPU work has been timed; returns the best pass."""
     from oracle import nplda_oracle as O
     if threads:
         torch.set_num_threads(threads)
@@ -129,13 +141,18 @@ def cpu_forward_timing(kp, n_chunks, repeats, threads=None):
     args = (kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
     with torch.no_grad():
         O.nplda_score(x1[:4096], x2[:4096], *args)   # warm the thread pool
-        best = None
-        for _ in range(repeats):
+        best, total, passes = None, 0.0, 0
+        while passes < repeats or total < min_seconds:
             t0 = time.perf_counter()
             for _ in range(n_chunks):
                 s = O.nplda_score(x1, x2, *args)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
+            total += dt
+            passes += 1
+            if total > 30.0:
+                break
+    cpu_forward_timing.last = {"passes": passes, "total_s": total}
     return n_chunks * REF_CHUNK / best, best, float(s[0])
 
 
@@ -145,7 +162,7 @@ def run_reference(args):
         return
     kp = kaldi_params()
     threads = os.cpu_count()
-    n_chunks = 2
+    n_chunks = 10                                    # one step = the configs[1] workload: 1,024,000 pairs in scoring-loop chunks
     torch.set_num_threads(threads)
     for _ in range(args.warmup):
         cpu_forward_timing(kp, 1, 1, threads)
@@ -192,7 +209,7 @@ def run_ours(args):
                       ("centering_and_wccn_plda.weight", "W2"), ("centering_and_wccn_plda.bias", "b2"),
                       ("P_sqrt", "P_sqrt"), ("Q", "Q")):
         sd[name].copy_(kp[key])
-    model.impl = {"auto": npl.IMPL_AUTO, "simt": npl.IMPL_SIMT, "tc": npl.IMPL_TC}[args.kernel]
+    model.impl = {"auto": npl.IMPL_AUTO, "simt": npl.IMPL_SIMT, "tc": npl.IMPL_TC, "f8": npl.IMPL_TC_F8}[args.kernel]
     model.process_group = group
     model.eval()
 
@@ -289,7 +306,9 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         value = world * n * args.steps / (total_ms * 1e-3)
         achieved = n * BYTES_PER_PAIR / (k1_ms * 1e-3) / 1e9
-        cpu_rate, cpu_s, _ = cpu_forward_timing(kp, 10, 2, os.cpu_count()) if not args.no_cpu_baseline else (None, 0, 0)
+        cpu_rate, cpu_s, _ = (cpu_forward_timing(kp, 10, 3, os.cpu_count(), min_seconds=12.0)
+                              if not args.no_cpu_baseline else (None, 0, 0))
+        tl = trial_list_leg(model, kp, dev) if (not args.skip_trial_list and world == 1) else None
         res = {
             "metric": "trial-pairs scored/sec (512-d xvec)", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -301,7 +320,7 @@ def run_ours(args):
                        "one all-reduce of 12 fp64 accumulators per step" if world > 1 else "single GPU",
                        "l2": "inputs (4.1 GB per step) larger than L2 (126 MB); no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "K1 fused score kernel", "k1_ms": k1_ms,
+                         "traffic": measured_traffic(), "kernel": "K1 fused score kernel", "k1_ms": k1_ms,
                          "bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src},
             "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "pairs/s",
                     "h2d_bytes_per_step": n * (2 * D_IN * 4 + 4), "d2h_bytes_per_step": 4, "steps": e2e_steps,
@@ -312,12 +331,68 @@ def run_ours(args):
         }
         if cpu_rate is not None:
             res["cpu_baseline"] = {"value": cpu_rate, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"10 x {REF_CHUNK}-pair chunks (same synthetic chunk re-scored), best of 2, "
-                                             f"oracle port of NeuralPlda.forward under no_grad, {cpu_s:.1f} s",
+                                   "sample": f"passes of 10 x {REF_CHUNK}-pair chunks (1,024,000 pairs, same synthetic chunk "
+                                             f"re-scored) for {cpu_forward_timing.last['total_s']:.1f} s of CPU work "
+                                             f"({cpu_forward_timing.last['passes']} passes), best pass {cpu_s:.2f} s; oracle "
+                                             f"port of NeuralPlda.forward under no_grad",
                                    "torch_threads": torch.get_num_threads()}
+        if tl is not None:
+            res["trial_list"] = tl
         print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def trial_list_leg(model, kp, dev):
+    """Extra, separately-labelled measurement (never mixed into `value` / `roofline`): BASELINE.json
+    configs[2] in the INDEXED layout the reference's scoring loop actually has (a table of unique
+    x-vectors + a trial list, scorefile_generator.py:29-36): 10 M trials = 2500 enrol x 4000 test over 6500
+    utterances, every utterance transformed once (nplda_table_prepare) and each trial scored as
+    r[i] + r[j] + A[i].B[j] (nplda_score_pairs)."""
+    from oracle import nplda_oracle as O
+    table, i1, i2, _ = O.synth_grid(2500, 4000, 500, seed=1003, mean=kp["mean"])
+    t, a, b = table.to(dev), i1.to(dev), i2.to(dev)
+    n = a.numel()
+    stream = torch.cuda.current_stream()
+
+    def full():
+        model.packed.rowtab_key = None               # table prepare inside every step
+        return model.forward_indexed(t, a, b)[0]
+
+    s = full()
+    sub = torch.arange(0, n, 997)
+    ref = O.nplda_score(table[i1[sub]], table[i2[sub]], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"]).double()
+    got = s[sub.to(dev)].cpu().double()
+    worst = float(((got - ref).abs() / (1e-4 * torch.maximum(ref.abs(), ref.pow(2).mean().sqrt()))).max())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record(stream)
+    for _ in range(reps):
+        full()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    ha, hb, hs = i1.pin_memory(), i2.pin_memory(), torch.empty(n, pin_memory=True)
+
+    def e2e():
+        model.packed.rowtab_key = None
+        s_ = model.forward_indexed(t, ha.to(dev, non_blocking=True), hb.to(dev, non_blocking=True))[0]
+        hs.copy_(s_, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        e2e()
+    dt = (time.perf_counter() - t0) / 5
+    return {"workload": "configs[2] indexed: 10M trials = 2500 x 4000 grid over 6500 x-vectors (table resident in HBM), "
+                        "table prepare + pair scoring every step",
+            "value": n / (ms * 1e-3), "unit": "trials/s", "ms_per_step": ms,
+            "e2e": {"value": n / dt, "unit": "trials/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 4 * n,
+                    "api": "NeuralPlda.forward_indexed on pinned host index tensors, scores copied back to pinned host memory"},
+            "bytes_per_trial": {"hbm_indices_and_score": 20, "l2_row_gather": 1408},
+            "parity_worst_over_bound_strided_sample": worst}
 
 
 def main():
@@ -326,7 +401,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc", "f8"])
+    ap.add_argument("--skip-trial-list", action="store_true", help="skip the extra indexed trial-list measurement")
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only; prints no bench line")

@@ -10,7 +10,9 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; 
 timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --skip-e2e --skip-trial-list > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_tc -s 2 -c 1 -f -o gpurun_out/${TAG}_score_tc \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --skip-e2e --skip-trial-list > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_pairs -s 1 -c 1 -f -o gpurun_out/${TAG}_score_pairs \
+    python tools/quick_pairs.py > gpurun_out/${TAG}_ncu_pairs.log 2>&1; echo "ncu pairs rc=$?"
 tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_smoke.log | tail -2; cat gpurun_out/${TAG}_bench.json; cat gpurun_out/${TAG}_bench_ref.json

@@ -1,0 +1,76 @@
+"""Turns the raw ncu outputs a `tools/gpu_validate.sh <tag>` run left in gpurun_out/ into the small committed
+summaries under profiles/: launch list with per-kernel shares, key metrics of the --set full captures, and
+profiles/k1_traffic.json (DRAM bytes per K1 launch, read by bench.py for roofline.traffic).
+Usage: python tools/summarize_profiles.py <tag> [round-name]"""
+import csv, io, json, os, re, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r1"
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "sm__cycles_elapsed.avg.per_second", "sm__cycles_elapsed.max",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "derived__memory_l1_wavefronts_shared_excessive",
+        "launch__registers_per_thread", "launch__block_size", "launch__grid_size", "launch__shared_mem_per_block_dynamic",
+        "sm__inst_executed_pipe_tensor.sum", "smsp__cycles_active.avg"]
+
+# ---- launch list
+src = os.path.join(G, f"{tag}_launches.csv")
+if os.path.exists(src):
+    rows = [r for r in csv.reader(l for l in open(src) if l.startswith('"'))]
+    hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
+    agg = {}
+    for r in rows[1:]:
+        if r[ix["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        name = r[ix["Kernel Name"]]
+        v = float(r[ix["Metric Value"]].replace(",", ""))
+        unit = r[ix["Metric Unit"]]
+        v_us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v_us
+    ours = {k: v for k, v in agg.items() if "nplda" in k or "tcg::" in k}
+    tot = sum(v[1] for v in ours.values())
+    with open(os.path.join(P, f"{rnd}_launches.csv"), "w") as f:
+        f.write(f"# ncu launch list, {rnd} (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare shares)\n")
+        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --skip-e2e\n")
+        f.write("# kernels of libnplda.so only (torch's synthetic-data generator kernels omitted); share = of libnplda time\n")
+        f.write("share_pct,launches,avg_us,kernel\n")
+        for k, v in sorted(ours.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{100 * v[1] / tot:.2f},{v[0]},{v[1] / v[0]:.1f},\"{k[:110]}\"\n")
+    print("wrote launches", len(ours))
+
+# ---- full captures
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return rows[0], rows[1], rows[2:]
+
+for name, outname in ((f"{tag}_score_tc.ncu-rep", f"{rnd}_score_tc_kernel_ncu.csv"), (f"{tag}_score_pairs.ncu-rep", f"{rnd}_score_pairs_kernel_ncu.csv")):
+    rep = os.path.join(G, name)
+    if not os.path.exists(rep):
+        continue
+    hdr, units, launches = raw(rep)
+    vals = launches[0]
+    kname = vals[hdr.index("Kernel Name")]
+    with open(os.path.join(P, outname), "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on, {rnd}: {kname[:100]}, B200\n")
+        f.write("metric,unit,value\n")
+        got = {}
+        for h, u, v in zip(hdr, units, vals):
+            base = h.split("TriageCompute.")[-1]
+            if any(base == k for k in KEYS):
+                f.write(f"{base},{u},{v}\n"); got[base] = (u, v)
+    print("wrote", outname)
+    if "score_tc" in name and "dram__bytes_read.sum" in got:
+        def tobytes(u, v):
+            v = float(v.replace(",", ""))
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        rd, wr = tobytes(*got["dram__bytes_read.sum"]), tobytes(*got["dram__bytes_write.sum"])
+        json.dump({"kernel": kname[:80], "pairs": 1000000, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                   "source": f"ncu --set full --clock-control none, one launch of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline "
+                             f"--skip-e2e` (tools/gpu_validate.sh {tag}); summary in profiles/{outname}"},
+                  open(os.path.join(P, "k1_traffic.json"), "w"), indent=1)
+        print("wrote k1_traffic.json", rd, wr)
