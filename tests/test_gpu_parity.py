@@ -509,3 +509,62 @@ def test_large_properties_1m(kaldi_params):
         ref = O.nplda_score(x1[idx].cpu(), x2[idx].cpu(), kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
         ok, worst = parity_ok(s[idx], ref, rel=1e-4)
         assert ok, worst
+
+
+def test_config3_10m_grid_trial_list(kaldi_params):
+    """BASELINE.json configs[2]: 10M trials = 2500 enrol x 4000 test grid over 6500 x-vectors, indexed layout.
+    Oracle on a strided subsample; properties: the grid is symmetric under swapping the roles of the two index
+    lists, and scoring the list in ragged chunks gives the same bits."""
+    kp = kaldi_params
+    table, i1, i2, lab = O.synth_grid(2500, 4000, 500, seed=1003, mean=kp["mean"])
+    m = make_nplda(kp)
+    t, a, b = table.to(DEV), i1.to(DEV), i2.to(DEV)
+    s, flag = m.forward_indexed(t, a, b)
+    assert int(flag.item()) == 0 and s.numel() == 10_000_000
+    sub = torch.arange(0, s.numel(), 1009)
+    ref = O.nplda_score(table[i1[sub]], table[i2[sub]], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    ok, worst = parity_ok(s[sub.to(DEV)], ref, rel=1e-4)
+    assert ok, worst
+    s_swapped, _ = m.forward_indexed(t, b, a)                       # S(i, j) == S(j, i) (models.py:373-375 is symmetric)
+    np.testing.assert_allclose(s_swapped.cpu().numpy(), s.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    parts = [m.forward_indexed(t, a[lo:hi], b[lo:hi])[0] for lo, hi in ((0, 1), (1, 3_333_333), (3_333_333, 10_000_000))]
+    assert torch.equal(torch.cat(parts), s)
+    # targets score higher than non-targets on this generator (SURVEY 8d): a degenerate kernel would not separate them
+    labd = lab.to(DEV).bool()
+    assert float(s[labd].mean()) > float(s[~labd].mean()) + 0.5
+
+
+def test_config4_50m_sharded_accumulators(kaldi_params):
+    """BASELINE.json configs[3]: 50M trials = 5000 x 10000 grid, sharded by contiguous trial ranges as the
+    multi-GPU path shards them (dist.shard_range).  The raw fp64 loss accumulators of the shards must add up to
+    the accumulators of the whole list (the all-reduce payload), and the loss finalised from the sum must equal
+    the loss of the whole list -- while the mean of per-shard losses does not."""
+    from neuralplda_b200 import dist as D
+    kp = kaldi_params
+    table, i1, i2, lab = O.synth_grid(5000, 10000, 700, seed=1004, mean=kp["mean"])
+    m = make_nplda(kp)
+    t, a, b, y = table.to(DEV), i1.to(DEV), i2.to(DEV), lab.to(DEV)
+    n = a.numel()
+    assert n == 50_000_000
+    s, _ = m.forward_indexed(t, a, b)
+    th = torch.cat([m.threshold[bt].detach() for bt in NC.beta])
+    whole = F_.loss_accumulators(s, y, th, NC.alpha, m.threshold_Xent)
+    world = 8
+    shards = []
+    for r in range(world):
+        lo, hi = D.shard_range(n, world, r)
+        sr, _ = m.forward_indexed(t, a[lo:hi], b[lo:hi])
+        assert torch.equal(sr, s[lo:hi])
+        shards.append(F_.loss_accumulators(sr, y[lo:hi], th, NC.alpha, m.threshold_Xent))
+    summed = torch.stack(shards).sum(0)
+    np.testing.assert_allclose(summed.cpu().numpy(), whole.cpu().numpy(), rtol=1e-12)
+    assert float(summed[-1]) == n
+    loss_whole = F_.finalize(whole, NC.beta)[0].item()
+    loss_sum = F_.finalize(summed, NC.beta)[0].item()
+    assert loss_sum == pytest.approx(loss_whole, rel=1e-6)
+    per_shard = np.mean([F_.finalize(sh, NC.beta)[0].item() for sh in shards])
+    assert abs(per_shard - loss_whole) > 1e-7 * abs(loss_whole)     # averaging per-rank losses is NOT the same thing
+    sub = torch.arange(0, n, 50021)
+    ref = O.nplda_score(table[i1[sub]], table[i2[sub]], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    ok, worst = parity_ok(s[sub.to(DEV)], ref, rel=1e-4)
+    assert ok, worst
