@@ -12,7 +12,8 @@
  *    ends in _host; fp32 tensors are contiguous row-major; the caller owns all
  *    buffers (PyTorch allocations); the library keeps no global mutable state
  *    and allocates nothing that outlives a call except explicit workspaces
- *    the caller passes in.
+ *    the caller passes in (one exception: NPLDA_IMPL_TC_F8 keeps an 8 KB ring of
+ *    range-guard flags per device, allocated on first use).
  *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
  *    and nothing synchronises unless stated.
  *  - return value: 0 = OK; > 0 = a cudaError_t; < 0 = NPLDA_ERR_*.
@@ -33,6 +34,8 @@ extern "C" {
 #define NPLDA_ERR_UNSUPPORTED_DIM (-2) /* layer widths beyond what the kernels are built for */
 #define NPLDA_ERR_WORKSPACE (-3)      /* workspace too small                                 */
 #define NPLDA_ERR_NO_DEVICE (-4)      /* no sm_100 device / kernel image not loadable        */
+#define NPLDA_ERR_IO (-5)             /* file cannot be opened / read / written               */
+#define NPLDA_ERR_FORMAT (-6)         /* trial file rows with differing numbers of fields     */
 
 /* kernel selection for the score kernels */
 #define NPLDA_IMPL_AUTO 0   /* NPLDA_IMPL_TC when the shape allows, else SIMT */
@@ -212,6 +215,38 @@ int64_t nplda_host_scratch_bytes(int64_t chunk_pairs, int d_in);
 int nplda_score_fwd_host(const float *x1_host, const float *x2_host, int64_t n, int d_in, int d1,
                          int d2, const void *pack, float *scores_host, int64_t chunk_pairs,
                          void *dev_scratch, int64_t dev_scratch_bytes, int is_dplda, int impl);
+
+/* ---------------------------------------------------------------------------
+ * Host-side text I/O either side of the path; no device work.
+ * Trial-list reader: replaces np.genfromtxt(file, dtype='str') + the per-row
+ * dict lookups of sv_trials_loaders.py:376-383 / 399-406 and
+ * scorefile_generator.py:26 / 45.  Fields are split on runs of blanks, '#' starts
+ * a comment, empty lines are skipped, all rows must have the same field count
+ * (else NPLDA_ERR_FORMAT, genfromtxt's ValueError).
+ * nplda_trials_map_ids: column `col` of rows [first_row, rows) looked up in a table
+ * of n_ids ids (one buffer, every id terminated by '\n'; values[r] or r when
+ * values == NULL; later duplicates win).  mode 0: field as is; 1: os.path.splitext
+ * root (sv_trials_loaders.py:403); 2: basename + splitext (:432).  Unknown -> -1.
+ * nplda_trials_col_float: Python float() of a column (labels), ok[i] = 0 where it
+ * does not parse (the reference drops such rows, :379-383).
+ * nplda_scores_write: rows [first_row, rows): first ncols_keep fields + the score as
+ * numpy prints a float32 (str(np.float32(s)): shortest round-trip digits), tab
+ * separated, '\n' terminated, after an optional header line -- the files of
+ * scorefile_generator.py:37-38 (sre: all columns, header + "\tLLR") and :54-55
+ * (voices: 2 columns, no header), byte for byte.
+ * ------------------------------------------------------------------------- */
+typedef struct nplda_trials nplda_trials;
+int nplda_trials_open(const char *path, nplda_trials **out);
+void nplda_trials_close(nplda_trials *t);
+int64_t nplda_trials_rows(const nplda_trials *t);
+int nplda_trials_cols(const nplda_trials *t);
+int64_t nplda_trials_field(const nplda_trials *t, int64_t row, int col, const char **ptr);   /* length; not NUL-terminated */
+int nplda_trials_map_ids(const nplda_trials *t, int col, int mode, const char *ids, int64_t ids_bytes,
+                         int64_t n_ids, const int64_t *values, int64_t first_row, int64_t *idx_out);
+int nplda_trials_col_float(const nplda_trials *t, int col, int64_t first_row, float *out, uint8_t *ok);
+int nplda_scores_write(const char *path, const nplda_trials *t, int64_t first_row, int ncols_keep,
+                       const float *scores, const char *header_line);
+int nplda_format_f32(float v, char *out24);   /* str(np.float32(v)) into out24 (not NUL-terminated); returns the length */
 
 #ifdef __cplusplus
 }

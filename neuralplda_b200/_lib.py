@@ -60,6 +60,15 @@ SIGNATURES = {
                         + [c_vp, c_i64, c_vp]),
     "nplda_minc_sweep": (c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
                                  ctypes.POINTER(ctypes.c_double), c_int, c_vp, c_vp, c_vp]),
+    "nplda_trials_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "nplda_trials_close": (None, [c_vp]),
+    "nplda_trials_rows": (c_i64, [c_vp]),
+    "nplda_trials_cols": (c_int, [c_vp]),
+    "nplda_trials_field": (c_i64, [c_vp, c_i64, c_int, ctypes.POINTER(c_vp)]),
+    "nplda_trials_map_ids": (c_int, [c_vp, c_int, c_int, ctypes.c_char_p, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "nplda_trials_col_float": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
+    "nplda_scores_write": (c_int, [ctypes.c_char_p, c_vp, c_i64, c_int, c_vp, ctypes.c_char_p]),
+    "nplda_format_f32": (c_int, [ctypes.c_float, ctypes.c_char_p]),
     "nplda_host_scratch_bytes": (c_i64, [c_i64, c_int]),
     "nplda_score_fwd_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_i64,
                                      c_int, c_int]),

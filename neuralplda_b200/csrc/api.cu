@@ -87,6 +87,8 @@ extern "C" const char *nplda_error_string(int code) {
         case NPLDA_ERR_UNSUPPORTED_DIM: return "nplda: unsupported layer dimensions for this kernel";
         case NPLDA_ERR_WORKSPACE: return "nplda: workspace too small";
         case NPLDA_ERR_NO_DEVICE: return "nplda: no usable sm_100 device";
+        case NPLDA_ERR_IO: return "nplda: file cannot be opened, read or written";
+        case NPLDA_ERR_FORMAT: return "nplda: trial file rows have differing numbers of fields";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

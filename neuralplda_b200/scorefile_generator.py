@@ -15,35 +15,50 @@ import numpy as np
 import torch
 
 from .sv_trials_loaders import get_table, strip_id
+from .textio import TrialFile, MODE_BASENAME_SPLITEXT
 
 
-def _score_trials(trials, mega_dict, model, device, batch_size):
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise RuntimeError("neuralplda_b200 scores on the GPU only; got device '%s'" % device)
-    tab = get_table(mega_dict, device)
-    r1 = tab.rows_for_ids([strip_id(d) for d in trials[:, 0]])
-    r2 = tab.rows_for_ids([strip_id(d) for d in trials[:, 1]])
+def _score_rows(r1, r2, tab, model, device, batch_size):
     was_training = model.training
     model = model.to(device).eval()
     out = []
-    for i in range(0, len(trials), batch_size):
+    r1, r2 = torch.from_numpy(r1), torch.from_numpy(r2)
+    for i in range(0, len(r1), batch_size):
         s, flag = model.forward_indexed(tab.table, r1[i:i + batch_size].to(device), r2[i:i + batch_size].to(device))
         out.append(s)
     scores = torch.cat(out).cpu().numpy() if out else np.zeros(0, np.float32)
     model.train(was_training)
-    return scores.astype(np.float32).astype(str)
+    return scores.astype(np.float32)
+
+
+def _generate(score_filename, trials_file, mega_dict, model, device, batch_size, sre):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("neuralplda_b200 scores on the GPU only; got device '%s'" % device)
+    tab = get_table(mega_dict, device)
+    with TrialFile(trials_file) as tf:
+        first = 1 if sre else 0                      # sre files carry a header row (scorefile_generator.py:27-28)
+        if tf.cols < 2:
+            raise IndexError("trial files need at least the enrol and test columns")
+        r1 = tf.map_ids(0, tab.ids, mode=MODE_BASENAME_SPLITEXT, first_row=first)     # sv_trials_loaders.py:432
+        r2 = tf.map_ids(1, tab.ids, mode=MODE_BASENAME_SPLITEXT, first_row=first)
+        bad = np.nonzero((r1 < 0) | (r2 < 0))[0]
+        if bad.size:                                  # the reference's dict lookup raises KeyError
+            row = int(bad[0]) + first
+            raise KeyError(strip_id(tf.field(row, 0 if r1[bad[0]] < 0 else 1)))
+        scores = _score_rows(r1, r2, tab, model, device, batch_size)
+        if sre:
+            header = "\t".join(tf.row(0)) + "\tLLR" if tf.rows else "\tLLR"
+            tf.write_scores(score_filename, scores, tf.cols, header_line=header, first_row=first)
+        else:
+            tf.write_scores(score_filename, scores, 2)
 
 
 def generate_sre_scores(score_filename, trials_file, mega_dict, model, device, batch_size=102400):
-    trials = np.genfromtxt(trials_file, dtype='str')
-    header = '\t'.join(trials[0]) + '\tLLR'
-    trials = trials[1:]
-    scores = _score_trials(trials, mega_dict, model, device, batch_size)
-    np.savetxt(score_filename, np.c_[trials, scores], header=header, fmt='%s', delimiter='\t', comments='')
+    """scorefile_generator.py:22-39: header row kept, all columns + "LLR"."""
+    _generate(score_filename, trials_file, mega_dict, model, device, batch_size, sre=True)
 
 
 def generate_voices_scores(score_filename, trials_file, mega_dict, model, device, batch_size=102400):
-    trials = np.genfromtxt(trials_file, dtype='str')[:, :2]
-    scores = _score_trials(trials, mega_dict, model, device, batch_size)
-    np.savetxt(score_filename, np.c_[trials, scores], fmt='%s', delimiter='\t', comments='')
+    """scorefile_generator.py:41-56: first two columns + score, no header."""
+    _generate(score_filename, trials_file, mega_dict, model, device, batch_size, sre=False)

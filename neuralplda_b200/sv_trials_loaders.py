@@ -101,20 +101,24 @@ def load_xvec_trials_from_idbatch(mega_dict, trials, device):
 
 def _read_trials(f, id_to_num_dict, strip_ext_col2):
     """Rows with unknown ids or unparsable labels are silently dropped, as the
-    reference's try/except does (sv_trials_loaders.py:379-383, 402-406)."""
-    t = np.genfromtxt(f, dtype='str')
-    if t.ndim == 1:
-        t = t.reshape(1, -1)
-    x1, x2, l = [], [], []
-    for tr in t:
-        try:
-            b_id = os.path.splitext(tr[1])[0] if strip_ext_col2 else tr[1]
-            a, b, c = id_to_num_dict[tr[0]], id_to_num_dict[b_id], float(tr[2])
-            x1.append(a); x2.append(b); l.append(c)
-        except Exception:
-            pass
-    return TensorDataset(torch.tensor(x1, dtype=torch.int64), torch.tensor(x2, dtype=torch.int64),
-                         torch.tensor(l, dtype=torch.float32))
+    reference's try/except does (sv_trials_loaders.py:379-383, 402-406).  Parsing and
+    the id lookups run in the native reader (textio.TrialFile), one pass over the file."""
+    from .textio import TrialFile, MODE_ASIS, MODE_SPLITEXT
+    keys = list(id_to_num_dict)
+    if not all(isinstance(k, str) for k in keys):
+        raise TypeError("id_to_num_dict must map utterance id strings to row numbers")
+    vals = np.asarray([id_to_num_dict[k] for k in keys], dtype=np.int64)
+    with TrialFile(f) as tf:
+        if tf.rows == 0 or tf.cols < 3:               # tr[2] raises in the reference: every row is dropped
+            x1 = x2 = np.zeros(0, np.int64); lab = np.zeros(0, np.float32)
+        else:
+            p1 = tf.map_ids(0, keys, None, MODE_ASIS)
+            p2 = tf.map_ids(1, keys, None, MODE_SPLITEXT if strip_ext_col2 else MODE_ASIS)
+            lab, ok = tf.col_float(2)
+            keep = (p1 >= 0) & (p2 >= 0) & ok
+            x1, x2, lab = vals[p1[keep]], vals[p2[keep]], lab[keep]
+    return TensorDataset(torch.from_numpy(np.ascontiguousarray(x1)), torch.from_numpy(np.ascontiguousarray(x2)),
+                         torch.from_numpy(np.ascontiguousarray(lab, dtype=np.float32)))
 
 
 def combine_trials_and_get_loader(trials_key_files_list, id_to_num_dict, subsample_factors=None, batch_size=2048, subset=0):
