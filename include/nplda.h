@@ -217,6 +217,22 @@ int nplda_score_fwd_host(const float *x1_host, const float *x2_host, int64_t n, 
                          void *dev_scratch, int64_t dev_scratch_bytes, int is_dplda, int impl);
 
 /* ---------------------------------------------------------------------------
+ * Cohort score normalisation: the arithmetic of the reference's
+ * utils/adaptive_score_normalization.py on the device, in float64 like the script.
+ * nplda_cohort_stats: scores [m, c] fp32 row-major (one row per enrol / test id, its
+ * scores against the c cohort utterances, e.g. an id x cohort grid from
+ * nplda_score_pairs) -> stats [m, 4] doubles: mean, std (population, np.std) over
+ * the row (:33-34), and mean, std over the top_n LOWEST scores of the row -- the
+ * first top_n of the ascending sort, as :32/:35-36 compute them (all c if c < top_n).
+ * nplda_score_norm: for trial i with rows e = enrol_row[i], t = test_row[i] of stats
+ * (:62-66): out[0*n+i] = znorm, out[1*n+i] = tnorm, out[2*n+i] = snorm,
+ * out[3*n+i] = asnorm1.  Rows outside [0, m) set *bad_index_flag.
+ * ------------------------------------------------------------------------- */
+int nplda_cohort_stats(const float *scores, int64_t m, int64_t c, int64_t top_n, double *stats, void *stream);
+int nplda_score_norm(const float *raw, const int64_t *enrol_row, const int64_t *test_row, int64_t n,
+                     const double *stats, int64_t m, double *out, int32_t *bad_index_flag, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Host-side text I/O either side of the path; no device work.
  * Trial-list reader: replaces np.genfromtxt(file, dtype='str') + the per-row
  * dict lookups of sv_trials_loaders.py:376-383 / 399-406 and

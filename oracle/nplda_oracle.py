@@ -375,3 +375,30 @@ def gather_numbatch(mega_dict, num_to_id, d1, d2):
 def format_scores(scores_f32):
     """Score text as written by scorefile_generator.py:37,54: str(np.float32)."""
     return np.asarray(scores_f32, dtype=np.float32).astype(str)
+
+
+# ----------------------------------------------------------------------------
+# Cohort score normalisation (SURVEY.md section 8 f-4)
+# ----------------------------------------------------------------------------
+
+
+def cohort_stats(cohort_scores, top_n=500):
+    """utils/adaptive_score_normalization.py:32-36.  cohort_scores [m, c] (one row per enrol / test id) ->
+    [m, 4] float64: mean, std over the row; mean, std over the first top_n entries of the ASCENDING sort
+    (the top_n lowest scores -- the script sorts ascending and slices [:ASnorm_topN]).  np.std is the
+    population standard deviation."""
+    s = np.sort(np.asarray(cohort_scores, dtype=np.float64), axis=1)
+    return np.stack([np.mean(s, axis=1), np.std(s, axis=1),
+                     np.mean(s[:, :top_n], axis=1), np.std(s[:, :top_n], axis=1)], axis=1)
+
+
+def score_norm(raw, enrol_row, test_row, stats):
+    """utils/adaptive_score_normalization.py:61-66 for every trial; rows index `stats` (the script's dicts).
+    Returns [4, n] float64: znorm, tnorm, snorm, asnorm1."""
+    raw = np.asarray(raw, dtype=np.float64)
+    e, t = stats[np.asarray(enrol_row)], stats[np.asarray(test_row)]
+    z = (raw - e[:, 0]) / e[:, 1]
+    tn = (raw - t[:, 0]) / t[:, 1]
+    sn = (z + tn) / 2
+    asn = ((raw - e[:, 2]) / e[:, 3] + (raw - t[:, 2]) / t[:, 3]) / 2
+    return np.stack([z, tn, sn, asn])

@@ -568,3 +568,72 @@ def test_config4_50m_sharded_accumulators(kaldi_params):
     ref = O.nplda_score(table[i1[sub]], table[i2[sub]], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
     ok, worst = parity_ok(s[sub.to(DEV)], ref, rel=1e-4)
     assert ok, worst
+
+
+# ------------------------------------------------------------------------------
+# f-4: cohort score normalisation (utils/adaptive_score_normalization.py)
+# ------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("m,c,top_n", [(7, 510, 500), (3, 40, 500), (33, 4097, 500), (5, 1000, 1), (2, 3000, 2999)])
+def test_cohort_stats_vs_oracle(m, c, top_n):
+    """Row statistics incl. the N lowest scores (radix select == sort()[:N]); ties, negative zero, duplicates of
+    the boundary value.  fp64 sums in a different order than numpy's: 1e-12 relative."""
+    from neuralplda_b200 import adaptive_score_normalization as asn
+    g = torch.Generator().manual_seed(100 + c)
+    x = torch.randn(m, c, generator=g) * 0.3 - 0.8
+    x[:, 5] = x[:, 17]
+    x[0, : min(c, 300)] = x[0, 0]                                # a long run of equal values across the boundary
+    x[-1, 1::2] = -0.0
+    x[-1, 0::2] = 0.0
+    got = asn.cohort_statistics(x.to(DEV), top_n).cpu().numpy()
+    want = O.cohort_stats(x.numpy(), top_n)
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+
+
+def test_score_norm_golden_files(tmp_path):
+    """The four normalised score files of the unmodified reference script (tests/golden/c7_*): values within
+    1e-6 (raw scores travel as float32 here, the script parses the text as float64), same rows and header."""
+    import shutil
+    from neuralplda_b200 import adaptive_score_normalization as asn
+    raw = str(tmp_path / "raw.tsv")
+    shutil.copy(os.path.join(GOLDEN, "c7_raw_scores.tsv"), raw)
+    out = asn.normalize_score_file(raw, os.path.join(GOLDEN, "c7_cohort_scores.tsv"), DEV)
+    for k, name in enumerate(asn.NORMS):
+        want = open(os.path.join(GOLDEN, "c7_raw_scores.tsv_%s.tsv" % name)).read().splitlines()
+        got = open(raw + "_%s.tsv" % name).read().splitlines()
+        assert len(got) == len(want) and got[0] == want[0]
+        for lg, lw in zip(got[1:], want[1:]):
+            fg, fw = lg.split("\t"), lw.split("\t")
+            assert fg[:-1] == fw[:-1]
+            assert abs(float(fg[-1]) - float(fw[-1])) <= 1e-6 * max(1.0, abs(float(fw[-1])))
+        np.testing.assert_allclose(out[k], [float(l.split("\t")[-1]) for l in want[1:]], rtol=1e-6, atol=1e-6)
+
+
+def test_score_norm_unknown_row_raises():
+    from neuralplda_b200 import adaptive_score_normalization as asn
+    stats = asn.cohort_statistics(torch.randn(4, 64, device=DEV), 10)
+    raw = torch.randn(5, device=DEV)
+    with pytest.raises(KeyError):
+        asn.normalize_scores(raw, torch.tensor([0, 1, 2, 3, 4], device=DEV), torch.zeros(5, dtype=torch.int64, device=DEV), stats)
+
+
+def test_cohort_grid_scoring_feeds_normalisation(kaldi_params):
+    """End to end on the device: id x cohort grid through the embed-once kernel -> statistics -> normalised
+    trial scores, against the oracle fed with the oracle's own scores (1e-3: score parity 1e-4 divided by std)."""
+    from neuralplda_b200 import adaptive_score_normalization as asn
+    kp = kaldi_params
+    table, _, _, _ = O.synth_grid(30, 620, 25, seed=11, mean=kp["mean"])      # rows 0..29 ids, 30..649 cohort
+    m = make_nplda(kp)
+    ids, coh = torch.arange(30), torch.arange(30, 650)
+    S = asn.score_cohort(m, table.to(DEV), ids.to(DEV), coh.to(DEV), batch_ids=7)
+    with torch.no_grad():
+        y = O.nplda_embed(table, kp["W1"], kp["b1"], kp["W2"], kp["b2"])
+        Sref = O.nplda_score_from_embeddings(y[ids].repeat_interleave(620, 0), y[coh].repeat(30, 1), kp["P_sqrt"], kp["Q"]).view(30, 620)
+    ok, worst = parity_ok(S.cpu().flatten(), Sref.flatten(), rel=1e-4)
+    assert ok, worst
+    e, t = torch.arange(0, 15).repeat(4), torch.arange(15, 30).repeat_interleave(4)
+    raw, _ = m.forward_indexed(table.to(DEV), e.to(DEV), t.to(DEV))
+    got = asn.normalize_scores(raw, e.to(DEV), t.to(DEV), asn.cohort_statistics(S, 500)).cpu().numpy()
+    want = O.score_norm(raw.cpu().numpy(), e.numpy(), t.numpy(), O.cohort_stats(Sref.numpy(), 500))
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-3)

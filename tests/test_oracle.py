@@ -160,3 +160,25 @@ def test_gather_and_scorefile_formats(ref_out, kaldi_params):
         assert (e, tst) == (tr[0], tr[1])
         assert float(val) == pytest.approx(sc, rel=2e-5, abs=2e-6)
     assert O.format_scores(np.float32([0.5]))[0] == "0.5"
+
+
+def _read_norm_golden():
+    raw = np.genfromtxt(os.path.join(GOLDEN, "c7_raw_scores.tsv"), dtype=str)[1:]
+    coh = np.genfromtxt(os.path.join(GOLDEN, "c7_cohort_scores.tsv"), dtype=str, skip_header=1)
+    c = len(np.unique(coh[:, 1]))
+    ids = list(coh[:, 0].reshape(-1, c)[:, 0])
+    mat = coh[:, -1].astype(float).reshape(-1, c)
+    er = np.asarray([ids.index(e) for e in raw[:, 0]])
+    tr = np.asarray([ids.index(t.replace(".sph", "")) for t in raw[:, 1]])
+    want = np.stack([np.genfromtxt(os.path.join(GOLDEN, "c7_raw_scores.tsv_%s.tsv" % n), dtype=str)[:, -1].astype(float)
+                     for n in ("znorm", "tnorm", "snorm", "asnorm1")])
+    return raw[:, -1].astype(float), er, tr, mat, want
+
+
+def test_score_normalisation_matches_reference_script():
+    """oracle vs the four files the unmodified adaptive_score_normalization.py wrote
+    (tests/golden/make_golden_norm.py); float64 throughout, so 1e-12 relative."""
+    raw, er, tr, mat, want = _read_norm_golden()
+    assert mat.shape[1] > 500                                   # the top-N slice is a strict subset
+    got = O.score_norm(raw, er, tr, O.cohort_stats(mat, 500))
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)

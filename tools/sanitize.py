@@ -1,0 +1,29 @@
+"""Small run of every forward kernel family for compute-sanitizer (memcheck): TC (both modes, incl. the guarded
+fallback), SIMT, indexed, embed-once pair scoring, losses, backward."""
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import neuralplda_b200 as npl
+from oracle import nplda_oracle as O
+import bench
+dev = torch.device("cuda:0")
+kp = bench.kaldi_params()
+m = npl.NeuralPlda(bench.NC).to(dev)
+sd = m.state_dict()
+for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias", "b1"), ("centering_and_wccn_plda.weight", "W2"),
+                  ("centering_and_wccn_plda.bias", "b2"), ("P_sqrt", "P_sqrt"), ("Q", "Q")):
+    sd[name].copy_(kp[key])
+x1, x2, t = O.synth_pairs(20000 + 37, 50, seed=3, mean=kp["mean"])
+a, b, y = x1.to(dev), x2.to(dev), t.to(dev)
+for impl in (npl.IMPL_TC, npl.IMPL_TC_F8, npl.IMPL_SIMT):
+    m.impl = impl
+    with torch.no_grad():
+        s = m(a, b); s2 = m(a * 1000, b * 1000)
+    print("impl", impl, float(s.sum()), float(s2.sum()))
+m.impl = npl.IMPL_AUTO
+loss = m.loss(m(a[:4096], b[:4096]), y[:4096]); loss.backward()
+table, i1, i2, _ = O.synth_grid(40, 50, 7, seed=2, mean=kp["mean"])
+s, f = m.forward_indexed(table.to(dev), i1.to(dev), i2.to(dev))
+s, f = m.forward_indexed(table.to(dev), i1.to(dev), i2.to(dev), embed_once=False)
+print("minc", m.minc(m(a[:4096], b[:4096]).detach(), y[:4096])[0].item())
+torch.cuda.synchronize()
+print("sanitize run ok")
