@@ -138,6 +138,16 @@ int nplda_table_prepare(const float *table, int64_t n_rows, int d_in, int d1, in
                         int is_dplda, float *rowtab, void *stream);
 int nplda_score_pairs(const float *rowtab, int64_t n_rows, const int64_t *idx1, const int64_t *idx2,
                       int64_t n, float *scores, int32_t *bad_index_flag, void *stream);
+/* nplda_score_grid: the full enrol x test grid of a trial list (BASELINE.json configs[2]/[3];
+ * the id x cohort matrix utils/adaptive_score_normalization.py:32 reads) as one
+ * [n_enrol,176] x [176,n_test] fp32 product over the row table:
+ * scores[i * ld_scores + j] = S(enrol_rows[i], test_rows[j]), ld_scores >= n_test
+ * (enrol-major trial order).  4 bytes of HBM traffic per trial instead of 20 + two
+ * row gathers.  Rows outside [0, n_rows) set *bad_index_flag; their row / column of
+ * the grid scores 0. */
+int nplda_score_grid(const float *rowtab, int64_t n_rows, const int64_t *enrol_rows, int64_t n_enrol,
+                     const int64_t *test_rows, int64_t n_test, float *scores, int64_t ld_scores,
+                     int32_t *bad_index_flag, void *stream);
 
 /* ---------------------------------------------------------------------------
  * K2: loss / detection-cost accumulators.

@@ -7,7 +7,7 @@ utils/adaptive_score_normalization.py (a top-level script with hard-coded paths)
             asnorm1 = ((s - mean_top[e]) / std_top[e] + (s - mean_top[t]) / std_top[t]) / 2   (float64)
 
 Device kernels: csrc/norm.cu (`nplda_cohort_stats`, `nplda_score_norm`); the id x cohort score matrix comes from
-the embed-once trial-list kernel (`model.forward_indexed`).  GPU only, like the rest of the package.
+the grid kernel over rows embedded once (`model.forward_grid`).  GPU only, like the rest of the package.
 """
 from __future__ import annotations
 
@@ -61,21 +61,13 @@ def normalize_scores(raw_scores, enrol_rows, test_rows, stats):
     return out
 
 
-def score_cohort(model, table, id_rows, cohort_rows, batch_ids=4096):
+def score_cohort(model, table, id_rows, cohort_rows):
     """The [ids, cohort] score matrix the script reads from its cohort score file: every id row of `table`
-    against every cohort row, through the embed-once trial-list kernel (rows are transformed once)."""
-    require_cuda(table, id_rows, cohort_rows)
-    id_rows = id_rows.to(torch.int64)
-    cohort_rows = cohort_rows.to(torch.int64)
-    c = cohort_rows.numel()
-    out = torch.empty(id_rows.numel(), c, dtype=torch.float32, device=table.device)
-    with torch.no_grad():
-        for i in range(0, id_rows.numel(), batch_ids):
-            ids = id_rows[i:i + batch_ids]
-            s, flag = model.forward_indexed(table, ids.repeat_interleave(c), cohort_rows.repeat(ids.numel()),
-                                            embed_once=True)
-            out[i:i + ids.numel()] = s.view(-1, c)
-    return out
+    against every cohort row, one grid product over rows that are transformed once (model.forward_grid)."""
+    scores, flag = model.forward_grid(table, id_rows, cohort_rows)
+    if scores.numel() and int(flag.item()):
+        raise KeyError("an id or cohort row lies outside the x-vector table")
+    return scores
 
 
 def normalize_score_file(raw_score_filename, cohort_score_filename, device="cuda", top_n=ASnorm_topN):

@@ -255,6 +255,33 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
     return scores, flag
 
 
+def score_grid(kind, table, enrol_rows, test_rows, params, dims, packed):
+    """[E, T] scores of every enrol row against every test row of `table` (enrol-major trial order): the row
+    table of nplda_table_prepare (cached like in score_indexed) and one fp32 grid product (nplda_score_grid)."""
+    require_cuda(table, enrol_rows, test_rows)
+    d_in, d1, d2 = dims
+    if table.dim() != 2 or table.shape[1] != d_in:
+        raise RuntimeError(f"table must be [rows, {d_in}]")
+    if max(d1, d2) >= 176:
+        raise RuntimeError("grid scoring supports layer widths up to 175")
+    table = _f32c(table)
+    er = enrol_rows.to(torch.int64).contiguous()
+    tr = test_rows.to(torch.int64).contiguous()
+    if er.dim() != 1 or tr.dim() != 1:
+        raise RuntimeError("enrol_rows and test_rows must be 1-D")
+    dev = table.device
+    scores = torch.empty(er.numel(), tr.numel(), dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if scores.numel():
+        if table.shape[0] == 0:
+            raise RuntimeError("empty x-vector table")
+        rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
+        with torch.cuda.device(dev):
+            check(lib().nplda_score_grid(ptr(rowtab), table.shape[0], ptr(er), er.numel(), ptr(tr), tr.numel(),
+                                         ptr(scores), tr.numel(), ptr(flag), stream_ptr()), "nplda_score_grid")
+    return scores, flag
+
+
 # ------------------------------------------------------------------------------
 # Losses
 # ------------------------------------------------------------------------------

@@ -190,6 +190,12 @@ class NeuralPlda(_PldaBase):
                                             self.packed, self.impl, embed_once)
         return scores, flag
 
+    def forward_grid(self, table, enrol_rows, test_rows):
+        """[E, T] scores of every enrol row against every test row of a device-resident x-vector table
+        (enrol-major, the order of an enrol x test trial list); no gradient.  Returns (scores, bad_index_flag)."""
+        with torch.no_grad():
+            return F_.score_grid("nplda", table, enrol_rows, test_rows, self._params(), self._dims(), self.packed)
+
     # The two half-steps of forward are part of the reference's public surface (models.py:366-376).
     # No reference call site uses them separately (forward is the hot path and never materialises
     # embeddings); they are served by the fp32 kernels and are not differentiable here.
@@ -239,6 +245,12 @@ class DPlda(_PldaBase):
             scores, flag = F_.score_indexed("dplda", table, idx1, idx2, self._params(), self._dims(),
                                             self.packed, self.impl, embed_once)
         return scores, flag
+
+    def forward_grid(self, table, enrol_rows, test_rows):
+        """[E, T] scores of every enrol row against every test row of a device-resident x-vector table
+        (enrol-major, the order of an enrol x test trial list); no gradient.  Returns (scores, bad_index_flag)."""
+        with torch.no_grad():
+            return F_.score_grid("dplda", table, enrol_rows, test_rows, self._params(), self._dims(), self.packed)
 
     def extract_plda_embeddings(self, x):
         return F_.embed("dplda", x, self._params(), self._dims(), self.packed)

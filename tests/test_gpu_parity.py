@@ -626,7 +626,7 @@ def test_cohort_grid_scoring_feeds_normalisation(kaldi_params):
     table, _, _, _ = O.synth_grid(30, 620, 25, seed=11, mean=kp["mean"])      # rows 0..29 ids, 30..649 cohort
     m = make_nplda(kp)
     ids, coh = torch.arange(30), torch.arange(30, 650)
-    S = asn.score_cohort(m, table.to(DEV), ids.to(DEV), coh.to(DEV), batch_ids=7)
+    S = asn.score_cohort(m, table.to(DEV), ids.to(DEV), coh.to(DEV))
     with torch.no_grad():
         y = O.nplda_embed(table, kp["W1"], kp["b1"], kp["W2"], kp["b2"])
         Sref = O.nplda_score_from_embeddings(y[ids].repeat_interleave(620, 0), y[coh].repeat(30, 1), kp["P_sqrt"], kp["Q"]).view(30, 620)
@@ -637,3 +637,79 @@ def test_cohort_grid_scoring_feeds_normalisation(kaldi_params):
     got = asn.normalize_scores(raw, e.to(DEV), t.to(DEV), asn.cohort_statistics(S, 500)).cpu().numpy()
     want = O.score_norm(raw.cpu().numpy(), e.numpy(), t.numpy(), O.cohort_stats(Sref.numpy(), 500))
     np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------
+# Grid scoring (nplda_score_grid): enrol x test grids without an index pair per trial
+# ------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("kind", ["nplda", "dplda"])
+@pytest.mark.parametrize("ne,nt", [(1, 1), (61, 83), (128, 128), (129, 257), (300, 7)])
+def test_grid_scoring_vs_oracle(ref_out, kaldi_params, kind, ne, nt):
+    """Every enrol row against every test row, ragged tile tails and odd leading dimensions (scalar-store path),
+    both models, against the oracle on the gathered pairs (1e-4) and against the trial-list kernel."""
+    kp = kaldi_params
+    table, i1, i2, _ = O.synth_grid(ne, nt, 17, seed=2000 + ne, mean=kp["mean"])
+    if kind == "nplda":
+        m = make_nplda(kp)
+        ref = O.nplda_score(table[i1], table[i2], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    else:
+        m = make_dplda(kp, ref_out)
+        w, c = dplda_weights(ref_out)
+        ref = O.dplda_score(table[i1], table[i2], kp["W1"], kp["b1"], w, c)
+    t = table.to(DEV)
+    er, tr = torch.arange(ne, device=DEV), torch.arange(ne, ne + nt, device=DEV)
+    assert torch.equal(i1.view(ne, nt)[:, 0], er.cpu()) and torch.equal(i2.view(ne, nt)[0], tr.cpu())
+    s, flag = m.forward_grid(t, er, tr)
+    assert s.shape == (ne, nt) and int(flag.item()) == 0
+    ok, worst = parity_ok(s.flatten(), ref, rel=1e-4)
+    assert ok, worst
+    s_list, _ = m.forward_indexed(t, i1.to(DEV), i2.to(DEV), embed_once=True)
+    ok, worst = parity_ok(s.flatten(), s_list.cpu(), rel=2e-5)         # same rows, 170-term fp32 sums in another order
+    assert ok, worst
+    # permuted / repeated rows select the same scores
+    perm_e, perm_t = torch.randperm(ne, device=DEV), torch.randint(0, nt, (nt + 3,), device=DEV)
+    s2, _ = m.forward_grid(t, er[perm_e], tr[perm_t])
+    assert torch.equal(s2, s[perm_e][:, perm_t])
+
+
+def test_grid_scoring_bad_rows_and_empty(kaldi_params):
+    kp = kaldi_params
+    table, _, _, _ = O.synth_grid(20, 30, 5, seed=9, mean=kp["mean"])
+    m = make_nplda(kp)
+    t = table.to(DEV)
+    er, tr = torch.arange(20, device=DEV), torch.arange(20, 50, device=DEV)
+    good, _ = m.forward_grid(t, er, tr)
+    er_bad = er.clone(); er_bad[3] = 50                                   # one past the table
+    tr_bad = tr.clone(); tr_bad[7] = -1
+    s, flag = m.forward_grid(t, er_bad, tr_bad)
+    assert int(flag.item()) != 0
+    assert torch.all(s[3] == 0) and torch.all(s[:, 7] == 0)
+    keep_e, keep_t = [i for i in range(20) if i != 3], [j for j in range(30) if j != 7]
+    assert torch.equal(s[keep_e][:, keep_t], good[keep_e][:, keep_t])
+    s0, _ = m.forward_grid(t, er[:0], tr)
+    assert s0.shape == (0, 30)
+    with pytest.raises(RuntimeError):
+        m.forward_grid(table, er, tr)                                      # CPU table: no fallback
+
+
+def test_config3_10m_grid_kernel(kaldi_params):
+    """BASELINE.json configs[2] through the grid kernel: 2500 x 4000 = 10M trials; oracle on a strided subsample,
+    agreement with the trial-list kernel on every trial, symmetry S(i,j) = S(j,i) via the transposed grid."""
+    kp = kaldi_params
+    table, i1, i2, lab = O.synth_grid(2500, 4000, 500, seed=1003, mean=kp["mean"])
+    m = make_nplda(kp)
+    t = table.to(DEV)
+    er, tr = torch.arange(2500, device=DEV), torch.arange(2500, 6500, device=DEV)
+    s, flag = m.forward_grid(t, er, tr)
+    assert int(flag.item()) == 0 and s.shape == (2500, 4000)
+    sub = torch.arange(0, s.numel(), 1009)
+    ref = O.nplda_score(table[i1[sub]], table[i2[sub]], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    ok, worst = parity_ok(s.flatten()[sub.to(DEV)], ref, rel=1e-4)
+    assert ok, worst
+    s_list, _ = m.forward_indexed(t, i1.to(DEV), i2.to(DEV))
+    ok, worst = parity_ok(s.flatten(), s_list.cpu(), rel=2e-5)
+    assert ok, worst
+    st, _ = m.forward_grid(t, tr, er)
+    np.testing.assert_allclose(st.t().cpu().numpy(), s.cpu().numpy(), rtol=1e-5, atol=1e-6)
