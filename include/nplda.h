@@ -61,22 +61,34 @@ int64_t nplda_launch_count(void);
 /* ---------------------------------------------------------------------------
  * Packed weights.  The score kernels consume the affine layers transposed
  * (k-major), zero-padded and, for the tensor-core path, split into bf16 hi/lo
- * images in the tcgen05 shared-memory layout.  Packing is one small kernel; it
- * must be re-run whenever the parameters change (every optimiser step).
- * nplda_pack_bytes() gives the workspace size for given dims.
+ * images in the tcgen05 shared-memory layout.  Packing is three small kernels
+ * (~6 us); it must be re-run whenever the parameters may have changed -- the
+ * Python layer re-packs on every call, because neither `.data.copy_()` (the
+ * reference's own idiom, models.py:449-457, :420) nor fused optimisers bump
+ * tensor._version.  nplda_pack_bytes() gives the workspace size for given dims;
+ * ZERO the workspace once when it is allocated.
+ * flags: NPLDA_PACK_MIXED also builds the layer-1 image of NPLDA_IMPL_TC_F8
+ * (two more kernels; without it that impl falls back to NPLDA_IMPL_TC on the
+ * device); NPLDA_PACK_EPOCH_ODD selects which of the two fingerprint slots this
+ * call fills -- alternate it between successive packs of one workspace.  The
+ * fingerprint (a 64-bit content hash of the packed parameters) is what
+ * nplda_table_prepare(NPLDA_PREPARE_IF_CHANGED) validates a cached row table
+ * against, on the device.
  * ------------------------------------------------------------------------- */
+#define NPLDA_PACK_MIXED 1
+#define NPLDA_PACK_EPOCH_ODD 2
 int64_t nplda_pack_bytes(int d_in, int d1, int d2);
 
 /* NeuralPlda parameters (models.py:349-363): W1 [d1,d_in], b1 [d1], W2 [d2,d1],
  * b2 [d2], P_sqrt [d2], Q [d2]. */
 int nplda_pack_weights(const float *W1, const float *b1, const float *W2, const float *b2,
                        const float *p_sqrt, const float *q, int d_in, int d1, int d2,
-                       void *pack, int64_t pack_bytes, void *stream);
+                       void *pack, int64_t pack_bytes, int flags, void *stream);
 
 /* DPlda parameters (models.py:464-476): W1 [d1,d_in], b1 [d1],
  * logistic_regres.weight [2*d1*d1+d1], logistic_regres.bias [1]. */
 int dplda_pack_weights(const float *W1, const float *b1, const float *w_lr, const float *c_lr,
-                       int d_in, int d1, void *pack, int64_t pack_bytes, void *stream);
+                       int d_in, int d1, void *pack, int64_t pack_bytes, int flags, void *stream);
 
 /* ---------------------------------------------------------------------------
  * K1: fused score forward.
@@ -120,6 +132,13 @@ int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *i
                             const int64_t *idx2, int64_t n, int d_in, int d1, const void *pack,
                             float *scores, int32_t *bad_index_flag, int impl, void *stream);
 
+/* Batch gather alone (the device half of load_xvec_trials_from_numbatch / _from_idbatch,
+ * sv_trials_loaders.py:418-437, for callers that want the materialised [n, d] pair the
+ * reference's training loop passes to forward): x1[t] = table[idx1[t]], x2[t] = table[idx2[t]].
+ * Rows outside [0, n_rows) set *bad_index_flag (device or pinned host memory) and are zero-filled. */
+int nplda_gather_pairs(const float *table, int64_t n_rows, int d, const int64_t *idx1, const int64_t *idx2,
+                       int64_t n, float *x1, float *x2, int32_t *bad_index_flag, void *stream);
+
 /* ---------------------------------------------------------------------------
  * Trial-list scoring with every utterance transformed ONCE.
  * Replaces the per-batch gather + double forward of the scoring loop
@@ -129,13 +148,19 @@ int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *i
  * per-utterance rows (NeuralPlda: A = y, B = 2 P_sqrt^2 y, r = sum Q y^2;
  * DPlda: A = u, B = (Wb + Wb^T) u, r = u^T Ww u + ws.u + c/2).
  * nplda_table_prepare: table [n_rows, d_in] fp32 -> rowtab (nplda_rowtab_bytes(n_rows)
- * bytes, caller-owned); re-run when the table or the parameters change.
+ * bytes, caller-owned); re-run when the table or the parameters change.  flags:
+ * NPLDA_PACK_EPOCH_ODD as given to the pack call that filled `pack`;
+ * NPLDA_PREPARE_IF_CHANGED makes the call a device-side no-op (three empty
+ * launches) when rowtab was built by an earlier call from a pack with the same
+ * parameter fingerprint -- pass it when the same table is scored again, so that
+ * "pack + prepare" can precede every scoring call.
  * nplda_score_pairs: scores[t] = S(idx1[t], idx2[t]); indices outside [0, n_rows)
  * set *bad_index_flag and score 0, never a fault.  Layer widths up to 175.
  * ------------------------------------------------------------------------- */
 int64_t nplda_rowtab_bytes(int64_t n_rows);
+#define NPLDA_PREPARE_IF_CHANGED 1
 int nplda_table_prepare(const float *table, int64_t n_rows, int d_in, int d1, int d2, const void *pack,
-                        int is_dplda, float *rowtab, void *stream);
+                        int is_dplda, float *rowtab, int flags, void *stream);
 int nplda_score_pairs(const float *rowtab, int64_t n_rows, const int64_t *idx1, const int64_t *idx2,
                       int64_t n, float *scores, int32_t *bad_index_flag, void *stream);
 /* nplda_score_grid: the full enrol x test grid of a trial list (BASELINE.json configs[2]/[3];

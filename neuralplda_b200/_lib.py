@@ -19,6 +19,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8 = 0, 1, 2, 3
 LOSS_SOFTCDET, LOSS_CROSSENTROPY = 0, 1
+PACK_MIXED, PACK_EPOCH_ODD, PREPARE_IF_CHANGED = 1, 2, 1
 MAX_BETAS = 8
 
 _lib = None
@@ -35,16 +36,17 @@ SIGNATURES = {
     "nplda_error_string": (ctypes.c_char_p, [c_int]),
     "nplda_launch_count": (c_i64, []),
     "nplda_pack_bytes": (c_i64, [c_int, c_int, c_int]),
-    "nplda_pack_weights": (c_int, [c_vp] * 6 + [c_int] * 3 + [c_vp, c_i64, c_vp]),
-    "dplda_pack_weights": (c_int, [c_vp] * 4 + [c_int] * 2 + [c_vp, c_i64, c_vp]),
+    "nplda_pack_weights": (c_int, [c_vp] * 6 + [c_int] * 3 + [c_vp, c_i64, c_int, c_vp]),
+    "dplda_pack_weights": (c_int, [c_vp] * 4 + [c_int] * 2 + [c_vp, c_i64, c_int, c_vp]),
     "nplda_score_fwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "dplda_score_fwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "nplda_score_fwd_indexed": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp,
                                         c_vp, c_int, c_vp]),
     "dplda_score_fwd_indexed": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
                                         c_int, c_vp]),
+    "nplda_gather_pairs": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "nplda_rowtab_bytes": (c_i64, [c_i64]),
-    "nplda_table_prepare": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
+    "nplda_table_prepare": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "nplda_score_pairs": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nplda_embed_fwd": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "nplda_score_from_embeddings": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -119,8 +121,33 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """The current stream of the current device as a void* (the raw-handle query avoids building a Stream object
+    per launch; the small-batch training loop of the reference is bound by such host costs)."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(dev):
+    """Context that makes `dev` the current CUDA device; free when it already is."""
+    if dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NO_GUARD
+    return torch.cuda.device(dev)
 
 
 def require_cuda(*tensors):

@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ._lib import check, lib, ptr, require_cuda, stream_ptr
+from ._lib import check, lib, on_device, ptr, require_cuda, stream_ptr
 from .textio import TrialFile
 
 ASnorm_topN = 500                                     # adaptive_score_normalization.py:12
@@ -31,7 +31,7 @@ def cohort_statistics(cohort_scores, top_n=ASnorm_topN):
         raise RuntimeError("top_n must be positive")
     x = cohort_scores.to(torch.float32).contiguous()
     stats = torch.empty(x.shape[0], 4, dtype=torch.float64, device=x.device)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         check(lib().nplda_cohort_stats(ptr(x), x.shape[0], x.shape[1], int(top_n), ptr(stats), stream_ptr()),
               "nplda_cohort_stats")
     return stats
@@ -53,7 +53,7 @@ def normalize_scores(raw_scores, enrol_rows, test_rows, stats):
     n = raw.numel()
     out = torch.empty(4, n, dtype=torch.float64, device=raw.device)
     flag = torch.zeros(1, dtype=torch.int32, device=raw.device)
-    with torch.cuda.device(raw.device):
+    with on_device(raw.device):
         check(lib().nplda_score_norm(ptr(raw), ptr(er), ptr(tr), n, ptr(stats), stats.shape[0], ptr(out), ptr(flag),
                                      stream_ptr()), "nplda_score_norm")
     if n and int(flag.item()):

@@ -31,7 +31,8 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
              float *scores, int mode, cudaStream_t st);   // score_tc.cu
 
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
-             float *out, int64_t ld_out, cudaStream_t st);   // score_simt.cu
+             float *out, int64_t ld_out, cudaStream_t st, const unsigned long long *fp_cur = nullptr,
+             const unsigned long long *fp_built = nullptr);   // score_simt.cu
 
 // S = sum_k Q y1^2 + Q y2^2 + 2 P_sqrt^2 y1 y2 from materialised embeddings (models.py:372-376): one warp per pair
 __global__ void __launch_bounds__(256) score_from_emb_kernel(const float *__restrict__ y1, const float *__restrict__ y2,

@@ -25,6 +25,7 @@ struct PackLayout {
     int64_t p;     // [NP]            P = P_sqrt^2
     int64_t q;     // [NP]
     int64_t c;     // [4]             DPlda constant (logistic_regres.bias)
+    int64_t fp;    // 2 x u64         content fingerprint of the packed parameters, slot = pack epoch parity (pack.cu)
     int64_t tc;    // tensor-core images (bf16 hi/lo, tcgen05 smem layout), see score_tc.cu
     int64_t tc_bytes;
     int64_t total;
@@ -47,6 +48,7 @@ inline PackLayout make_pack_layout(int d_in, int d1, int d2) {
     L.p = take(NP * 4);
     L.q = take(NP * 4);
     L.c = take(16);
+    L.fp = take(16);
     L.tc_bytes = tc_image_bytes(d_in, d1, d2);
     L.tc = take(L.tc_bytes);
     L.total = o;

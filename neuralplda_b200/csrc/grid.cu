@@ -40,7 +40,8 @@ struct Args {
 __global__ void __launch_bounds__(NT, 2) score_grid_kernel(Args g) {
     __shared__ __align__(16) float As[2 * A_STAGE];
     __shared__ __align__(16) float Bs[2 * B_STAGE];
-    __shared__ float re[TM], rt[TN];                     // r of the tile's rows / columns; NaN marks a bad index
+    __shared__ float re[TM], rt[TN];                     // r of the tile's rows / columns
+    __shared__ unsigned char bade[TM], badt[TN];         // index outside the table
     __shared__ int64_t eoff[TM], toff[TN];               // float offsets of the rows in the table
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(NT, 2) score_grid_kernel(Args g) {
         const bool bad = r < 0 || r >= g.n_rows;
         if (bad) { *g.bad_flag = 1; r = 0; }
         eoff[tid] = r * ROW_FLOATS;
-        re[tid] = bad ? __int_as_float(0x7fc00000) : g.rowtab[r * ROW_FLOATS + ROW_LD - 1];
+        bade[tid] = bad;
+        re[tid] = g.rowtab[r * ROW_FLOATS + ROW_LD - 1];
     } else {
         const int t = tid - TM;
         const int64_t j = min(j0 + t, g.nt - 1);
@@ -61,7 +63,8 @@ __global__ void __launch_bounds__(NT, 2) score_grid_kernel(Args g) {
         const bool bad = r < 0 || r >= g.n_rows;
         if (bad) { *g.bad_flag = 1; r = 0; }
         toff[t] = r * ROW_FLOATS;
-        rt[t] = bad ? __int_as_float(0x7fc00000) : g.rowtab[r * ROW_FLOATS + ROW_LD - 1];
+        badt[t] = bad;
+        rt[t] = g.rowtab[r * ROW_FLOATS + ROW_LD - 1];
     }
     __syncthreads();
 
@@ -99,15 +102,13 @@ __global__ void __launch_bounds__(NT, 2) score_grid_kernel(Args g) {
     store_b(b0, b1, 0);
     for (int c = 0; c < NCH; ++c) {
         const int s = c & 1;
-        if (c + 1 < NCH) {
+        cp_async_wait<0>();
+        __syncthreads();                                 // chunk c has landed; everyone is done reading stage s ^ 1
+        if (c + 1 < NCH) {                               // refill stage s ^ 1 behind the barrier, under this chunk's math
             load_a(c + 1, s ^ 1);
             b0 = *reinterpret_cast<const float4 *>(bsrc + (c + 1) * KG);
             b1 = *reinterpret_cast<const float4 *>(bsrc + (c + 1) * KG + 4);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
-        __syncthreads();
         if (c == NCH - 1) {                              // A[ROW_LD - 1] holds r, not a factor of the dot product
             if (tid < TM) As[s * A_STAGE + tid * LDA + KG - 1] = 0.f;
             __syncthreads();
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(NT, 2) score_grid_kernel(Args g) {
                 }
             }
         }
-        if (c + 1 < NCH) store_b(b0, b1, s ^ 1);         // the other stage was last read before this chunk's barrier
+        if (c + 1 < NCH) store_b(b0, b1, s ^ 1);         // stage s ^ 1 was last read before this chunk's barrier
     }
 
     // S = A.B + r_e + r_t; a bad row or column scores 0 (the flag is set), like nplda_score_pairs
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(NT, 2) score_grid_kernel(Args g) {
         const int64_t gi = i0 + m;
         if (gi >= g.ne) continue;
         const float r1 = re[m];
+        const bool b1 = bade[m];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int n = 4 * tx + 64 * j;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(NT, 2) score_grid_kernel(Args g) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 v[e] += r1 + rt[n + e];
-                if (r1 != r1 || rt[n + e] != rt[n + e]) v[e] = 0.f;
+                if (b1 || badt[n + e]) v[e] = 0.f;
             }
             float *dst = g.out + gi * g.ld + gj;
             if (g.vec_store && gj + 3 < g.nt) {

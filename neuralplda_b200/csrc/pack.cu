@@ -5,65 +5,98 @@
 namespace nplda {
 
 int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float *b2,
-                  const float *p_sqrt, const float *q, const PackLayout &L, char *pack,
+                  const float *p_sqrt, const float *q, const PackLayout &L, char *pack, int flags,
                   cudaStream_t st);   // score_tc.cu
 int tc_pack_dplda(const float *W1, const float *b1, const float *w_lr, const float *c_lr,
                   const PackLayout &L, char *pack, cudaStream_t st);   // score_tc.cu
 
-// out[k][n] = W[n][k] for n < N, k < K, else 0.   out is [Kp][NP].
-__device__ __forceinline__ void put_wt(float *out, const float *W, int N, int K, int ldw, int64_t e) {
-    int k = (int)(e / NP), n = (int)(e % NP);
-    out[e] = (n < N && k < K) ? W[(int64_t)n * ldw + k] : 0.f;
+// Content fingerprint of the packed parameters.  Callers cannot be trusted to say when parameters changed:
+// the reference itself writes them through `.data.copy_()` (models.py:449-457, :420) and fused optimisers update
+// them without touching tensor._version, so the Python layer re-packs on every call and anything CACHED beyond
+// the pack (the per-utterance row table of pairs.cu) is validated on the device against this value: the sum
+// over every packed element e of (bits(e) + c) * (2 pos(e) + 1) * odd  (mod 2^64) -- a change of any single
+// element always changes it.  Two slots: a pack call adds into slot (flags >> 1) & 1 and clears the other one
+// for the next call (stream order makes that safe; the buffer must be zeroed once when it is allocated).
+__device__ __forceinline__ unsigned long long fp_term(float v, int64_t pos) {
+    return ((unsigned long long)__float_as_uint(v) + 0x9E3779B9ull) * (2ull * (unsigned long long)pos + 1ull) *
+           0x9E3779B97F4A7C15ull;
 }
-__device__ __forceinline__ void put_vec(float *out, const float *v, int N, int n, bool square) {
+__device__ __forceinline__ void fp_commit(unsigned long long h, unsigned long long *slots, int parity) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(slots + parity, h);
+    if (blockIdx.x == 0 && threadIdx.x == 0) slots[parity ^ 1] = 0ull;
+}
+
+// out[k][n] = W[n][k] for n < N, k < K, else 0.   out is [Kp][NP].
+__device__ __forceinline__ float put_wt(float *out, const float *W, int N, int K, int ldw, int64_t e) {
+    int k = (int)(e / NP), n = (int)(e % NP);
+    const float v = (n < N && k < K) ? W[(int64_t)n * ldw + k] : 0.f;
+    out[e] = v;
+    return v;
+}
+__device__ __forceinline__ float put_vec(float *out, const float *v, int N, int n, bool square) {
     float x = (v != nullptr && n < N) ? v[n] : 0.f;
     out[n] = square ? x * x : x;
+    return x;
 }
 
 __global__ void pack_nplda_kernel(const float *__restrict__ W1, const float *__restrict__ b1,
                                   const float *__restrict__ W2, const float *__restrict__ b2,
                                   const float *__restrict__ p_sqrt, const float *__restrict__ q,
-                                  PackLayout L, char *pack) {
+                                  PackLayout L, char *pack, int parity) {
     const int64_t n1 = (int64_t)L.k1p * NP, n2 = (int64_t)L.k2p * NP;
     const int64_t total = n1 + n2 + 4 * NP;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+    const int64_t span = ((total + blockDim.x - 1) / blockDim.x) * blockDim.x;      // whole warps reach fp_commit
+    unsigned long long h = 0ull;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < span;
          e += (int64_t)gridDim.x * blockDim.x) {
+        if (e >= total) continue;
+        float v = 0.f;
         if (e < n1) {
-            put_wt((float *)(pack + L.w1t), W1, L.d1, L.d_in, L.d_in, e);
+            v = put_wt((float *)(pack + L.w1t), W1, L.d1, L.d_in, L.d_in, e);
         } else if (e < n1 + n2) {
-            put_wt((float *)(pack + L.w2t), W2, L.d2, L.d1, L.d1, e - n1);
+            v = put_wt((float *)(pack + L.w2t), W2, L.d2, L.d1, L.d1, e - n1);
         } else {
             int r = (int)(e - n1 - n2), which = r / NP, n = r % NP;
-            if (which == 0) put_vec((float *)(pack + L.b1), b1, L.d1, n, false);
-            if (which == 1) put_vec((float *)(pack + L.b2), b2, L.d2, n, false);
-            if (which == 2) put_vec((float *)(pack + L.p), p_sqrt, L.d2, n, true);   // P = P_sqrt^2 (models.py:373)
-            if (which == 3) put_vec((float *)(pack + L.q), q, L.d2, n, false);
+            if (which == 0) v = put_vec((float *)(pack + L.b1), b1, L.d1, n, false);
+            if (which == 1) v = put_vec((float *)(pack + L.b2), b2, L.d2, n, false);
+            if (which == 2) v = put_vec((float *)(pack + L.p), p_sqrt, L.d2, n, true);   // P = P_sqrt^2 (models.py:373)
+            if (which == 3) v = put_vec((float *)(pack + L.q), q, L.d2, n, false);
         }
+        h += fp_term(v, e);
     }
+    fp_commit(h, (unsigned long long *)(pack + L.fp), parity);
 }
 
 // logistic_regres.weight = [ vec(Wb) | vec(Ww) | ws ]  (cat order of models.py:487)
 __global__ void pack_dplda_kernel(const float *__restrict__ W1, const float *__restrict__ b1,
                                   const float *__restrict__ w_lr, const float *__restrict__ c_lr,
-                                  PackLayout L, char *pack) {
+                                  PackLayout L, char *pack, int parity) {
     const int Ld = L.d1;
     const int64_t n1 = (int64_t)L.k1p * NP, n2 = (int64_t)L.k2p * NP;
     const int64_t total = n1 + 2 * n2 + 2 * NP + 1;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+    const int64_t span = ((total + blockDim.x - 1) / blockDim.x) * blockDim.x;
+    unsigned long long h = 0ull;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < span;
          e += (int64_t)gridDim.x * blockDim.x) {
+        if (e >= total) continue;
+        float v;
         if (e < n1) {
-            put_wt((float *)(pack + L.w1t), W1, L.d1, L.d_in, L.d_in, e);
+            v = put_wt((float *)(pack + L.w1t), W1, L.d1, L.d_in, L.d_in, e);
         } else if (e < n1 + n2) {
-            put_wt((float *)(pack + L.w2t), w_lr + (int64_t)Ld * Ld, Ld, Ld, Ld, e - n1);        // Ww
+            v = put_wt((float *)(pack + L.w2t), w_lr + (int64_t)Ld * Ld, Ld, Ld, Ld, e - n1);        // Ww
         } else if (e < n1 + 2 * n2) {
-            put_wt((float *)(pack + L.w3t), w_lr, Ld, Ld, Ld, e - n1 - n2);                      // Wb
+            v = put_wt((float *)(pack + L.w3t), w_lr, Ld, Ld, Ld, e - n1 - n2);                      // Wb
         } else {
             int r = (int)(e - n1 - 2 * n2);
-            if (r < NP) put_vec((float *)(pack + L.b1), b1, L.d1, r, false);
-            else if (r < 2 * NP) put_vec((float *)(pack + L.b2), w_lr + 2 * (int64_t)Ld * Ld, Ld, r - NP, false);
-            else ((float *)(pack + L.c))[0] = c_lr ? c_lr[0] : 0.f;
+            if (r < NP) v = put_vec((float *)(pack + L.b1), b1, L.d1, r, false);
+            else if (r < 2 * NP) v = put_vec((float *)(pack + L.b2), w_lr + 2 * (int64_t)Ld * Ld, Ld, r - NP, false);
+            else { v = c_lr ? c_lr[0] : 0.f; ((float *)(pack + L.c))[0] = v; }
         }
+        h += fp_term(v, e);
     }
+    fp_commit(h, (unsigned long long *)(pack + L.fp), parity);
 }
 
 }  // namespace nplda
@@ -77,26 +110,26 @@ extern "C" int64_t nplda_pack_bytes(int d_in, int d1, int d2) {
 
 extern "C" int nplda_pack_weights(const float *W1, const float *b1, const float *W2, const float *b2,
                                   const float *p_sqrt, const float *q, int d_in, int d1, int d2,
-                                  void *pack, int64_t pack_bytes, void *stream) {
+                                  void *pack, int64_t pack_bytes, int flags, void *stream) {
     if (!W1 || !b1 || !W2 || !b2 || !p_sqrt || !q || !pack) return NPLDA_ERR_BAD_ARG;
     if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
     PackLayout L = make_pack_layout(d_in, d1, d2);
     if (pack_bytes < L.total) return NPLDA_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    pack_nplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack);
+    pack_nplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack, (flags >> 1) & 1);
     NPLDA_LAUNCH_CHECK();
-    return tc_pack_nplda(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack, st);
+    return tc_pack_nplda(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack, flags, st);
 }
 
 extern "C" int dplda_pack_weights(const float *W1, const float *b1, const float *w_lr,
                                   const float *c_lr, int d_in, int d1, void *pack,
-                                  int64_t pack_bytes, void *stream) {
+                                  int64_t pack_bytes, int flags, void *stream) {
     if (!W1 || !b1 || !w_lr || !pack) return NPLDA_ERR_BAD_ARG;
     if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
     PackLayout L = make_pack_layout(d_in, d1, d1);
     if (pack_bytes < L.total) return NPLDA_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    pack_dplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, w_lr, c_lr, L, (char *)pack);
+    pack_dplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, w_lr, c_lr, L, (char *)pack, (flags >> 1) & 1);
     NPLDA_LAUNCH_CHECK();
     return tc_pack_dplda(W1, b1, w_lr, c_lr, L, (char *)pack, st);
 }

@@ -11,6 +11,12 @@
 // nplda_table_prepare builds the row table [n_rows][2 * ROW_LD] = { A (ROW_LD floats, r stored in A[ROW_LD-1]) |
 // B (ROW_LD floats) } with the fp32 SIMT embed kernel; nplda_score_pairs streams the index pairs (16 B per
 // trial from HBM) and gathers two 704-byte rows per trial, which stay in L2 for tables up to ~80 k utterances.
+//
+// Validity of a cached row table is decided ON THE DEVICE: the table carries the fingerprint of the packed
+// parameters it was built from (pack.cu); with NPLDA_PREPARE_IF_CHANGED the prepare kernels return at once when
+// it equals the fingerprint of the current pack, so a caller may re-pack and "prepare" before every scoring call
+// at the cost of three empty launches, and never scores with rows of stale parameters -- however the parameters
+// were changed (`.data.copy_()`, fused optimisers: neither bumps tensor._version).
 #include <algorithm>
 
 #include "common.cuh"
@@ -18,14 +24,17 @@
 namespace nplda {
 
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
-             float *out, int64_t ld_out, cudaStream_t st);   // score_simt.cu
+             float *out, int64_t ld_out, cudaStream_t st, const unsigned long long *fp_cur = nullptr,
+             const unsigned long long *fp_built = nullptr);   // score_simt.cu
 
 constexpr int ROW_LD = 176;              // floats per half row (width <= 175; the last float of A holds r)
 constexpr int ROW_FLOATS = 2 * ROW_LD;
 
 // one warp per utterance: B = 2 P y, r = sum Q y^2 (y already sits in the A half)
 __global__ void __launch_bounds__(256) rowtab_nplda_kernel(float *__restrict__ rowtab, int64_t n_rows, int d,
-                                                           const float *__restrict__ p, const float *__restrict__ q) {
+                                                           const float *__restrict__ p, const float *__restrict__ q,
+                                                           const unsigned long long *fp_cur, const unsigned long long *fp_built) {
+    if (fp_cur != nullptr && *fp_cur == *fp_built) return;
     const int lane = threadIdx.x & 31;
     const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = w0; r < n_rows; r += nw) {
@@ -45,7 +54,9 @@ __global__ void __launch_bounds__(256) rowtab_nplda_kernel(float *__restrict__ r
 // one CTA per utterance: B = (Wb + Wb^T) u, r = u^T Ww u + ws . u + c / 2.  wwt[k][n] = Ww[n][k], wbt[k][n] = Wb[n][k].
 __global__ void __launch_bounds__(NP) rowtab_dplda_kernel(float *__restrict__ rowtab, int64_t n_rows, int d,
                                                           const float *__restrict__ wwt, const float *__restrict__ wbt,
-                                                          const float *__restrict__ ws, const float *__restrict__ c) {
+                                                          const float *__restrict__ ws, const float *__restrict__ c,
+                                                          const unsigned long long *fp_cur, const unsigned long long *fp_built) {
+    if (fp_cur != nullptr && *fp_cur == *fp_built) return;
     __shared__ float u[NP];
     __shared__ float red[NP / 32];
     const int n = threadIdx.x;
@@ -74,6 +85,8 @@ __global__ void __launch_bounds__(NP) rowtab_dplda_kernel(float *__restrict__ ro
         }
     }
 }
+
+__global__ void rowtab_commit_kernel(const unsigned long long *fp_cur, unsigned long long *fp_built) { *fp_built = *fp_cur; }
 
 // one warp per trial: S = r[i] + r[j] + A[i] . B[j]; 44 float4 per half row = lanes 0..31 + lanes 0..11
 __global__ void __launch_bounds__(256) score_pairs_kernel(const float *__restrict__ rowtab, int64_t n_rows,
@@ -108,11 +121,11 @@ using namespace nplda;
 
 extern "C" int64_t nplda_rowtab_bytes(int64_t n_rows) {
     if (n_rows < 0) return NPLDA_ERR_BAD_ARG;
-    return n_rows * ROW_FLOATS * (int64_t)sizeof(float);
+    return n_rows * ROW_FLOATS * (int64_t)sizeof(float) + 256;     // + the fingerprint the rows were built from
 }
 
 extern "C" int nplda_table_prepare(const float *table, int64_t n_rows, int d_in, int d1, int d2, const void *pack,
-                                   int is_dplda, float *rowtab, void *stream) {
+                                   int is_dplda, float *rowtab, int flags, void *stream) {
     if (n_rows < 0 || !pack || (n_rows > 0 && (!table || !rowtab))) return NPLDA_ERR_BAD_ARG;
     if (is_dplda) d2 = d1;
     if (!dims_supported(d_in, d1, d2) || d1 >= ROW_LD || d2 >= ROW_LD) return NPLDA_ERR_UNSUPPORTED_DIM;
@@ -120,16 +133,22 @@ extern "C" int nplda_table_prepare(const float *table, int64_t n_rows, int d_in,
     PackLayout L = make_pack_layout(d_in, d1, d2);
     cudaStream_t st = (cudaStream_t)stream;
     const char *pk = (const char *)pack;
-    int rc = simt_aux(is_dplda ? 3 : 2, table, nullptr, n_rows, L, pk, rowtab, ROW_FLOATS, st);
+    const unsigned long long *fp_cur = (const unsigned long long *)(pk + L.fp) + ((flags >> 1) & 1);
+    unsigned long long *fp_built = (unsigned long long *)(rowtab + n_rows * ROW_FLOATS);
+    const unsigned long long *g_cur = (flags & NPLDA_PREPARE_IF_CHANGED) ? fp_cur : nullptr;
+    int rc = simt_aux(is_dplda ? 3 : 2, table, nullptr, n_rows, L, pk, rowtab, ROW_FLOATS, st, g_cur, fp_built);
     if (rc != NPLDA_OK) return rc;
     if (is_dplda) {
         const int grid = (int)std::min<int64_t>(n_rows, 8 * (int64_t)sm_count());
         rowtab_dplda_kernel<<<grid, NP, 0, st>>>(rowtab, n_rows, d1, (const float *)(pk + L.w2t), (const float *)(pk + L.w3t),
-                                                 (const float *)(pk + L.b2), (const float *)(pk + L.c));
+                                                 (const float *)(pk + L.b2), (const float *)(pk + L.c), g_cur, fp_built);
     } else {
         const int grid = (int)std::min<int64_t>((n_rows + 7) / 8, 8 * (int64_t)sm_count());
-        rowtab_nplda_kernel<<<grid, 256, 0, st>>>(rowtab, n_rows, d2, (const float *)(pk + L.p), (const float *)(pk + L.q));
+        rowtab_nplda_kernel<<<grid, 256, 0, st>>>(rowtab, n_rows, d2, (const float *)(pk + L.p), (const float *)(pk + L.q),
+                                                 g_cur, fp_built);
     }
+    NPLDA_LAUNCH_CHECK();
+    rowtab_commit_kernel<<<1, 1, 0, st>>>(fp_cur, fp_built);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }

@@ -468,7 +468,7 @@ static int gemm_tn(const float *A, int lda, int M, const float *B, int ldb, int 
     const int ntn = (N + GT_N - 1) / GT_N;
     int splits = std::max(1, 2 * sm_count() / ntn);
     int64_t rows = (R + splits - 1) / splits;
-    rows = std::max<int64_t>((rows + GT_K - 1) / GT_K * GT_K, 16 * GT_K);
+    rows = std::max<int64_t>((rows + GT_K - 1) / GT_K * GT_K, 2 * GT_K);   // small batches: more CTAs, fewer chunks each
     splits = (int)((R + rows - 1) / rows);
     const bool vec = lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0;
     dim3 grid(ntn, splits);

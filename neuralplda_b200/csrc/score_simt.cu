@@ -28,6 +28,7 @@ struct Args {
     int64_t ld_out;                // row stride of the embedding output (floats)
     const float *w1t, *b1, *w2t, *w3t, *b2, *p, *q, *c;
     float *scores;
+    const unsigned long long *fp_cur, *fp_built;   // embed modes: skip the launch when *fp_cur == *fp_built (pairs.cu)
 };
 
 // MODE: 0 NeuralPlda score, 1 DPlda score, 2 NeuralPlda embeddings y[n,d2], 3 DPlda embeddings u[n,d1],
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) score_kernel(Args g) {
     constexpr bool EMBED = MODE == 2 || MODE == 3;
     constexpr bool FROM_EMB = MODE == 4;
     constexpr int ROWS_PER_UNIT = EMBED ? 1 : 2;             // an embed tile is 128 input rows, a score tile 64 pairs
+    if (EMBED && g.fp_cur != nullptr && *g.fp_cur == *g.fp_built) return;   // row table still valid for these parameters
     extern __shared__ __align__(16) float smem[];
     float *As = smem;
     float *Ws = smem + 2 * A_STAGE;
@@ -257,6 +259,7 @@ int score_simt(bool dplda, const float *x1, const float *x2, const int64_t *i1, 
                int64_t n_rows, int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack,
                float *scores, cudaStream_t st) {
     simt::Args a;
+    a.fp_cur = a.fp_built = nullptr;
     a.x1 = x1; a.x2 = x2; a.i1 = i1; a.i2 = i2; a.n_rows = n_rows; a.bad_flag = bad_flag;
     a.n = n; a.d_in = L.d_in; a.k1p = L.k1p; a.k2p = L.k2p;
     a.w1t = (const float *)(pack + L.w1t); a.b1 = (const float *)(pack + L.b1);
@@ -273,8 +276,10 @@ int score_simt(bool dplda, const float *x1, const float *x2, const int64_t *i1, 
 
 // mode 2: NeuralPlda embeddings, 3: DPlda embeddings, 4: DPlda score from embeddings (x1, x2 = u rows)
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
-             float *out, int64_t ld_out, cudaStream_t st) {
+             float *out, int64_t ld_out, cudaStream_t st, const unsigned long long *fp_cur,
+             const unsigned long long *fp_built) {
     simt::Args a;
+    a.fp_cur = fp_cur; a.fp_built = fp_built;
     a.x1 = x1; a.x2 = x2 ? x2 : x1; a.i1 = a.i2 = nullptr; a.n_rows = 0; a.bad_flag = nullptr;
     a.n = n; a.d_in = mode == 4 ? L.d1 : L.d_in; a.k1p = L.k1p; a.k2p = L.k2p;
     a.w1t = (const float *)(pack + L.w1t); a.b1 = (const float *)(pack + L.b1);

@@ -205,6 +205,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
     constexpr uint32_t IDESC = make_idesc_bf16(128, NPAD);
     constexpr uint32_t IDESC_F16 = make_idesc_fmt(0, 0, 128, NPAD), IDESC_E4M3 = make_idesc_fmt(0, 0, 128, NPAD);
     const float s1 = MODE == 1 ? g.hdr[0] : 1.f;
+    const bool img_ok = MODE != 1 || g.hdr[2] != 0.f;      // mixed image built by this pack (NPLDA_PACK_MIXED)?
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ptime = PROF ? clock64() : 0;
 
     if (warp < EPI_WARPS) {
@@ -356,7 +357,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const bool tile_end = MODE == 1 && ++stage_in_tile == g.nst1;
             auto guard_check = [&]() {
                 const int64_t pr = (blockIdx.x + tile_i * gridDim.x) * TP + pl;
-                if (pr < g.n && (amax < 0.25f || amax >= 256.f)) *reinterpret_cast<volatile int *>(g.guard) = 1;
+                if (pr < g.n && (amax < 0.25f || amax >= 256.f || !img_ok)) *reinterpret_cast<volatile int *>(g.guard) = 1;
                 amax = 0.f; stage_in_tile = 0; ++tile_i;
             };
             // mbarrier parity waits are only unambiguous for a waiter that observes EVERY phase of a
@@ -657,7 +658,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
 // Step s of an image covers K = [16 s, 16 s + 16):  [hi chunk 0][hi chunk 1][lo chunk 0][lo chunk 1],
 // a chunk = 22 core matrices of 8 rows x 8 k (128 B each); element (row n, k) of a chunk sits at
 // (n/8)*128 + (n%8)*16 + (k%8)*2.
-__global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ksteps, uint8_t *__restrict__ img) {
+__global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ksteps, uint8_t *__restrict__ img,
+                               float *__restrict__ hdr_invalidate) {
+    // hdr[2] = 0 marks the MODE 1 image as not built (pack flag NPLDA_PACK_MIXED off): the mixed kernel then flags
+    // every tile for the bf16x3 pass behind it
+    if (hdr_invalidate && blockIdx.x == 0 && threadIdx.x == 0) { hdr_invalidate[0] = 1.f; hdr_invalidate[1] = 1.f; hdr_invalidate[2] = 0.f; }
     const int64_t total = (int64_t)ksteps * 2 * NPAD * 8;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int kk = (int)(e & 7);
@@ -705,6 +710,7 @@ __global__ void tc_absmax_kernel(const float *__restrict__ W, int64_t count, flo
         gw = max(-100, min(100, gw));
         hdr[0] = exp2f((float)-(gw + 9));   // epilogue scale
         hdr[1] = exp2f((float)(gw + 9));    // W -> W'
+        hdr[2] = 1.f;                       // image valid
     }
 }
 
@@ -777,17 +783,19 @@ bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed) {
 }
 
 int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float *b2, const float *p_sqrt,
-                  const float *q, const PackLayout &L, char *pack, cudaStream_t st) {
+                  const float *q, const PackLayout &L, char *pack, int flags, cudaStream_t st) {
     (void)b1; (void)b2; (void)p_sqrt; (void)q;   // the fp32 padded vectors of the SIMT pack are shared
     if (!tc_dims_ok(L.d_in, L.d1, L.d2)) return NPLDA_OK;
     uint8_t *img1 = (uint8_t *)pack + L.tc;
     uint8_t *img2 = img1 + (tcg::image_bytes(L.d_in / 16) + 255) / 256 * 256;
-    tcg::tc_pack_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / 16, img1);
-    NPLDA_LAUNCH_CHECK();
-    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(W2, L.d2, L.d1, round_up(L.d1, 16) / 16, img2);
-    NPLDA_LAUNCH_CHECK();
     uint8_t *img1m = img2 + (tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256;
     float *hdr = (float *)(img1m + tcg::mixed_image_bytes(L.d_in));
+    const bool mixed = (flags & NPLDA_PACK_MIXED) != 0;
+    tcg::tc_pack_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / 16, img1, mixed ? nullptr : hdr);
+    NPLDA_LAUNCH_CHECK();
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(W2, L.d2, L.d1, round_up(L.d1, 16) / 16, img2, nullptr);
+    NPLDA_LAUNCH_CHECK();
+    if (!mixed) return NPLDA_OK;
     tcg::tc_absmax_kernel<<<1, 1024, 0, st>>>(W1, (int64_t)L.d1 * L.d_in, hdr);
     NPLDA_LAUNCH_CHECK();
     tcg::tc_pack_mixed_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / tcg::KST, hdr, img1m);

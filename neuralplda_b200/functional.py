@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import check, lib, ptr, require_cuda, stream_ptr
+from ._lib import check, lib, on_device, ptr, require_cuda, stream_ptr
 
 
 def _f32c(t):
@@ -21,56 +21,80 @@ def _f32c(t):
 
 
 class PackedWeights:
-    """Device workspace holding the packed weights of one module, re-packed only
-    when a parameter changed (tracked through tensor._version / data_ptr)."""
+    """Device workspace holding the packed weights of one module.
+
+    The weights are re-packed on EVERY call (three small kernels): parameter changes cannot be detected on the
+    host -- the reference itself writes parameters through `.data.copy_()` (models.py:449-457, :420) and fused
+    optimisers update them in place, and neither bumps tensor._version.  What is cached beyond the pack (the
+    per-utterance row table of the trial-list / grid paths) is validated on the device against the content
+    fingerprint the pack kernel computes (csrc/pack.cu, csrc/pairs.cu)."""
 
     def __init__(self):
         self.buf = None
-        self.key = None
+        self.epoch = 0
 
-    def get(self, kind, params, d_in, d1, d2):
-        key = (kind, d_in, d1, d2) + tuple((p.data_ptr(), p._version, p.device) for p in params)
-        if key != self.key:
-            dev = params[0].device
-            nbytes = lib().nplda_pack_bytes(d_in, d1, d2)
-            if nbytes < 0:
-                check(nbytes, "nplda_pack_bytes")
-            if self.buf is None or self.buf.numel() < nbytes or self.buf.device != dev:
-                self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            ps = [_f32c(p.detach()) for p in params]
-            with torch.cuda.device(dev):
-                if kind == "nplda":
-                    rc = lib().nplda_pack_weights(*[ptr(p) for p in ps], d_in, d1, d2, ptr(self.buf),
-                                                  self.buf.numel(), stream_ptr())
-                else:
-                    rc = lib().dplda_pack_weights(*[ptr(p) for p in ps], d_in, d1, ptr(self.buf),
-                                                  self.buf.numel(), stream_ptr())
-            check(rc, "pack_weights")
-            self.key = key
-            self.rowtab_key = None          # per-utterance rows depend on the parameters
+    def get(self, kind, params, d_in, d1, d2, mixed=False):
+        dev = params[0].device
+        nbytes = lib().nplda_pack_bytes(d_in, d1, d2)
+        if nbytes < 0:
+            check(nbytes, "nplda_pack_bytes")
+        if self.buf is None or self.buf.numel() != nbytes or self.buf.device != dev:
+            self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            self.rowtab_key = None
+        self.epoch ^= 1
+        flags = (_lib.PACK_MIXED if mixed else 0) | (_lib.PACK_EPOCH_ODD if self.epoch else 0)
+        ps = [_f32c(p.detach()) for p in params]
+        with on_device(dev):
+            if kind == "nplda":
+                rc = lib().nplda_pack_weights(*[ptr(p) for p in ps], d_in, d1, d2, ptr(self.buf),
+                                              self.buf.numel(), flags, stream_ptr())
+            else:
+                rc = lib().dplda_pack_weights(*[ptr(p) for p in ps], d_in, d1, ptr(self.buf),
+                                              self.buf.numel(), flags, stream_ptr())
+        check(rc, "pack_weights")
         return self.buf
 
     rowtab = None
     rowtab_key = None
 
-    def rowtab_valid(self, table):
-        return self.rowtab_key == (table.data_ptr(), table._version, tuple(table.shape), self.key)
+    @staticmethod
+    def _table_key(kind, table, d_in, d1, d2):
+        return (kind, d_in, d1, d2, table.data_ptr(), table._version, tuple(table.shape), table.device)
+
+    def rowtab_valid(self, kind, table, d_in, d1, d2):
+        """Rows of THIS table are in the cache (whether they match the current parameters is checked on the device)."""
+        return self.rowtab_key == self._table_key(kind, table, d_in, d1, d2)
 
     def get_rowtab(self, kind, table, params, d_in, d1, d2):
-        """Per-utterance score operands of `table` (nplda_table_prepare), rebuilt only when the table or a
-        parameter changed."""
+        """Per-utterance score operands of `table` (nplda_table_prepare).  The table is identified on the host
+        (pointer, version, shape -- a table is an input the caller owns; the loaders' table is never written);
+        the parameters by the fingerprint of the fresh pack, on the device: the prepare call is a few empty
+        launches when nothing changed."""
         pack = self.get(kind, params, d_in, d1, d2)
-        key = (table.data_ptr(), table._version, tuple(table.shape), self.key)
-        if key != self.rowtab_key:
-            n_rows = table.shape[0]
-            nbytes = lib().nplda_rowtab_bytes(n_rows)
-            if self.rowtab is None or self.rowtab.numel() * 4 < nbytes or self.rowtab.device != table.device:
-                self.rowtab = torch.empty(max(1, nbytes // 4), dtype=torch.float32, device=table.device)
-            with torch.cuda.device(table.device):
-                check(lib().nplda_table_prepare(ptr(table), n_rows, d_in, d1, d2, ptr(pack), 0 if kind == "nplda" else 1,
-                                                ptr(self.rowtab), stream_ptr()), "nplda_table_prepare")
-            self.rowtab_key = key
+        key = self._table_key(kind, table, d_in, d1, d2)
+        n_rows = table.shape[0]
+        nbytes = lib().nplda_rowtab_bytes(n_rows)
+        if self.rowtab is None or self.rowtab.numel() * 4 < nbytes or self.rowtab.device != table.device:
+            self.rowtab = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=table.device)
+            self.rowtab_key = None
+        flags = (_lib.PREPARE_IF_CHANGED if key == self.rowtab_key else 0) | (_lib.PACK_EPOCH_ODD if self.epoch else 0)
+        with on_device(table.device):
+            check(lib().nplda_table_prepare(ptr(table), n_rows, d_in, d1, d2, ptr(pack), 0 if kind == "nplda" else 1,
+                                            ptr(self.rowtab), flags, stream_ptr()), "nplda_table_prepare")
+        self.rowtab_key = key
         return self.rowtab
+
+
+def _zero_grads(params, need):
+    """Zeroed gradient buffers for the parameters that need one: slices of ONE allocation (one fill launch per
+    backward instead of one per parameter; the reference trains with 128-pair batches, where launches count)."""
+    sizes = [(p.numel() + 3) // 4 * 4 if nd else 0 for p, nd in zip(params, need)]     # 16-byte aligned slices
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=params[0].device)
+    out, o = [], 0
+    for p, nd, sz in zip(params, need, sizes):
+        out.append(flat[o:o + p.numel()].view(p.shape) if nd else None)
+        o += sz
+    return out
 
 
 def _check_pair_inputs(x1, x2, d_in):
@@ -93,9 +117,9 @@ class NpldaScoreFn(torch.autograd.Function):
         _check_pair_inputs(x1, x2, d_in)
         x1c, x2c = _f32c(x1), _f32c(x2)
         n = x1c.shape[0]
-        pack = packed.get("nplda", (W1, b1, W2, b2, P_sqrt, Q), d_in, d1, d2)
+        pack = packed.get("nplda", (W1, b1, W2, b2, P_sqrt, Q), d_in, d1, d2, mixed=(impl == _lib.IMPL_TC_F8))
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
-        with torch.cuda.device(x1c.device):
+        with on_device(x1c.device):
             check(lib().nplda_score_fwd(ptr(x1c), ptr(x2c), n, d_in, d1, d2, ptr(pack), ptr(scores), impl,
                                         stream_ptr()), "nplda_score_fwd")
         ctx.save_for_backward(x1c, x2c, W1, b1, W2, b2, P_sqrt, Q)
@@ -111,11 +135,11 @@ class NpldaScoreFn(torch.autograd.Function):
         ds = _f32c(ds)
         need = ctx.needs_input_grad
         params = [_f32c(p.detach()) for p in (W1, b1, W2, b2, P_sqrt, Q)]
-        grads = [torch.zeros_like(p) if need[2 + i] else None for i, p in enumerate(params)]
+        grads = _zero_grads(params, need[2:8])
         dx1 = torch.zeros_like(x1) if need[0] else None
         dx2 = torch.zeros_like(x2) if need[1] else None
         if n > 0:
-            with torch.cuda.device(dev):
+            with on_device(dev):
                 wsb = lib().nplda_bwd_workspace_bytes(n, d_in, d1, d2)
                 if wsb < 0:
                     check(wsb, "nplda_bwd_workspace_bytes")
@@ -139,7 +163,7 @@ class DpldaScoreFn(torch.autograd.Function):
         n = x1c.shape[0]
         pack = packed.get("dplda", (W1, b1, w_lr, c_lr), d_in, d1, d1)
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
-        with torch.cuda.device(x1c.device):
+        with on_device(x1c.device):
             check(lib().dplda_score_fwd(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), impl,
                                         stream_ptr()), "dplda_score_fwd")
         ctx.save_for_backward(x1c, x2c, W1, b1, w_lr)
@@ -154,14 +178,11 @@ class DpldaScoreFn(torch.autograd.Function):
         ds = _f32c(ds)
         need = ctx.needs_input_grad
         W1c, b1c, wc = _f32c(W1.detach()), _f32c(b1.detach()), _f32c(w_lr.detach())
-        dW1 = torch.zeros_like(W1c) if need[2] else None
-        db1 = torch.zeros_like(b1c) if need[3] else None
-        dw = torch.zeros_like(wc) if need[4] else None
-        dc = torch.zeros(1, dtype=torch.float32, device=dev) if need[5] else None
+        dW1, db1, dw, dc = _zero_grads([W1c, b1c, wc, b1c[:1]], need[2:6])       # dc: [1] like logistic_regres.bias
         dx1 = torch.zeros_like(x1) if need[0] else None
         dx2 = torch.zeros_like(x2) if need[1] else None
         if n > 0:
-            with torch.cuda.device(dev):
+            with on_device(dev):
                 wsb = lib().nplda_bwd_workspace_bytes(n, d_in, d1, d1)
                 if wsb < 0:
                     check(wsb, "nplda_bwd_workspace_bytes")
@@ -186,7 +207,7 @@ def embed(kind, x, params, dims, packed):
     pack = packed.get(kind, params, d_in, d1, d2)
     width = d2 if kind == "nplda" else d1
     out = torch.empty(n, width, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         check(lib().nplda_embed_fwd(ptr(x), n, d_in, d1, d2, ptr(pack), ptr(out), 0 if kind == "nplda" else 1,
                                     stream_ptr()), "nplda_embed_fwd")
     return out
@@ -204,7 +225,7 @@ def score_from_embeddings(kind, e1, e2, params, dims, packed):
     e1, e2 = _f32c(e1), _f32c(e2)
     n = e1.shape[0]
     scores = torch.empty(n, dtype=torch.float32, device=e1.device)
-    with torch.cuda.device(e1.device):
+    with on_device(e1.device):
         if kind == "nplda":
             ps, q = _f32c(params[4].detach()), _f32c(params[5].detach())
             check(lib().nplda_score_from_embeddings(ptr(e1), ptr(e2), n, d2, ptr(ps), ptr(q), ptr(scores),
@@ -233,18 +254,18 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
         raise RuntimeError("index tensors must be 1-D and the same length")
     n = i1.numel()
     dev = table.device
-    pack = packed.get(kind, params, d_in, d1, d2)
     scores = torch.empty(n, dtype=torch.float32, device=dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     if embed_once is None:
-        embed_once = max(d1, d2) < 176 and table.shape[0] > 0 and (packed.rowtab_valid(table) or table.shape[0] <= 2 * n)
+        embed_once = max(d1, d2) < 176 and table.shape[0] > 0 and (packed.rowtab_valid(kind, table, d_in, d1, d2) or table.shape[0] <= 2 * n)
     if embed_once:
         rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib().nplda_score_pairs(ptr(rowtab), table.shape[0], ptr(i1), ptr(i2), n, ptr(scores), ptr(flag),
                                           stream_ptr()), "nplda_score_pairs")
         return scores, flag
-    with torch.cuda.device(dev):
+    pack = packed.get(kind, params, d_in, d1, d2, mixed=(impl == _lib.IMPL_TC_F8))
+    with on_device(dev):
         if kind == "nplda":
             rc = lib().nplda_score_fwd_indexed(ptr(table), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1, d2,
                                                ptr(pack), ptr(scores), ptr(flag), impl, stream_ptr())
@@ -276,7 +297,7 @@ def score_grid(kind, table, enrol_rows, test_rows, params, dims, packed):
         if table.shape[0] == 0:
             raise RuntimeError("empty x-vector table")
         rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib().nplda_score_grid(ptr(rowtab), table.shape[0], ptr(er), er.numel(), ptr(tr), tr.numel(),
                                          ptr(scores), tr.numel(), ptr(flag), stream_ptr()), "nplda_score_grid")
     return scores, flag
@@ -301,7 +322,7 @@ def loss_accumulators(scores, target, thresholds, alpha, th_xent, group=None):
     acc = torch.zeros(4 * K + 4, dtype=torch.float64, device=s.device)
     th = None if K == 0 else _f32c(thresholds.detach())
     thx = None if th_xent is None else _f32c(th_xent.detach())
-    with torch.cuda.device(s.device):
+    with on_device(s.device):
         check(lib().nplda_loss_accum(ptr(s), ptr(t), s.numel(), ptr(th), K, float(alpha), ptr(thx), ptr(acc),
                                      stream_ptr()), "nplda_loss_accum")
     if group is not None:
@@ -313,7 +334,7 @@ def loss_accumulators(scores, target, thresholds, alpha, th_xent, group=None):
 def finalize(acc, betas):
     out = torch.empty(4, dtype=torch.float32, device=acc.device)
     K = len(betas)
-    with torch.cuda.device(acc.device):
+    with on_device(acc.device):
         check(lib().nplda_loss_finalize(ptr(acc), _lib.betas_array(betas), K, ptr(out), stream_ptr()),
               "nplda_loss_finalize")
     return out
@@ -343,7 +364,7 @@ class LossFn(torch.autograd.Function):
         g = _f32c(g).reshape(1)
         th = None if thresholds is None else _f32c(thresholds.detach())
         thx = None if th_xent is None else _f32c(th_xent.detach())
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib().nplda_loss_bwd(ptr(s), ptr(t), s.numel(), ptr(th), _lib.betas_array(ctx.betas), K,
                                        ctx.alpha, ptr(thx), ptr(acc), ctx.loss_id, ptr(g), ptr(ds), ptr(dth),
                                        stream_ptr()), "nplda_loss_bwd")
@@ -362,7 +383,7 @@ def minc_sweep(tgt_sorted, non_sorted, sum_t, sum_n, betas):
     dev = tgt_sorted.device
     out_min = torch.empty(K, dtype=torch.float32, device=dev)
     out_arg = torch.empty(K, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib().nplda_minc_sweep(ptr(tgt_sorted), tgt_sorted.numel(), ptr(non_sorted), non_sorted.numel(),
                                      ctypes.c_float(sum_t), ctypes.c_float(sum_n), _lib.betas_array(betas), K,
                                      ptr(out_min), ptr(out_arg), stream_ptr()), "nplda_minc_sweep")

@@ -20,7 +20,7 @@ import torch.nn as nn
 from . import _lib, functional as F_
 from . import kaldi_io_lite
 
-_TRANSIENT = ("_packed", "_impl", "_group")
+_TRANSIENT = ("_packed", "_impl", "_group", "_alpha_cache")
 
 
 class _PldaBase(nn.Module):
@@ -98,6 +98,19 @@ class _PldaBase(nn.Module):
         return self
 
     # ---- losses (models.py:384-404; 497-517) -----------------------------------
+    def _alpha_value(self):
+        """float(self.alpha) without a device->host read per loss call: alpha is a tensor that follows the module
+        to the GPU (models.py:360); its value is cached against the tensor's identity and version."""
+        a = self.alpha
+        if not isinstance(a, torch.Tensor):
+            return float(a)
+        key = (id(a), a._version)
+        c = self.__dict__.get("_alpha_cache")
+        if c is None or c[0] != key:
+            c = (key, float(a))
+            self.__dict__["_alpha_cache"] = c
+        return c[1]
+
     def _thresholds(self):
         if len(self.beta) == 0:
             return None
@@ -108,11 +121,11 @@ class _PldaBase(nn.Module):
 
     def softcdet(self, output, target):
         return F_.LossFn.apply(output, target, self._thresholds(), self._th_xent(), self.beta,
-                               float(self.alpha), _lib.LOSS_SOFTCDET, self.process_group)
+                               self._alpha_value(), _lib.LOSS_SOFTCDET, self.process_group)
 
     def crossentropy(self, output, target):
         return F_.LossFn.apply(output, target, self._thresholds(), self._th_xent(), self.beta,
-                               float(self.alpha), _lib.LOSS_CROSSENTROPY, self.process_group)
+                               self._alpha_value(), _lib.LOSS_CROSSENTROPY, self.process_group)
 
     def loss(self, output, target):
         # case-sensitive dispatch, anything else returns None (models.py:395-399)
@@ -123,7 +136,7 @@ class _PldaBase(nn.Module):
 
     def cdet(self, output, target):
         with torch.no_grad():
-            acc = F_.loss_accumulators(output, target, self._thresholds(), float(self.alpha), self._th_xent(),
+            acc = F_.loss_accumulators(output, target, self._thresholds(), self._alpha_value(), self._th_xent(),
                                        self.process_group)
             return F_.finalize(acc, self.beta)[2].clone()
 

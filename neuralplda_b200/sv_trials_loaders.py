@@ -11,12 +11,15 @@ NeuralPlda.forward_indexed).
 """
 from __future__ import annotations
 
+import ctypes
 import os
 import weakref
 
 import numpy as np
 import torch
 from torch.utils.data import TensorDataset, DataLoader, ConcatDataset, Subset
+
+from ._lib import check, lib, on_device, ptr, stream_ptr
 
 
 class XvectorTable:
@@ -69,15 +72,59 @@ def _rows_from_nums(tab, num_to_id_dict, data):
     return torch.tensor([ident[2][int(i)] for i in nums], dtype=torch.int64)
 
 
+class _BadIndexFlag:
+    """int32 flag in pinned host memory that the gather kernel raises for rows outside the table.  The host reads
+    it without a synchronising copy: a raised flag is seen at the next loader call after the kernel ran (the
+    reference's loop reads loss.item() every step, so at the next batch at the latest)."""
+
+    def __init__(self):
+        self.t = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.ptr = ctypes.c_void_p(self.t.data_ptr())
+
+    def check(self):
+        if int(self.t[0]) != 0:
+            self.t[0] = 0
+            raise KeyError("a trial of an earlier batch referred to a row outside the x-vector table "
+                           "(the reference raises KeyError from its dict lookup)")
+
+
+def _gather(tab, r1, r2):
+    """(X1, X2) = (table[r1], table[r2]) on the device, one launch (nplda_gather_pairs)."""
+    flag = tab.__dict__.get("_bad_flag")
+    if flag is None:
+        flag = tab._bad_flag = _BadIndexFlag()
+    flag.check()
+    n, d = r1.numel(), tab.table.shape[1]
+    x1 = torch.empty(n, d, dtype=torch.float32, device=tab.device)
+    x2 = torch.empty(n, d, dtype=torch.float32, device=tab.device)
+    with on_device(tab.table.device):
+        check(lib().nplda_gather_pairs(ptr(tab.table), tab.table.shape[0], d, ptr(r1), ptr(r2), n, ptr(x1), ptr(x2),
+                                       flag.ptr, stream_ptr()), "nplda_gather_pairs")
+    return x1, x2
+
+
+def _device_rows(tab, num_to_id_dict, data, device):
+    """Row indices on the device.  Index tensors that already are on the GPU (the reference's loop moves the batch
+    there first, xvector_NeuralPlda_pytorch.py:37) stay there when num_to_id_dict enumerates list(mega_dict) --
+    no device->host round trip, no synchronisation; out-of-range rows are caught by the gather kernel."""
+    if data.is_cuda and data.dtype == torch.int64 and data.dim() == 1:
+        ident = getattr(tab, "_ident", None)
+        if ident is not None and ident[0] is num_to_id_dict and ident[1]:
+            return data.to(device).contiguous()
+    return _rows_from_nums(tab, num_to_id_dict, data).to(device, non_blocking=True)
+
+
 def load_xvec_trials_from_numbatch(mega_dict, num_to_id_dict, data1, data2, device):
     """sv_trials_loaders.py:418-426: (X1, X2) [B, D] fp32 on `device`."""
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("neuralplda_b200 keeps x-vectors on the GPU; got device '%s'" % device)
     tab = get_table(mega_dict, device)
-    r1 = _rows_from_nums(tab, num_to_id_dict, data1).to(device, non_blocking=True)
-    r2 = _rows_from_nums(tab, num_to_id_dict, data2).to(device, non_blocking=True)
-    return tab.table.index_select(0, r1), tab.table.index_select(0, r2)
+    r1 = _device_rows(tab, num_to_id_dict, data1, tab.table.device)
+    r2 = _device_rows(tab, num_to_id_dict, data2, tab.table.device)
+    if r1.shape != r2.shape:
+        raise RuntimeError("data1 and data2 must have the same length")
+    return _gather(tab, r1, r2)
 
 
 def strip_id(s):
@@ -94,9 +141,9 @@ def load_xvec_trials_from_idbatch(mega_dict, trials, device):
     if trials.size == 0:
         empty = tab.table.new_zeros((0, tab.table.shape[1]))
         return empty, empty.clone()
-    r1 = tab.rows_for_ids([strip_id(d) for d in trials[:, 0]]).to(device, non_blocking=True)
-    r2 = tab.rows_for_ids([strip_id(d) for d in trials[:, 1]]).to(device, non_blocking=True)
-    return tab.table.index_select(0, r1), tab.table.index_select(0, r2)
+    r1 = tab.rows_for_ids([strip_id(d) for d in trials[:, 0]]).to(tab.table.device, non_blocking=True)
+    r2 = tab.rows_for_ids([strip_id(d) for d in trials[:, 1]]).to(tab.table.device, non_blocking=True)
+    return _gather(tab, r1, r2)
 
 
 def _read_trials(f, id_to_num_dict, strip_ext_col2):

@@ -24,6 +24,18 @@ loss = m.loss(m(a[:4096], b[:4096]), y[:4096]); loss.backward()
 table, i1, i2, _ = O.synth_grid(40, 50, 7, seed=2, mean=kp["mean"])
 s, f = m.forward_indexed(table.to(dev), i1.to(dev), i2.to(dev))
 s, f = m.forward_indexed(table.to(dev), i1.to(dev), i2.to(dev), embed_once=False)
+from neuralplda_b200 import adaptive_score_normalization as asn
+from neuralplda_b200.sv_trials_loaders import load_xvec_trials_from_numbatch
+er, tr = torch.arange(40, device=dev), torch.arange(40, 90, device=dev)
+S = m.forward_grid(table.to(dev), er, tr)[0]
+S = m.forward_grid(table.to(dev), torch.arange(0, 90, device=dev), torch.arange(0, 90, device=dev).repeat(4))[0]   # 90 x 360, ragged tiles
+st = asn.cohort_statistics(S, 100)
+z = asn.normalize_scores(S[:, 0].contiguous(), torch.arange(90, device=dev), torch.arange(90, device=dev).flip(0), st)
+mega = {"u%d" % i: table[i].numpy() for i in range(table.shape[0])}
+n2i = dict(enumerate(mega))
+for _ in range(2):
+    g1, g2 = load_xvec_trials_from_numbatch(mega, n2i, i1[:300].to(dev), i2[:300].to(dev), dev)
+print("grid", float(S.sum()), "norm", float(z.sum()), "gather", float(g1.sum()))
 print("minc", m.minc(m(a[:4096], b[:4096]).detach(), y[:4096])[0].item())
 torch.cuda.synchronize()
 print("sanitize run ok")
