@@ -11,11 +11,16 @@
 //      done by a split-row SGEMM (gemm_tn) that adds its tiles atomically.
 // All gradient outputs are ADDED INTO.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "simt_tile.cuh"
 
 namespace nplda {
+
+int gemm_tn_tc(const float *A, int lda, int M, const float *B, int ldb, int N, int64_t R, float *C, int ldc,
+               cudaStream_t st);   // gemm_tc.cu: C[n][m] += sum_r A[r][m] B[r][n], N <= 176
+
 namespace bwd {
 
 using namespace simt;
@@ -499,6 +504,16 @@ static int64_t workspace_bytes(int64_t n, int d_in, int d1, int d2) {
     return make_pack(d_in, d1, d2).total * 4 + 3 * 2 * cap * NP * 4 + 1024;
 }
 
+// C[M,N] += A^T B: the tcgen05 bf16x3 kernel for batches worth its launch (NPLDA_BWD_GEMM=simt|tc forces one)
+static int gemm_tn_auto(const float *A, int lda, int M, const float *B, int ldb, int N, int64_t R, float *C,
+                        int ldc, cudaStream_t st) {
+    const char *e = getenv("NPLDA_BWD_GEMM");
+    const int forced = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0));
+    const bool tc_ok = M <= 176;
+    if (tc_ok && (forced == 2 || (forced == 0 && R >= 8192))) return gemm_tn_tc(B, ldb, N, A, lda, M, R, C, ldc, st);
+    return gemm_tn(A, lda, M, B, ldb, N, R, C, ldc, st);
+}
+
 template <bool DPLDA>
 static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2, const float *W1,
                const float *b1, const float *W2, const float *b2, const float *ps, const float *q,
@@ -545,19 +560,19 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
         int rc = NPLDA_OK;
         const float *U0 = U, *U1 = U + cap * NP, *G0 = G, *G1 = G + cap * NP, *DA0 = DA, *DA1 = DA + cap * NP;
         if (dW1) {
-            if ((rc = gemm_tn(DA0, NP, d1, a.x1, d_in, d_in, nc, dW1, d_in, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn(DA1, NP, d1, a.x2, d_in, d_in, nc, dW1, d_in, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(DA0, NP, d1, a.x1, d_in, d_in, nc, dW1, d_in, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(DA1, NP, d1, a.x2, d_in, d_in, nc, dW1, d_in, st)) != NPLDA_OK) return rc;
         }
         if (!DPLDA && dW2) {
-            if ((rc = gemm_tn(G0, NP, d2, U0, NP, d1, nc, dW2, d1, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn(G1, NP, d2, U1, NP, d1, nc, dW2, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G0, NP, d2, U0, NP, d1, nc, dW2, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G1, NP, d2, U1, NP, d1, nc, dW2, d1, st)) != NPLDA_OK) return rc;
         }
         if (DPLDA && dw_lr) {
             float *dWb = dw_lr, *dWw = dw_lr + (int64_t)d1 * d1;
-            if ((rc = gemm_tn(G0, NP, d1, U0, NP, d1, nc, dWw, d1, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn(G1, NP, d1, U1, NP, d1, nc, dWw, d1, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn(G0, NP, d1, U1, NP, d1, nc, dWb, d1, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn(G1, NP, d1, U0, NP, d1, nc, dWb, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G0, NP, d1, U0, NP, d1, nc, dWw, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G1, NP, d1, U1, NP, d1, nc, dWw, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G0, NP, d1, U1, NP, d1, nc, dWb, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G1, NP, d1, U0, NP, d1, nc, dWb, d1, st)) != NPLDA_OK) return rc;
         }
         if (dx1) {
             dx_kernel<<<(int)std::min<int64_t>(nc, 8 * sm_count()), 256, d1 * 4, st>>>(DA0, W1, d1, d_in, nc, dx1 + c0 * d_in);

@@ -848,3 +848,79 @@ def test_loader_gather_bit_exact(ref_out):
         L.load_xvec_trials_from_numbatch(mega, num_to_id, d1.to(DEV), d2.to(DEV), torch.device(DEV))
     X1, _ = L.load_xvec_trials_from_numbatch(mega, num_to_id, d1.to(DEV), d2.to(DEV), torch.device(DEV))   # flag cleared
     assert torch.equal(X1.cpu(), R1)
+
+
+@pytest.mark.parametrize("kind", ["nplda", "dplda"])
+def test_tensor_core_weight_gradients(ref_out, kaldi_params, cfg1, kind):
+    """The dW contractions (dW1 = DA^T X, dW2 = DY^T U; DPlda dWw / dWb) on the tcgen05 bf16x3 kernel
+    (csrc/gemm_tc.cu, taken for batches >= 8192 rows) against the fp32 SIMT contraction on the same batch: every
+    parameter gradient within 1e-4 of its largest entry; ragged row counts exercise the zero-filled tails."""
+    x1, x2, t = cfg1
+    n = 9000 + 37
+    a, b, y = x1[:n].to(DEV), x2[:n].to(DEV), t[:n].to(DEV)
+    grads = {}
+    for mode in ("simt", "tc"):
+        os.environ["NPLDA_BWD_GEMM"] = mode
+        try:
+            m = make_nplda(kaldi_params, loss="crossentropy") if kind == "nplda" else make_dplda(kaldi_params, ref_out)
+            m.loss(m(a, b), y).backward()
+            torch.cuda.synchronize()
+            grads[mode] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        finally:
+            os.environ.pop("NPLDA_BWD_GEMM", None)
+    assert set(grads["tc"]) == set(grads["simt"]) and len(grads["tc"]) >= 4
+    for k, gs in grads["simt"].items():
+        scale = float(gs.abs().max()) + 1e-30
+        assert float((grads["tc"][k] - gs).abs().max()) <= 1e-4 * scale, k
+
+
+@pytest.mark.parametrize("lossname", ["SoftCdet", "crossentropy"])
+def test_tensor_core_weight_gradients_vs_reference_autograd(ref_out, kaldi_params, cfg1, lossname, monkeypatch):
+    """Same golden check as test_nplda_training_step_gradients (the unmodified reference's .grad on 2048 pairs), with
+    the tensor-core contraction forced for this small batch."""
+    monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
+    test_nplda_training_step_gradients(ref_out, kaldi_params, cfg1, lossname)
+
+
+def test_config5_dplda_training_step_shard(ref_out, kaldi_params):
+    """BASELINE.json configs[4]: DPlda, 10M trials over 8 GPUs = 1.25M pairs per rank, one forward + BCE + backward
+    with the LDA frozen (xvector_DPlda_pytorch.py:140-147).  One rank's shard at full size: the loss and the
+    gradients of the whole shard equal the pair-count-weighted sums over two unequal parts (what the all-reduce of
+    raw sums relies on), frozen parameters get no gradient, and the forward agrees with the oracle on a subsample."""
+    kp = kaldi_params
+    n = 1_250_000
+    g = torch.Generator(device=DEV).manual_seed(1005)
+    mean = kp["mean"].to(DEV)
+    spk = torch.randn(2000, 512, generator=g, device=DEV)
+    s1 = torch.randint(0, 2000, (n,), generator=g, device=DEV)
+    same = torch.rand(n, generator=g, device=DEV) < 0.1
+    s2 = torch.where(same, s1, torch.randint(0, 2000, (n,), generator=g, device=DEV))
+    x1 = mean + spk[s1] + 0.7 * torch.randn(n, 512, generator=g, device=DEV)
+    x2 = mean + spk[s2] + 0.7 * torch.randn(n, 512, generator=g, device=DEV)
+    t = (s1 == s2).float()
+    m = make_dplda(kp, ref_out)
+    for p in (m.centering_and_LDA.weight, m.centering_and_LDA.bias):
+        p.requires_grad_(False)
+
+    def step(lo, hi):
+        m.zero_grad(set_to_none=True)
+        out = m(x1[lo:hi], x2[lo:hi])
+        loss = m.loss(out, t[lo:hi])
+        loss.backward()
+        return loss.item(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}, out.detach()
+
+    L, G, out = step(0, n)
+    assert "centering_and_LDA.weight" not in G and "logistic_regres.weight" in G
+    cut = 400_003
+    L1, G1, _ = step(0, cut)
+    L2, G2, _ = step(cut, n)
+    assert L == pytest.approx((cut * L1 + (n - cut) * L2) / n, rel=1e-5)
+    for k in G:
+        want = (cut * G1[k] + (n - cut) * G2[k]) / n
+        scale = float(want.abs().max()) + 1e-30
+        assert float((G[k] - want).abs().max()) <= 2e-4 * scale, k
+    idx = torch.arange(0, n, 1223, device=DEV)
+    w, c = dplda_weights(ref_out)
+    ref = O.dplda_score(x1[idx].cpu(), x2[idx].cpu(), kp["W1"], kp["b1"], w, c)
+    ok, worst = parity_ok(out[idx], ref, rel=1e-4)
+    assert ok, worst
