@@ -28,7 +28,8 @@ int score_simt(bool dplda, const float *x1, const float *x2, const int64_t *i1, 
 bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed);   // score_tc.cu
 int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2,
              int64_t n_rows, int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack,
-             float *scores, int mode, cudaStream_t st);   // score_tc.cu
+             float *scores, int mode, cudaStream_t st, float *aout = nullptr, float *yout = nullptr,
+             int64_t emit_cap = 0);   // score_tc.cu
 
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
              float *out, int64_t ld_out, cudaStream_t st, const unsigned long long *fp_cur = nullptr,

@@ -21,6 +21,11 @@ namespace nplda {
 int gemm_tn_tc(const float *A, int lda, int M, const float *B, int ldb, int N, int64_t R, float *C, int ldc,
                cudaStream_t st);   // gemm_tc.cu: C[n][m] += sum_r A[r][m] B[r][n], N <= 176
 
+bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed);   // score_tc.cu
+int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2, int64_t n_rows,
+             int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack, float *scores, int mode, cudaStream_t st,
+             float *aout, float *yout, int64_t emit_cap);   // score_tc.cu (EMIT mode when aout != nullptr)
+
 namespace bwd {
 
 using namespace simt;
@@ -119,7 +124,11 @@ __device__ __forceinline__ void col_add(float *colacc, int which, int tx, int j,
     if (lane < 16) atomicAdd(colacc + which * NP + 4 * tx + 64 * j + e, v);
 }
 
-template <bool DPLDA, bool VEC>
+// PRE (NeuralPlda only): a = W1 x + b1 and y = W2 u + b2 of every row were written by the tensor-core forward kernel
+// in its EMIT mode (score_tc.cu) into the DA and G areas of the workspace; the two recomputations (80 % of this
+// kernel's flops) are replaced by loads.  Each thread later overwrites exactly the elements it loaded here with
+// dL/da and dL/dy, so the aliasing is race-free.
+template <bool DPLDA, bool VEC, bool PRE>
 __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
     extern __shared__ __align__(16) float smem[];
     float *As = smem;
@@ -154,6 +163,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
 
         // ---- recompute layer 1 ----
         float2 acc[8][6];
+        if (PRE) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float *arow = g.DA + ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float4 v = *reinterpret_cast<const float4 *>(arow + 64 * j);
+                    if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);   // the emitted rows are 176 wide
+                    acc[i][2 * j] = make_float2(v.x, v.y);
+                    acc[i][2 * j + 1] = make_float2(v.z, v.w);
+                }
+            }
+        } else {
         zero_acc(acc);
         load_a_chunk<VEC>(As, rowp, 0, g.d_in, tid);
         load_w_chunk(Ws, g.w1t, 0, tid);
@@ -172,6 +194,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
             mma_chunk(acc, As + (c & 1) * A_STAGE, LDA, Ws + (c & 1) * W_STAGE, tx, ty);
             __syncthreads();
         }
+        }
 
         // ---- u = a / max(|a|, eps); keep 1/den per row; U -> smem + workspace ----
         float rden[8];
@@ -188,8 +211,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
                 float ss = 0.f;
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    acc[i][j].x += bb[j].x;
-                    acc[i][j].y += bb[j].y;
+                    if (!PRE) {                         // the emitted a already carries the bias
+                        acc[i][j].x += bb[j].x;
+                        acc[i][j].y += bb[j].y;
+                    }
                     ss = fmaf(acc[i][j].x, acc[i][j].x, ss);
                     ss = fmaf(acc[i][j].y, acc[i][j].y, ss);
                 }
@@ -217,10 +242,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
 
         if (!DPLDA) {
             // ---- recompute layer 2, form dL/dy in place ----
-            layer2_gemm(acc, Us, Ws, g.w2t, g.k2p, tx, ty, tid);
+            if (PRE) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float *yrow = g.G + ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        float4 v = *reinterpret_cast<const float4 *>(yrow + 64 * j);
+                        if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        acc[i][2 * j] = make_float2(v.x, v.y);
+                        acc[i][2 * j + 1] = make_float2(v.z, v.w);
+                    }
+                }
+            } else {
+                layer2_gemm(acc, Us, Ws, g.w2t, g.k2p, tx, ty, tid);
+            }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                float4 b2 = *reinterpret_cast<const float4 *>(g.b2 + 4 * tx + 64 * j);
+                float4 b2 = PRE ? make_float4(0.f, 0.f, 0.f, 0.f)          // the emitted y already carries b2
+                                : *reinterpret_cast<const float4 *>(g.b2 + 4 * tx + 64 * j);
                 float4 P = *reinterpret_cast<const float4 *>(g.p + 4 * tx + 64 * j);
                 float4 Q = *reinterpret_cast<const float4 *>(g.q + 4 * tx + 64 * j);
                 const float bv[4] = {b2.x, b2.y, b2.z, b2.w};
@@ -499,9 +539,12 @@ __global__ void dx_kernel(const float *__restrict__ DA, const float *__restrict_
     }
 }
 
+// room for the forward pack (tensor-core weight images) at the end of the workspace, used by the EMIT path
+static int64_t fwd_pack_room(int d_in, int d1, int d2) { return make_pack_layout(d_in, d1, d2).total + 256; }
+
 static int64_t workspace_bytes(int64_t n, int d_in, int d1, int d2) {
     const int64_t cap = (std::min(n, CHUNK_PAIRS) + TILE_PAIRS - 1) / TILE_PAIRS * TILE_PAIRS;
-    return make_pack(d_in, d1, d2).total * 4 + 3 * 2 * cap * NP * 4 + 1024;
+    return make_pack(d_in, d1, d2).total * 4 + 3 * 2 * cap * NP * 4 + 1024 + fwd_pack_room(d_in, d1, d2);
 }
 
 // C[M,N] += A^T B: the tcgen05 bf16x3 kernel for batches worth its launch (NPLDA_BWD_GEMM=simt|tc forces one)
@@ -539,7 +582,21 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
     NPLDA_LAUNCH_CHECK();
 
     const bool vec = (d_in % 4 == 0) && (((uintptr_t)x1 & 15) == 0) && (((uintptr_t)x2 & 15) == 0);
-    auto kern = vec ? bwd_tile_kernel<DPLDA, true> : bwd_tile_kernel<DPLDA, false>;
+    // NeuralPlda at the tensor-core kernel's shapes and batches worth the extra launches: layer 1 and layer 2 are
+    // not recomputed in fp32 here but emitted by the tcgen05 forward kernel (NPLDA_BWD_EMIT=0|1 forces a side)
+    const PackLayout FL = make_pack_layout(d_in, d1, d2);
+    bool pre = false;
+    if (!DPLDA && vec && tc_shape_ok(false, FL, false) && FL.total <= fwd_pack_room(d_in, d1, d2)) {
+        const char *e = getenv("NPLDA_BWD_EMIT");
+        pre = e ? e[0] == '1' : n >= 4096;
+    }
+    char *fpack = (char *)(DA + 2 * cap * NP);
+    if (pre) {
+        int rc = nplda_pack_weights(W1, b1, W2, b2, ps, q, d_in, d1, d2, fpack, FL.total, 0, st);
+        if (rc != NPLDA_OK) return rc;
+    }
+    auto kern = pre ? bwd_tile_kernel<DPLDA, true, !DPLDA>
+                    : (vec ? bwd_tile_kernel<DPLDA, true, false> : bwd_tile_kernel<DPLDA, false, false>);
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
 
     for (int64_t c0 = 0; c0 < n; c0 += CHUNK_PAIRS) {
@@ -553,6 +610,10 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
         a.db1 = db1; a.db2 = db2; a.dq = dq; a.dpsqrt = dps;
         a.dws = dw_lr ? dw_lr + 2 * (int64_t)d1 * d1 : nullptr; a.dc = dc;
         const int64_t ntiles = (nc + TILE_PAIRS - 1) / TILE_PAIRS;
+        if (pre) {
+            int rc = score_tc(false, a.x1, a.x2, nullptr, nullptr, 0, nullptr, nc, FL, fpack, nullptr, 0, st, DA, G, cap);
+            if (rc != NPLDA_OK) return rc;
+        }
         kern<<<(int)std::min<int64_t>(ntiles, sm_count()), NTHREADS, BWD_SMEM_BYTES, st>>>(a);
         NPLDA_LAUNCH_CHECK();
 

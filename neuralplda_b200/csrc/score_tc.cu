@@ -87,6 +87,8 @@ struct Args {
                             //         guard != nullptr: run only if guard[0] is set (fallback pass), then clear it
 
     float *scores;
+    float *aout, *yout;     // EMIT (backward, score_bwd.cu): a = W1 x + b1 and y rows, [2 * emit_cap][EMIT_LD] fp32,
+    int64_t emit_cap;       //       side 0 of pair p in row p, side 1 in row emit_cap + p; no scores are written
     long long *trace;       // cycle-accounting buffer (env NPLDA_TC_PROF), CTA 0 only
     int dbg;                // bottleneck experiments (env NPLDA_TC_DEBUG): 1 no x loads, 2 no weight copies, 4 no MMAs
 };
@@ -163,7 +165,9 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
 // fails already parks the warp for ~60 cycles), so these are plain polling waits.
 #define WAIT_OFFPATH(bar, par) mbar_wait(bar, par)
 
-template <bool PROF, int MODE>
+constexpr int EMIT_LD = 192;   // row stride of the emitted a / y rows = NP of the SIMT backward workspace
+
+template <bool PROF, int MODE, bool EMIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -222,6 +226,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         const float2 *ps = reinterpret_cast<const float2 *>(par + 2 * NPAD);
         const float2 *qs = reinterpret_cast<const float2 *>(par + 3 * NPAD);
 
+        float *ea0 = nullptr, *ea1 = nullptr, *ey0 = nullptr, *ey1 = nullptr;   // EMIT: this thread's two rows of the tile
         auto pass1 = [&](const uint32_t (&v)[8], int c0, float (&ss)[4]) {
             const float2 ba = b1s[(c0 >> 1) + cq], bb = b1s[(c0 >> 1) + 4 + cq];
             const float a00 = fmaf(__uint_as_float(v[0]), s1, ba.x), a01 = fmaf(__uint_as_float(v[1]), s1, ba.y);
@@ -232,6 +237,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             ss[0] = fmaf(a02, a02, ss[0]); ss[1] = fmaf(a03, a03, ss[1]);
             ss[2] = fmaf(a10, a10, ss[2]); ss[3] = fmaf(a11, a11, ss[3]);
             ss[2] = fmaf(a12, a12, ss[2]); ss[3] = fmaf(a13, a13, ss[3]);
+            if (EMIT) {
+                *reinterpret_cast<float2 *>(ea0 + c0 + 2 * cq) = make_float2(a00, a01);
+                *reinterpret_cast<float2 *>(ea0 + c0 + 8 + 2 * cq) = make_float2(a02, a03);
+                *reinterpret_cast<float2 *>(ea1 + c0 + 2 * cq) = make_float2(a10, a11);
+                *reinterpret_cast<float2 *>(ea1 + c0 + 8 + 2 * cq) = make_float2(a12, a13);
+            }
             uint32_t hi, lo;
             const int kc = c0 >> 3;
             split_bf16x2(a00, a01, hi, lo);
@@ -254,6 +265,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const float y10 = fmaf(__uint_as_float(v[2]), r1, ba.x), y11 = fmaf(__uint_as_float(v[3]), r1, ba.y);
             const float y02 = fmaf(__uint_as_float(v[4]), r0, bb.x), y03 = fmaf(__uint_as_float(v[5]), r0, bb.y);
             const float y12 = fmaf(__uint_as_float(v[6]), r1, bb.x), y13 = fmaf(__uint_as_float(v[7]), r1, bb.y);
+            if (EMIT) {
+                *reinterpret_cast<float2 *>(ey0 + c0 + 2 * cq) = make_float2(y00, y01);
+                *reinterpret_cast<float2 *>(ey0 + c0 + 8 + 2 * cq) = make_float2(y02, y03);
+                *reinterpret_cast<float2 *>(ey1 + c0 + 2 * cq) = make_float2(y10, y11);
+                *reinterpret_cast<float2 *>(ey1 + c0 + 8 + 2 * cq) = make_float2(y12, y13);
+            }
             sc[0] = fmaf(qa.x, fmaf(y00, y00, y10 * y10), sc[0]); sc[0] = fmaf(2.f * pa.x, y00 * y10, sc[0]);
             sc[1] = fmaf(qa.y, fmaf(y01, y01, y11 * y11), sc[1]); sc[1] = fmaf(2.f * pa.y, y01 * y11, sc[1]);
             sc[0] = fmaf(qb.x, fmaf(y02, y02, y12 * y12), sc[0]); sc[0] = fmaf(2.f * pb.x, y02 * y12, sc[0]);
@@ -264,6 +281,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const int d = (int)(i & 1);
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
             const uint32_t taddr = tbase + d * NPAD;
+            if (EMIT) {
+                const int64_t pe = min((blockIdx.x + i * gridDim.x) * TP + pl, g.emit_cap - 1);
+                ea0 = g.aout + pe * EMIT_LD; ea1 = g.aout + (g.emit_cap + pe) * EMIT_LD;
+                ey0 = g.yout + pe * EMIT_LD; ey1 = g.yout + (g.emit_cap + pe) * EMIT_LD;
+            }
             // ---- layer-1 accumulator: a = D + b1, |a|, bf16 hi/lo of a -> U (normalised after layer 2) ----
             PMARK(5);
             WAIT_OFFPATH(&d_full[d], par_d);
@@ -324,7 +346,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + pl;
-            if (cq == 0 && pr < g.n) g.scores[pr] = s;
+            if (!EMIT && cq == 0 && pr < g.n) g.scores[pr] = s;
         }
         if (warp == 0 && lane == 0) PFLUSH(0);
     } else if (warp < WARP_MMA) {
@@ -830,9 +852,9 @@ static int *guard_slot() {
     return ring[dev] + 2 * (ticket.fetch_add(1, std::memory_order_relaxed) & 1023u);
 }
 
-template <bool PROF, int MODE>
+template <bool PROF, int MODE, bool EMIT = false>
 static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Args &a, int grid, cudaStream_t st) {
-    auto kern = tcg::score_tc_kernel<PROF, MODE>;
+    auto kern = tcg::score_tc_kernel<PROF, MODE, EMIT>;
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
     kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
     NPLDA_LAUNCH_CHECK();
@@ -842,7 +864,8 @@ static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Ar
 // mode 0: bf16x3 kernel.  mode 1: fp16 + 2 x e4m3 kernel for layer 1, then the bf16x3 kernel as a guarded
 // fallback pass (a no-op launch unless the range guard fired).
 int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2, int64_t n_rows,
-             int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack, float *scores, int mode, cudaStream_t st) {
+             int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack, float *scores, int mode, cudaStream_t st,
+             float *aout, float *yout, int64_t emit_cap) {
     (void)i2; (void)n_rows; (void)bad_flag;
     if (dplda || i1 || !tc_dims_ok(L.d_in, L.d1, L.d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n >= (int64_t)1 << 31) return NPLDA_ERR_UNSUPPORTED_DIM;   // TMA row coordinates are int32
@@ -860,6 +883,13 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
     a.b1 = (const float *)(pack + L.b1); a.b2 = (const float *)(pack + L.b2);
     a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.q);
     a.scores = scores;
+    a.aout = aout; a.yout = yout; a.emit_cap = emit_cap;
+    if (aout != nullptr) {      // backward: a and y rows for the SIMT tile kernel, bf16x3 kernel, no scores
+        if (!yout || emit_cap < (n + tcg::TP - 1) / tcg::TP * tcg::TP) return NPLDA_ERR_BAD_ARG;
+        a.guard = nullptr; a.dbg = 0; a.trace = nullptr;
+        const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
+        return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
+    }
     {
         const char *e = getenv("NPLDA_TC_DEBUG");
         a.dbg = e ? atoi(e) : 0;

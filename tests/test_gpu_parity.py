@@ -924,3 +924,37 @@ def test_config5_dplda_training_step_shard(ref_out, kaldi_params):
     ref = O.dplda_score(x1[idx].cpu(), x2[idx].cpu(), kp["W1"], kp["b1"], w, c)
     ok, worst = parity_ok(out[idx], ref, rel=1e-4)
     assert ok, worst
+
+
+def test_backward_with_emitted_activations(kaldi_params, cfg1):
+    """NeuralPlda backward with a = W1 x + b1 and y emitted by the tcgen05 forward kernel (EMIT mode) instead of being
+    recomputed in fp32 by the tile kernel: all parameter gradients and the input gradients within 1e-4 of their
+    largest entry of the all-fp32 path, on a ragged batch spanning a partial tile."""
+    x1, x2, t = cfg1
+    n = 9000 + 37
+    y = t[:n].to(DEV)
+    grads = {}
+    for emit in ("0", "1"):
+        os.environ["NPLDA_BWD_EMIT"] = emit
+        os.environ["NPLDA_BWD_GEMM"] = "simt"
+        try:
+            m = make_nplda(kaldi_params, loss="SoftCdet")
+            a, b = x1[:n].to(DEV).requires_grad_(True), x2[:n].to(DEV).requires_grad_(True)
+            m.loss(m(a, b), y).backward()
+            torch.cuda.synchronize()
+            grads[emit] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+            grads[emit]["x1"], grads[emit]["x2"] = a.grad.clone(), b.grad.clone()
+        finally:
+            os.environ.pop("NPLDA_BWD_EMIT", None)
+            os.environ.pop("NPLDA_BWD_GEMM", None)
+    for k, g0 in grads["0"].items():
+        scale = float(g0.abs().max()) + 1e-30
+        assert float((grads["1"][k] - g0).abs().max()) <= 1e-4 * scale, k
+
+
+@pytest.mark.parametrize("lossname", ["SoftCdet", "crossentropy"])
+def test_emitted_activations_vs_reference_autograd(ref_out, kaldi_params, cfg1, lossname, monkeypatch):
+    """The golden .grad of the unmodified reference (2048 pairs) with both tensor-core pieces of the backward forced."""
+    monkeypatch.setenv("NPLDA_BWD_EMIT", "1")
+    monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
+    test_nplda_training_step_gradients(ref_out, kaldi_params, cfg1, lossname)
