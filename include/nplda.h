@@ -107,6 +107,13 @@ int nplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d
  *   S = u1^T(Wb+Wb^T)u2 + u1^T Ww u1 + u2^T Ww u2 + ws.(u1+u2) + c          */
 int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,
                     const void *pack, float *scores, int impl, void *stream);
+/* The same with a caller-owned workspace of dplda_fwd_workspace_bytes(n, d_in, d1) bytes (256-byte aligned):
+ * for 512-170-like shapes NPLDA_IMPL_AUTO then evaluates layer 1 and the two 170 x 170 forms on the tensor cores
+ * (two EMIT passes of the tcgen05 kernel + one finishing kernel, ~3x the fp32 SIMT kernel); without a
+ * workspace, or for other shapes, it is dplda_score_fwd. */
+int64_t dplda_fwd_workspace_bytes(int64_t n, int d_in, int d1);
+int dplda_score_fwd_ws(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
+                       float *scores, int impl, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* The two half-steps of forward, which the reference exposes as public methods:
  * embeddings (models.py:366-370: y = W2 normalize(W1 x + b1) + b2, [n, d2]; DPlda 478-481:

@@ -44,6 +44,8 @@ SIGNATURES = {
                                         c_vp, c_int, c_vp]),
     "dplda_score_fwd_indexed": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
                                         c_int, c_vp]),
+    "dplda_fwd_workspace_bytes": (c_i64, [c_i64, c_int, c_int]),
+    "dplda_score_fwd_ws": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
     "nplda_gather_pairs": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "nplda_rowtab_bytes": (c_i64, [c_i64]),
     "nplda_table_prepare": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),

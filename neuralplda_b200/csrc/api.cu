@@ -31,6 +31,10 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
              float *scores, int mode, cudaStream_t st, float *aout = nullptr, float *yout = nullptr,
              int64_t emit_cap = 0);   // score_tc.cu
 
+bool tc_dplda_ok(const PackLayout &L);   // score_tc.cu
+int dplda_score_tc(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+                   void *workspace, int64_t workspace_bytes, cudaStream_t st);   // dplda_tc.cu
+
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
              float *out, int64_t ld_out, cudaStream_t st, const unsigned long long *fp_cur = nullptr,
              const unsigned long long *fp_built = nullptr);   // score_simt.cu
@@ -105,6 +109,21 @@ extern "C" int nplda_score_fwd(const float *x1, const float *x2, int64_t n, int 
 extern "C" int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,
                                const void *pack, float *scores, int impl, void *stream) {
     return score_dispatch(true, x1, x2, nullptr, nullptr, 0, nullptr, n, d_in, d1, d1, pack, scores, impl, stream);
+}
+
+extern "C" int dplda_score_fwd_ws(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
+                                  float *scores, int impl, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (n < 0 || !pack || (n > 0 && (!x1 || !x2 || !scores))) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n == 0) return NPLDA_OK;
+    const PackLayout L = make_pack_layout(d_in, d1, d1);
+    const bool aligned = ((((uintptr_t)x1) | ((uintptr_t)x2)) & 15) == 0;
+    const bool tc_ok = tc_dplda_ok(L) && aligned && workspace != nullptr;
+    if (impl == NPLDA_IMPL_TC && !tc_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (impl == NPLDA_IMPL_TC || (impl == NPLDA_IMPL_AUTO && tc_ok && n >= 1024))
+        return dplda_score_tc(x1, x2, n, L, (const char *)pack, scores, workspace, workspace_bytes, (cudaStream_t)stream);
+    return score_dispatch(true, x1, x2, nullptr, nullptr, 0, nullptr, n, d_in, d1, d1, pack, scores,
+                          impl == NPLDA_IMPL_SIMT ? NPLDA_IMPL_SIMT : NPLDA_IMPL_AUTO, stream);
 }
 
 extern "C" int nplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *idx1,

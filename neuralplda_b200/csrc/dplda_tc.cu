@@ -1,0 +1,83 @@
+// DPlda forward on the tensor cores (models.py:478-495 in the closed form of SURVEY.md 8 a-6):
+//     u = normalize(W1 x + b1)
+//     S = u1^T Pm u2 + u1^T Ww u1 + u2^T Ww u2 + ws.(u1 + u2) + c ,   Pm = Wb + Wb^T
+// The reference materialises a 57 970-wide feature vector per trial (models.py:483-489).  Here two passes of the
+// tcgen05 score kernel in EMIT mode (score_tc.cu) leave, per row, a = W1 x + b1, V = Ww u and Z = Pm u in a
+// workspace (layer 1 is evaluated in both passes: the kernel is bound by its x stream either way), and one
+// warp per pair finishes  S = (a1.Z2 + a1.V1 + ws.a1) / |a1| + (a2.V2 + ws.a2) / |a2| + c.
+// Pairs are processed in chunks so that the workspace stays at 3 x [2 * chunk][192] fp32.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace nplda {
+
+bool tc_dplda_ok(const PackLayout &L);   // score_tc.cu
+int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, int which,
+                        float *aout, float *yout, int64_t emit_cap, cudaStream_t st);   // score_tc.cu
+
+namespace dtc {
+
+constexpr int64_t CHUNK_PAIRS = 131072;
+constexpr int LD = NP;                   // 192 floats per emitted row, 176 of them written
+
+__global__ void __launch_bounds__(256) dplda_finish_kernel(const float *__restrict__ A, const float *__restrict__ V,
+                                                           const float *__restrict__ Z, int64_t cap, int64_t nc,
+                                                           const float *__restrict__ ws, const float *__restrict__ c,
+                                                           float *__restrict__ scores) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = w0; p < nc; p += nw) {
+        const float4 *a1 = reinterpret_cast<const float4 *>(A + p * LD), *a2 = reinterpret_cast<const float4 *>(A + (cap + p) * LD);
+        const float4 *v1 = reinterpret_cast<const float4 *>(V + p * LD), *v2 = reinterpret_cast<const float4 *>(V + (cap + p) * LD);
+        const float4 *z2 = reinterpret_cast<const float4 *>(Z + (cap + p) * LD);
+        const float4 *w4 = reinterpret_cast<const float4 *>(ws);
+        float n1 = 0.f, n2 = 0.f, t1 = 0.f, t2 = 0.f;
+        for (int k = lane; k < 176 / 4; k += 32) {
+            const float4 x1 = a1[k], x2 = a2[k], y1 = v1[k], y2 = v2[k], zz = z2[k], w = w4[k];
+            n1 += x1.x * x1.x + x1.y * x1.y + x1.z * x1.z + x1.w * x1.w;
+            n2 += x2.x * x2.x + x2.y * x2.y + x2.z * x2.z + x2.w * x2.w;
+            t1 += x1.x * (zz.x + y1.x + w.x) + x1.y * (zz.y + y1.y + w.y) + x1.z * (zz.z + y1.z + w.z) + x1.w * (zz.w + y1.w + w.w);
+            t2 += x2.x * (y2.x + w.x) + x2.y * (y2.y + w.y) + x2.z * (y2.z + w.z) + x2.w * (y2.w + w.w);
+        }
+        n1 = warp_sum(n1); n2 = warp_sum(n2); t1 = warp_sum(t1); t2 = warp_sum(t2);
+        if (lane == 0) scores[p] = t1 / fmaxf(sqrtf(n1), 1e-12f) + t2 / fmaxf(sqrtf(n2), 1e-12f) + c[0];
+    }
+}
+
+static int64_t cap_for(int64_t n) { return (std::min(n, CHUNK_PAIRS) + TILE_PAIRS - 1) / TILE_PAIRS * TILE_PAIRS; }
+
+}  // namespace dtc
+
+int dplda_score_tc(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+                   void *workspace, int64_t workspace_bytes, cudaStream_t st) {
+    if (!tc_dplda_ok(L)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    const int64_t cap = dtc::cap_for(n);
+    if (!workspace || ((uintptr_t)workspace & 255) != 0) return NPLDA_ERR_BAD_ARG;
+    if (workspace_bytes < 3 * 2 * cap * dtc::LD * 4) return NPLDA_ERR_WORKSPACE;
+    float *A = (float *)workspace, *V = A + 2 * cap * dtc::LD, *Z = V + 2 * cap * dtc::LD;
+    for (int64_t c0 = 0; c0 < n; c0 += dtc::CHUNK_PAIRS) {
+        const int64_t nc = std::min(dtc::CHUNK_PAIRS, n - c0);
+        const float *a = x1 + c0 * L.d_in, *b = x2 + c0 * L.d_in;
+        int rc = score_tc_dplda_emit(a, b, nc, L, pack, 0, A, V, cap, st);            // a, V = Ww u
+        if (rc != NPLDA_OK) return rc;
+        rc = score_tc_dplda_emit(a, b, nc, L, pack, 1, nullptr, Z, cap, st);          // Z = Pm u
+        if (rc != NPLDA_OK) return rc;
+        const int grid = (int)std::min<int64_t>((nc + 7) / 8, 16 * (int64_t)sm_count());
+        dtc::dplda_finish_kernel<<<grid, 256, 0, st>>>(A, V, Z, cap, nc, (const float *)(pack + L.b2),
+                                                        (const float *)(pack + L.c), scores + c0);
+        NPLDA_LAUNCH_CHECK();
+    }
+    return NPLDA_OK;
+}
+
+}  // namespace nplda
+
+using namespace nplda;
+
+extern "C" int64_t dplda_fwd_workspace_bytes(int64_t n, int d_in, int d1) {
+    if (n < 0) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (!tc_dplda_ok(make_pack_layout(d_in, d1, d1))) return 0;           // SIMT kernel: no workspace
+    return 3 * 2 * dtc::cap_for(n) * dtc::LD * 4;
+}

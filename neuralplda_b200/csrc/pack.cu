@@ -78,6 +78,9 @@ __global__ void pack_dplda_kernel(const float *__restrict__ W1, const float *__r
     const int64_t total = n1 + 2 * n2 + 2 * NP + 1;
     const int64_t span = ((total + blockDim.x - 1) / blockDim.x) * blockDim.x;
     unsigned long long h = 0ull;
+    if (blockIdx.x == 0)                              // p and q are not DPlda parameters: zero vectors the tensor-core
+        for (int i = threadIdx.x; i < 2 * NP; i += blockDim.x)     // EMIT passes use as "layer-2 bias"
+            ((float *)(pack + (i < NP ? L.p : L.q)))[i % NP] = 0.f;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < span;
          e += (int64_t)gridDim.x * blockDim.x) {
         if (e >= total) continue;

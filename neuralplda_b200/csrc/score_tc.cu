@@ -237,7 +237,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             ss[0] = fmaf(a02, a02, ss[0]); ss[1] = fmaf(a03, a03, ss[1]);
             ss[2] = fmaf(a10, a10, ss[2]); ss[3] = fmaf(a11, a11, ss[3]);
             ss[2] = fmaf(a12, a12, ss[2]); ss[3] = fmaf(a13, a13, ss[3]);
-            if (EMIT) {
+            if (EMIT && g.aout != nullptr) {
                 *reinterpret_cast<float2 *>(ea0 + c0 + 2 * cq) = make_float2(a00, a01);
                 *reinterpret_cast<float2 *>(ea0 + c0 + 8 + 2 * cq) = make_float2(a02, a03);
                 *reinterpret_cast<float2 *>(ea1 + c0 + 2 * cq) = make_float2(a10, a11);
@@ -265,7 +265,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const float y10 = fmaf(__uint_as_float(v[2]), r1, ba.x), y11 = fmaf(__uint_as_float(v[3]), r1, ba.y);
             const float y02 = fmaf(__uint_as_float(v[4]), r0, bb.x), y03 = fmaf(__uint_as_float(v[5]), r0, bb.y);
             const float y12 = fmaf(__uint_as_float(v[6]), r1, bb.x), y13 = fmaf(__uint_as_float(v[7]), r1, bb.y);
-            if (EMIT) {
+            if (EMIT && g.yout != nullptr) {
                 *reinterpret_cast<float2 *>(ey0 + c0 + 2 * cq) = make_float2(y00, y01);
                 *reinterpret_cast<float2 *>(ey0 + c0 + 8 + 2 * cq) = make_float2(y02, y03);
                 *reinterpret_cast<float2 *>(ey1 + c0 + 2 * cq) = make_float2(y10, y11);
@@ -283,8 +283,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const uint32_t taddr = tbase + d * NPAD;
             if (EMIT) {
                 const int64_t pe = min((blockIdx.x + i * gridDim.x) * TP + pl, g.emit_cap - 1);
-                ea0 = g.aout + pe * EMIT_LD; ea1 = g.aout + (g.emit_cap + pe) * EMIT_LD;
-                ey0 = g.yout + pe * EMIT_LD; ey1 = g.yout + (g.emit_cap + pe) * EMIT_LD;
+                if (g.aout != nullptr) { ea0 = g.aout + pe * EMIT_LD; ea1 = g.aout + (g.emit_cap + pe) * EMIT_LD; }
+                if (g.yout != nullptr) { ey0 = g.yout + pe * EMIT_LD; ey1 = g.yout + (g.emit_cap + pe) * EMIT_LD; }
             }
             // ---- layer-1 accumulator: a = D + b1, |a|, bf16 hi/lo of a -> U (normalised after layer 2) ----
             PMARK(5);
@@ -680,8 +680,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
 // Step s of an image covers K = [16 s, 16 s + 16):  [hi chunk 0][hi chunk 1][lo chunk 0][lo chunk 1],
 // a chunk = 22 core matrices of 8 rows x 8 k (128 B each); element (row n, k) of a chunk sits at
 // (n/8)*128 + (n%8)*16 + (k%8)*2.
+// sym: pack W + W^T (square W) -- DPlda's Pm = Wb + Wb^T and R = Ww + Ww^T.
 __global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ksteps, uint8_t *__restrict__ img,
-                               float *__restrict__ hdr_invalidate) {
+                               float *__restrict__ hdr_invalidate, int sym = 0) {
     // hdr[2] = 0 marks the MODE 1 image as not built (pack flag NPLDA_PACK_MIXED off): the mixed kernel then flags
     // every tile for the bf16x3 pass behind it
     if (hdr_invalidate && blockIdx.x == 0 && threadIdx.x == 0) { hdr_invalidate[0] = 1.f; hdr_invalidate[1] = 1.f; hdr_invalidate[2] = 0.f; }
@@ -692,7 +693,8 @@ __global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ks
         const int c = (int)(((e >> 3) / NPAD) & 1);
         const int s = (int)(((e >> 3) / NPAD) >> 1);
         const int k = s * 16 + c * 8 + kk;
-        const float w = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
+        float w = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
+        if (sym && n < N && k < K) w += W[(int64_t)k * K + n];
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
         uint8_t *st = img + (size_t)s * B_STEP;
@@ -825,9 +827,37 @@ int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float
     return NPLDA_OK;
 }
 
-int tc_pack_dplda(const float *, const float *, const float *, const float *, const PackLayout &, char *,
-                  cudaStream_t) {
-    return NPLDA_OK;   // DPlda scores run on the SIMT kernel (tc_shape_ok is false for it)
+// DPlda (models.py:464-495 in closed form): the tensor-core kernel serves it in EMIT mode -- layer 1 as for
+// NeuralPlda, "layer 2" = one of three square matrices applied to the un-normalised a (the length norm commutes):
+// image 0 = Ww, image 1 = Pm = Wb + Wb^T, image 2 = R = Ww + Ww^T (images 1 and 2 live in the mixed-image area).
+static uint8_t *dplda_image(const PackLayout &L, const char *pack, int which) {
+    uint8_t *img1 = (uint8_t *)pack + L.tc;
+    uint8_t *img2 = img1 + (tcg::image_bytes(L.d_in / 16) + 255) / 256 * 256;
+    if (which == 0) return img2;
+    const int64_t sq = (tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256;
+    uint8_t *area = img2 + sq;
+    return area + (which - 1) * sq;
+}
+
+bool tc_dplda_ok(const PackLayout &L) {
+    return tc_dims_ok(L.d_in, L.d1, L.d1) && L.tc_bytes > 0 &&
+           2 * ((tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256) <= tcg::mixed_image_bytes(L.d_in);
+}
+
+int tc_pack_dplda(const float *W1, const float *, const float *w_lr, const float *, const PackLayout &L, char *pack,
+                  cudaStream_t st) {
+    if (!tc_dplda_ok(L)) return NPLDA_OK;
+    const int ks2 = round_up(L.d1, 16) / 16;
+    const float *Wb = w_lr, *Ww = w_lr + (int64_t)L.d1 * L.d1;          // cat order of models.py:487
+    tcg::tc_pack_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / 16, (uint8_t *)pack + L.tc, nullptr, 0);
+    NPLDA_LAUNCH_CHECK();
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Ww, L.d1, L.d1, ks2, dplda_image(L, pack, 0), nullptr, 0);
+    NPLDA_LAUNCH_CHECK();
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Wb, L.d1, L.d1, ks2, dplda_image(L, pack, 1), nullptr, 1);
+    NPLDA_LAUNCH_CHECK();
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Ww, L.d1, L.d1, ks2, dplda_image(L, pack, 2), nullptr, 1);
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
 }
 
 // Range-guard slots of the mixed-precision path: a per-device ring of {flag, counter} pairs in device memory,
@@ -890,6 +920,7 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
         const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
         return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
     }
+    if (yout != nullptr) return NPLDA_ERR_BAD_ARG;
     {
         const char *e = getenv("NPLDA_TC_DEBUG");
         a.dbg = e ? atoi(e) : 0;
@@ -944,6 +975,30 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
         fflush(stdout);
     }
     return NPLDA_OK;
+}
+
+// DPlda in EMIT mode: rows a = W1 x + b1 (aout, may be null) and M u (yout) with M = image `which` of the DPlda pack
+// (0 Ww, 1 Pm, 2 R), u = a / |a|; zero "layer-2 bias" (the p area of a DPlda pack holds zeros).
+int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, int which,
+                        float *aout, float *yout, int64_t emit_cap, cudaStream_t st) {
+    if (!tc_dplda_ok(L) || !yout || which < 0 || which > 2) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n >= (int64_t)1 << 31 || emit_cap < (n + tcg::TP - 1) / tcg::TP * tcg::TP) return NPLDA_ERR_BAD_ARG;
+    CUtensorMap m1, m2;
+    if (!tcg::make_x_map(&m1, x1, n, L.d_in) || !tcg::make_x_map(&m2, x2, n, L.d_in)) return NPLDA_ERR_NO_DEVICE;
+    tcg::Args a;
+    a.x1 = x1; a.x2 = x2; a.n = n;
+    a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
+    a.w1img = (const uint8_t *)pack + L.tc;
+    a.w2img = dplda_image(L, pack, which);
+    a.hdr = (const float *)(pack + L.p);               // unused by MODE 0
+    a.guard = nullptr;
+    a.b1 = (const float *)(pack + L.b1);
+    a.b2 = (const float *)(pack + L.p);                // zeros
+    a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.p);
+    a.scores = nullptr; a.aout = aout; a.yout = yout; a.emit_cap = emit_cap;
+    a.trace = nullptr; a.dbg = 0;
+    const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
+    return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
 }
 
 }  // namespace nplda

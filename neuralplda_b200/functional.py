@@ -164,8 +164,12 @@ class DpldaScoreFn(torch.autograd.Function):
         pack = packed.get("dplda", (W1, b1, w_lr, c_lr), d_in, d1, d1)
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
         with on_device(x1c.device):
-            check(lib().dplda_score_fwd(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), impl,
-                                        stream_ptr()), "dplda_score_fwd")
+            wsb = lib().dplda_fwd_workspace_bytes(n, d_in, d1) if impl in (_lib.IMPL_AUTO, _lib.IMPL_TC) else 0
+            if wsb < 0:
+                check(wsb, "dplda_fwd_workspace_bytes")
+            ws = torch.empty(int(wsb), dtype=torch.uint8, device=x1c.device) if wsb > 0 else None
+            check(lib().dplda_score_fwd_ws(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), impl,
+                                           ptr(ws), int(wsb), stream_ptr()), "dplda_score_fwd")
         ctx.save_for_backward(x1c, x2c, W1, b1, w_lr)
         return scores
 
