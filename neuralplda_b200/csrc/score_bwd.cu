@@ -26,6 +26,10 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
              int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack, float *scores, int mode, cudaStream_t st,
              float *aout, float *yout, int64_t emit_cap);   // score_tc.cu (EMIT mode when aout != nullptr)
 
+bool tc_dplda_ok(const PackLayout &L);   // score_tc.cu
+int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, int which,
+                        float *aout, float *yout, int64_t emit_cap, cudaStream_t st);   // score_tc.cu
+
 namespace bwd {
 
 using namespace simt;
@@ -116,6 +120,7 @@ struct Args {
     int d_in, d1, d2, k1p, k2p, k2q;
     const float *w1t, *b1, *w2t, *w2n, *b2, *p, *q, *psq2, *rp, *ws;
     float *U, *G, *DA;         // [2*cap][NP]; G = DY (NeuralPlda) or g*U (DPlda)
+    const float *PMU;          // DPlda PRE: Pm u rows emitted by the tensor-core kernel
     float *db1, *db2, *dq, *dpsqrt, *dws, *dc;   // may be null
 };
 
@@ -124,7 +129,7 @@ __device__ __forceinline__ void col_add(float *colacc, int which, int tx, int j,
     if (lane < 16) atomicAdd(colacc + which * NP + 4 * tx + 64 * j + e, v);
 }
 
-// PRE (NeuralPlda only): a = W1 x + b1 and y = W2 u + b2 of every row were written by the tensor-core forward kernel
+// PRE: a = W1 x + b1 and y = W2 u + b2 (DPlda: R u, and Pm u in PMU) of every row were written by the tensor-core forward kernel
 // in its EMIT mode (score_tc.cu) into the DA and G areas of the workspace; the two recomputations (80 % of this
 // kernel's flops) are replaced by loads.  Each thread later overwrites exactly the elements it loaded here with
 // dL/da and dL/dy, so the aliasing is race-free.
@@ -306,7 +311,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
             layer2_gemm(acc, Us, Ws, g.w2n, g.k2q, tx, ty, tid);      // du = dy W2
         } else {
             // du = g * (R u_self + Pm u_other + ws);  g*u -> workspace
-            layer2_gemm<true>(acc, Us, Ws, g.rp, g.k2p, tx, ty, tid);
+            if (PRE) {                       // R u rows sit in the G area, Pm u rows in PMU (EMIT passes of score_tc.cu)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t rself = ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+                    const int64_t roth = ((int64_t)((i & 1) ^ 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        float4 v = *reinterpret_cast<const float4 *>(g.G + rself + 64 * j);
+                        const float4 w = *reinterpret_cast<const float4 *>(g.PMU + roth + 64 * j);
+                        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                        if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        acc[i][2 * j] = make_float2(v.x, v.y);
+                        acc[i][2 * j + 1] = make_float2(v.z, v.w);
+                    }
+                }
+            } else {
+                layer2_gemm<true>(acc, Us, Ws, g.rp, g.k2p, tx, ty, tid);
+            }
             float gtot = 0.f;
 #pragma unroll
             for (int jp = 0; jp < 4; ++jp) gtot += gs[jp];
@@ -544,7 +566,7 @@ static int64_t fwd_pack_room(int d_in, int d1, int d2) { return make_pack_layout
 
 static int64_t workspace_bytes(int64_t n, int d_in, int d1, int d2) {
     const int64_t cap = (std::min(n, CHUNK_PAIRS) + TILE_PAIRS - 1) / TILE_PAIRS * TILE_PAIRS;
-    return make_pack(d_in, d1, d2).total * 4 + 3 * 2 * cap * NP * 4 + 1024 + fwd_pack_room(d_in, d1, d2);
+    return make_pack(d_in, d1, d2).total * 4 + 4 * 2 * cap * NP * 4 + 1024 + fwd_pack_room(d_in, d1, d2);
 }
 
 // C[M,N] += A^T B: the tcgen05 bf16x3 kernel for batches worth its launch (NPLDA_BWD_GEMM=simt|tc forces one)
@@ -586,16 +608,18 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
     // not recomputed in fp32 here but emitted by the tcgen05 forward kernel (NPLDA_BWD_EMIT=0|1 forces a side)
     const PackLayout FL = make_pack_layout(d_in, d1, d2);
     bool pre = false;
-    if (!DPLDA && vec && tc_shape_ok(false, FL, false) && FL.total <= fwd_pack_room(d_in, d1, d2)) {
+    if (vec && (DPLDA ? tc_dplda_ok(FL) : tc_shape_ok(false, FL, false)) && FL.total <= fwd_pack_room(d_in, d1, d2)) {
         const char *e = getenv("NPLDA_BWD_EMIT");
         pre = e ? e[0] == '1' : n >= 4096;
     }
-    char *fpack = (char *)(DA + 2 * cap * NP);
+    float *PMU = DA + 2 * cap * NP;                        // DPlda EMIT only
+    char *fpack = (char *)(PMU + 2 * cap * NP);
     if (pre) {
-        int rc = nplda_pack_weights(W1, b1, W2, b2, ps, q, d_in, d1, d2, fpack, FL.total, 0, st);
+        int rc = DPLDA ? dplda_pack_weights(W1, b1, w_lr, nullptr, d_in, d1, fpack, FL.total, 0, st)
+                       : nplda_pack_weights(W1, b1, W2, b2, ps, q, d_in, d1, d2, fpack, FL.total, 0, st);
         if (rc != NPLDA_OK) return rc;
     }
-    auto kern = pre ? bwd_tile_kernel<DPLDA, true, !DPLDA>
+    auto kern = pre ? bwd_tile_kernel<DPLDA, true, true>
                     : (vec ? bwd_tile_kernel<DPLDA, true, false> : bwd_tile_kernel<DPLDA, false, false>);
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
 
@@ -610,8 +634,15 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
         a.db1 = db1; a.db2 = db2; a.dq = dq; a.dpsqrt = dps;
         a.dws = dw_lr ? dw_lr + 2 * (int64_t)d1 * d1 : nullptr; a.dc = dc;
         const int64_t ntiles = (nc + TILE_PAIRS - 1) / TILE_PAIRS;
-        if (pre) {
+        a.PMU = PMU;
+        if (pre && !DPLDA) {
             int rc = score_tc(false, a.x1, a.x2, nullptr, nullptr, 0, nullptr, nc, FL, fpack, nullptr, 0, st, DA, G, cap);
+            if (rc != NPLDA_OK) return rc;
+        }
+        if (pre && DPLDA) {                 // a and R u (image 2), then Pm u (image 1)
+            int rc = score_tc_dplda_emit(a.x1, a.x2, nc, FL, fpack, 2, DA, G, cap, st);
+            if (rc != NPLDA_OK) return rc;
+            rc = score_tc_dplda_emit(a.x1, a.x2, nc, FL, fpack, 1, nullptr, PMU, cap, st);
             if (rc != NPLDA_OK) return rc;
         }
         kern<<<(int)std::min<int64_t>(ntiles, sm_count()), NTHREADS, BWD_SMEM_BYTES, st>>>(a);

@@ -926,9 +926,10 @@ def test_config5_dplda_training_step_shard(ref_out, kaldi_params):
     assert ok, worst
 
 
-def test_backward_with_emitted_activations(kaldi_params, cfg1):
-    """NeuralPlda backward with a = W1 x + b1 and y emitted by the tcgen05 forward kernel (EMIT mode) instead of being
-    recomputed in fp32 by the tile kernel: all parameter gradients and the input gradients within 1e-4 of their
+@pytest.mark.parametrize("kind", ["nplda", "dplda"])
+def test_backward_with_emitted_activations(ref_out, kaldi_params, cfg1, kind):
+    """Backward with a = W1 x + b1 and y (DPlda: R u and Pm u) emitted by the tcgen05 forward kernel (EMIT mode) instead
+    of being recomputed in fp32 by the tile kernel: all parameter gradients and the input gradients within 1e-4 of their
     largest entry of the all-fp32 path, on a ragged batch spanning a partial tile."""
     x1, x2, t = cfg1
     n = 9000 + 37
@@ -938,7 +939,7 @@ def test_backward_with_emitted_activations(kaldi_params, cfg1):
         os.environ["NPLDA_BWD_EMIT"] = emit
         os.environ["NPLDA_BWD_GEMM"] = "simt"
         try:
-            m = make_nplda(kaldi_params, loss="SoftCdet")
+            m = make_nplda(kaldi_params, loss="SoftCdet") if kind == "nplda" else make_dplda(kaldi_params, ref_out)
             a, b = x1[:n].to(DEV).requires_grad_(True), x2[:n].to(DEV).requires_grad_(True)
             m.loss(m(a, b), y).backward()
             torch.cuda.synchronize()
