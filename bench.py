@@ -309,6 +309,7 @@ def run_ours(args):
         cpu_rate, cpu_s, _ = (cpu_forward_timing(kp, 10, 3, os.cpu_count(), min_seconds=12.0)
                               if not args.no_cpu_baseline else (None, 0, 0))
         tl = trial_list_leg(model, kp, dev) if (not args.skip_trial_list and world == 1) else None
+        tr = train_leg(kp, dev, x1, x2, t) if (not args.skip_trial_list and world == 1) else None
         res = {
             "metric": "trial-pairs scored/sec (512-d xvec)", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -338,9 +339,68 @@ def run_ours(args):
                                    "torch_threads": torch.get_num_threads()}
         if tl is not None:
             res["trial_list"] = tl
+        if tr is not None:
+            res["train_step"] = tr
         print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_leg(kp, dev, x1, x2, t):
+    """Extra, separately-labelled measurement: one training step (forward + BCE loss + backward into .grad) through the
+    module API on the resident 1M-pair batch, for NeuralPlda and for DPlda with the LDA frozen
+    (BASELINE.json configs[4]; its per-GPU share at 8 GPUs is 1.25M pairs).  CUDA events, 5 steps after one warm-up."""
+    import neuralplda_b200 as npl
+
+    class NCX(NC):
+        loss = "crossentropy"
+
+    class NCDP(NC):
+        loss = "crossentropy"
+        beta = [99.0]
+
+    def timeit(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n = x1.shape[0]
+    out = {"pairs": n, "loss": "crossentropy", "api": "model(x1, x2) -> model.loss(...) -> .backward()"}
+    m = npl.NeuralPlda(NCX).to(dev)
+    sd = m.state_dict()
+    for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias", "b1"),
+                      ("centering_and_wccn_plda.weight", "W2"), ("centering_and_wccn_plda.bias", "b2"),
+                      ("P_sqrt", "P_sqrt"), ("Q", "Q")):
+        sd[name].copy_(kp[key])
+
+    def nstep():
+        m.zero_grad(set_to_none=True)
+        m.loss(m(x1, x2), t).backward()
+
+    ms = timeit(nstep)
+    out["nplda"] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "pairs/s"}
+    d = npl.DPlda(NCDP).to(dev)
+    sd = d.state_dict()
+    sd["centering_and_LDA.weight"].copy_(kp["W1"]); sd["centering_and_LDA.bias"].copy_(kp["b1"])
+    for p_ in (d.centering_and_LDA.weight, d.centering_and_LDA.bias):
+        p_.requires_grad_(False)                               # xvector_DPlda_pytorch.py:140-147
+
+    def dstep():
+        d.zero_grad(set_to_none=True)
+        d.loss(d(x1, x2), t).backward()
+
+    ms = timeit(dstep)
+    out["dplda_lda_frozen"] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "pairs/s"}
+    with torch.no_grad():
+        ms = timeit(lambda: d(x1, x2))
+    out["dplda_forward"] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "pairs/s"}
+    return out
 
 
 def trial_list_leg(model, kp, dev):

@@ -35,7 +35,7 @@ constexpr int A_TILE = 2 * A_HALF;
 constexpr int B_HALF = NCHUNK * KCH_B;
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_HALF;   // 55,296
 constexpr int NSTAGE = 3;
-constexpr int CONV_WARPS = 16;
+constexpr int CONV_WARPS = 15;                 // + the MMA warp = 16 warps: 128 registers per thread
 constexpr int NTHREADS = (CONV_WARPS + 1) * 32;
 constexpr int HDR_BYTES = 1024;
 constexpr int SMEM_BYTES = HDR_BYTES + NSTAGE * STAGE_BYTES;
@@ -97,39 +97,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(Args g) {
 
     if (warp < CONV_WARPS) {
         // ---------------- converters: global fp32 -> bf16 hi/lo K-major core matrices ----------------
-        const int ntask = 16 * mtiles + 24;          // warp-tasks per stage: (operand column group of 32) x (8-row group)
-        Ring ring(NSTAGE);
-        for (int it = 0; it < nit; ++it, ring.advance()) {
+        // A warp-task = 32 consecutive columns of one operand x one 8-row group of the stage; warp w owns tasks
+        // w, w + 15, w + 30, w + 45.  What a task touches is fixed for the whole kernel (column, stage offset), only
+        // the rows advance: everything but the loads themselves is hoisted out of the loop, and the loads of stage
+        // it + 1 are issued before stage it is converted (two register sets), so that ~8 KB per warp are in flight.
+        const int ntask = 16 * mtiles + 24;
+        const float *src[4];                          // first row of the task in stage 0 (nullptr: column is padding)
+        int64_t ldq[4];
+        int soff[4], grp8[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int t = warp + CONV_WARPS * q;
+            soff[q] = -1; src[q] = nullptr; ldq[q] = 0; grp8[q] = 0;
+            if (t >= ntask) continue;
+            const bool isA = t < 16 * mtiles;
+            const int u = isA ? t : t - 16 * mtiles;
+            const int grp = u & 3, cw = u >> 2;                   // 8-row group, column group (A: mt * 4 + cw4)
+            const int c = (isA ? (cw & 3) : cw) * 32 + lane;      // column inside the M tile / inside B
+            const int mt = isA ? (cw >> 2) : 0;
+            const int col = isA ? m0 + mt * MT + c : c;           // column in the source matrix
+            if (!isA && c >= NPADN) continue;                     // the B image has 176 columns
+            soff[q] = (isA ? mt * A_TILE + grp * KCH_A : 2 * A_TILE + grp * KCH_B) + (c >> 3) * 128 + (c & 7) * 16;
+            grp8[q] = grp * 8;
+            ldq[q] = isA ? g.lda : g.ldb;
+            if (isA ? col < g.Mfeat : col < g.Nfeat) src[q] = (isA ? g.A : g.B) + col + (r0 + grp * 8) * ldq[q];
+        }
+        auto load_stage = [&](int it, float (&v)[4][8]) {
             const int64_t rb = r0 + (int64_t)it * KS;
-            float v[4][8];
-            int soff[4];                              // byte offset of the task's hi line inside the stage, -1 = nothing to store
+            const bool full_stage = rb + KS <= r1;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int t = warp + 16 * q;
-                soff[q] = -1;
+                const float *p = src[q] + (int64_t)it * KS * ldq[q];
+                if (src[q] == nullptr) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[q][j] = 0.f;
-                if (t >= ntask) continue;
-                const bool isA = t < 16 * mtiles;
-                const int u = isA ? t : t - 16 * mtiles;
-                const int grp = u & 3, cw = u >> 2;                   // 8-row group, column group (A: mt*4 + cw4)
-                const int c = (isA ? (cw & 3) : cw) * 32 + lane;      // column inside the M tile / inside B
-                const int mt = isA ? (cw >> 2) : 0;
-                const int col = isA ? m0 + mt * MT + c : c;           // column in the source matrix
-                const bool cok = isA ? col < g.Mfeat : col < g.Nfeat;
-                if (!isA && c >= NPADN) continue;                     // B image has 176 columns
-                soff[q] = (isA ? mt * A_TILE + grp * KCH_A : 2 * A_TILE + grp * KCH_B) + (c >> 3) * 128 + (c & 7) * 16;
-                if (cok) {
-                    const float *src = (isA ? g.A : g.B) + col;
-                    const int ld = isA ? g.lda : g.ldb;
-                    const int64_t rr = rb + grp * 8;
+                    for (int j = 0; j < 8; ++j) v[q][j] = 0.f;
+                } else if (full_stage) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (rr + j < r1) v[q][j] = __ldg(src + (rr + j) * ld);
+                    for (int j = 0; j < 8; ++j) v[q][j] = __ldg(p + j * ldq[q]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[q][j] = (rb + grp8[q] + j < r1) ? __ldg(p + j * ldq[q]) : 0.f;
                 }
             }
-            wait_or_trap(&empty[ring.stage], ring.phase ^ 1);         // the MMAs that read this stage have completed
-            uint8_t *st = stages + ring.stage * STAGE_BYTES;
+        };
+        auto store_stage = [&](const float (&v)[4][8], uint8_t *st) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (soff[q] < 0) continue;
@@ -142,17 +153,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(Args g) {
                 *reinterpret_cast<uint4 *>(st + soff[q]) = hi;
                 *reinterpret_cast<uint4 *>(st + soff[q] + (isA ? A_HALF : B_HALF)) = lo;
             }
+        };
+        Ring ring(NSTAGE);
+        float va[4][8], vb[4][8];
+        load_stage(0, va);
+        for (int it = 0; it < nit; it += 2) {
+            if (it + 1 < nit) load_stage(it + 1, vb);
+            wait_or_trap(&empty[ring.stage], ring.phase ^ 1);         // the MMAs that read this stage have completed
+            store_stage(va, stages + ring.stage * STAGE_BYTES);
             fence_proxy_async();                                      // generic-proxy stores -> tcgen05.mma operand reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[ring.stage]);
+            ring.advance();
+            if (it + 1 >= nit) break;
+            if (it + 2 < nit) load_stage(it + 2, va);
+            wait_or_trap(&empty[ring.stage], ring.phase ^ 1);
+            store_stage(vb, stages + ring.stage * STAGE_BYTES);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[ring.stage]);
+            ring.advance();
         }
         // ---------------- epilogue: C[n][m] += D[m][n] ----------------
         wait_or_trap(done, 0);
         tc_fence_after();
-        const int q4 = warp & 3;
+        const int q4 = warp & 3;                                      // a warp reaches the TMEM lanes of quadrant warp % 4
+        const int nwq = (CONV_WARPS - q4 + 3) / 4;                    // converter warps sharing this quadrant
         for (int mt = 0; mt < mtiles; ++mt) {
             const int m = m0 + mt * MT + 32 * q4 + lane;
-            for (int blk = warp >> 2; blk < NPADN / 16; blk += 4) {
+            for (int blk = warp >> 2; blk < NPADN / 16; blk += nwq) {
                 uint32_t r[16];
                 tmem_ld16(tmem + ((uint32_t)(32 * q4) << 16) + mt * NPADN + blk * 16, r);
                 tmem_ld_wait();

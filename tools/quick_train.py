@@ -16,7 +16,7 @@ class NCX(bench.NC):
     loss = "crossentropy"
 class NCD(bench.NC):
     loss = "crossentropy"; beta = [99.0]
-for n in (131072, 1_000_000):
+for n in ([int(sys.argv[1])] if len(sys.argv) > 1 else [131072, 1_000_000]):
     x1, x2, t = bench.synth_on_device(n, 1005, kp["mean"].to(dev), dev)
     m = npl.NeuralPlda(NCX).to(dev)
     sd = m.state_dict()

@@ -42,13 +42,39 @@ if os.path.exists(src):
             f.write(f"{100 * v[1] / tot:.2f},{v[0]},{v[1] / v[0]:.1f},\"{k[:110]}\"\n")
     print("wrote launches", len(ours))
 
+# ---- launch list of the training steps (tools/quick_train.py 131072: NeuralPlda step, DPlda forward, DPlda step)
+src = os.path.join(G, f"{tag}_train_launches.csv")
+if os.path.exists(src):
+    rows = [r for r in csv.reader(l for l in open(src) if l.startswith('"'))]
+    hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
+    agg = {}
+    for r in rows[1:]:
+        if r[ix["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        name = r[ix["Kernel Name"]]
+        v = float(r[ix["Metric Value"]].replace(",", ""))
+        unit = r[ix["Metric Unit"]]
+        v_us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v_us
+    ours = {k: v for k, v in agg.items() if "nplda" in k or "tcg::" in k or "gtc::" in k or "bwd::" in k or "simt::" in k}
+    tot = sum(v[1] for v in ours.values())
+    with open(os.path.join(P, f"{rnd}_train_launches.csv"), "w") as f:
+        f.write(f"# ncu launch list of training steps, {rnd} (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare shares)\n")
+        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv python tools/quick_train.py 131072\n")
+        f.write("# first 120 launches: warm-up + timed NeuralPlda steps (forward, BCE, backward) on 131072 pairs; libnplda kernels only\n")
+        f.write("share_pct,launches,avg_us,kernel\n")
+        for k, v in sorted(ours.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{100 * v[1] / tot:.2f},{v[0]},{v[1] / v[0]:.1f},\"{k[:110]}\"\n")
+    print("wrote train launches", len(ours))
+
 # ---- full captures
 def raw(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
-for name, outname in ((f"{tag}_score_tc.ncu-rep", f"{rnd}_score_tc_kernel_ncu.csv"), (f"{tag}_score_pairs.ncu-rep", f"{rnd}_score_pairs_kernel_ncu.csv")):
+for name, outname in ((f"{tag}_score_tc.ncu-rep", f"{rnd}_score_tc_kernel_ncu.csv"), (f"{tag}_score_pairs.ncu-rep", f"{rnd}_score_pairs_kernel_ncu.csv"),
+                      (f"{tag}_score_grid.ncu-rep", f"{rnd}_score_grid_kernel_ncu.csv"), (f"{tag}_gemm_tc.ncu-rep", f"{rnd}_gemm_tc_kernel_ncu.csv")):
     rep = os.path.join(G, name)
     if not os.path.exists(rep):
         continue
