@@ -187,6 +187,22 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # libraries (NCCL's version banner) write to the C-level stdout: keep fd 1 for the ONE JSON line
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _run_ours(args, saved_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+
+
+def _emit(saved_stdout, obj):
+    sys.stdout.flush()
+    os.write(saved_stdout, (json.dumps(obj) + "\n").encode())
+
+
+def _run_ours(args, saved_stdout):
     import torch.distributed as dist
     import neuralplda_b200 as npl
     from neuralplda_b200 import _lib, functional as F_
@@ -274,7 +290,7 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 10))
     if args.skip_e2e:                                # profiling runs (ncu) only: never a bench line
         if rank == 0:
-            print(json.dumps({"profiling_only": True, "k1_ms": k1_ms, "ms_per_step": total_ms / args.steps}), flush=True)
+            _emit(saved_stdout, {"profiling_only": True, "k1_ms": k1_ms, "ms_per_step": total_ms / args.steps})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -341,7 +357,7 @@ def run_ours(args):
             res["trial_list"] = tl
         if tr is not None:
             res["train_step"] = tr
-        print(json.dumps(res), flush=True)
+        _emit(saved_stdout, res)
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,6 +30,11 @@ bool tc_dplda_ok(const PackLayout &L);   // score_tc.cu
 int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, int which,
                         float *aout, float *yout, int64_t emit_cap, cudaStream_t st);   // score_tc.cu
 
+int64_t tc_rows_image_bytes(int d_in);   // score_tc.cu
+int tc_rows_image_pack(const float *Wkn, int64_t ldk, int N, int K, int d_in, uint8_t *img, cudaStream_t st);
+int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int d_in, const uint8_t *w1img, const uint8_t *w2img_any,
+                       int ksteps2, const float *zeros, float *aout, int64_t emit_cap, cudaStream_t st);
+
 namespace bwd {
 
 using namespace simt;
@@ -133,7 +138,10 @@ __device__ __forceinline__ void col_add(float *colacc, int which, int tx, int j,
 // in its EMIT mode (score_tc.cu) into the DA and G areas of the workspace; the two recomputations (80 % of this
 // kernel's flops) are replaced by loads.  Each thread later overwrites exactly the elements it loaded here with
 // dL/da and dL/dy, so the aliasing is race-free.
-template <bool DPLDA, bool VEC, bool PRE>
+// PHASE (with PRE, NeuralPlda): 0 = everything in one launch; 1 = up to dL/dy (U, DY rows and the b2 / P / Q sums), the
+// product dL/du = dL/dy . W2 then runs on the tensor cores (score_tc_rows_emit) into the PMU area; 2 = the rest
+// (dL/da from dL/du, b1 sums).
+template <bool DPLDA, bool VEC, bool PRE, int PHASE = 0>
 __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
     extern __shared__ __align__(16) float smem[];
     float *As = smem;
@@ -238,14 +246,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
                     u.y = acc[i][2 * j].y / den;
                     u.z = acc[i][2 * j + 1].x / den;
                     u.w = acc[i][2 * j + 1].y / den;
-                    *reinterpret_cast<float4 *>(urow + 64 * j) = u;
-                    if (live[jp]) *reinterpret_cast<float4 *>(grow + 64 * j) = u;
+                    if (PHASE != 2) {
+                        *reinterpret_cast<float4 *>(urow + 64 * j) = u;
+                        if (live[jp]) *reinterpret_cast<float4 *>(grow + 64 * j) = u;
+                    }
                 }
             }
         }
         __syncthreads();
 
-        if (!DPLDA) {
+        if (PHASE == 2) {
+            // dL/du rows from the tensor-core pass
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float *drow = g.PMU + ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float4 v = *reinterpret_cast<const float4 *>(drow + 64 * j);
+                    if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc[i][2 * j] = make_float2(v.x, v.y);
+                    acc[i][2 * j + 1] = make_float2(v.z, v.w);
+                }
+            }
+        } else if (!DPLDA) {
             // ---- recompute layer 2, form dL/dy in place ----
             if (PRE) {
 #pragma unroll
@@ -307,6 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
                     if (live[jp]) *reinterpret_cast<float4 *>(grow + 64 * j) = v;
                 }
             }
+            if (PHASE == 1) continue;                                 // du = dy W2 runs on the tensor cores
             __syncthreads();
             layer2_gemm(acc, Us, Ws, g.w2n, g.k2q, tx, ty, tid);      // du = dy W2
         } else {
@@ -562,7 +586,9 @@ __global__ void dx_kernel(const float *__restrict__ DA, const float *__restrict_
 }
 
 // room for the forward pack (tensor-core weight images) at the end of the workspace, used by the EMIT path
-static int64_t fwd_pack_room(int d_in, int d1, int d2) { return make_pack_layout(d_in, d1, d2).total + 256; }
+static int64_t fwd_pack_room(int d_in, int d1, int d2) {
+    return make_pack_layout(d_in, d1, d2).total + 512 + tc_rows_image_bytes(NP) + 256 + 1024;   // + dL/du image + zeros
+}
 
 static int64_t workspace_bytes(int64_t n, int d_in, int d1, int d2) {
     const int64_t cap = (std::min(n, CHUNK_PAIRS) + TILE_PAIRS - 1) / TILE_PAIRS * TILE_PAIRS;
@@ -622,6 +648,25 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
     auto kern = pre ? bwd_tile_kernel<DPLDA, true, true>
                     : (vec ? bwd_tile_kernel<DPLDA, true, false> : bwd_tile_kernel<DPLDA, false, false>);
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
+    // NeuralPlda with EMIT: dL/du = dL/dy . W2 also on the tensor cores (NPLDA_BWD_DU=0|1 forces a side): the tile
+    // kernel runs as two elementwise phases around a rows-in / rows-out pass of the tcgen05 kernel over the DY rows
+    bool du_tc = false;
+    uint8_t *duimg = (uint8_t *)(fpack + (FL.total + 255) / 256 * 256);
+    float *zeros = (float *)(duimg + (tc_rows_image_bytes(NP) + 255) / 256 * 256);
+    if (pre && !DPLDA && d2 <= NP) {
+        const char *e = getenv("NPLDA_BWD_DU");
+        du_tc = e ? e[0] == '1' : true;
+    }
+    auto kern1 = bwd_tile_kernel<false, true, true, 1>;
+    auto kern2 = bwd_tile_kernel<false, true, true, 2>;
+    if (du_tc) {
+        NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
+        NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
+        NPLDA_CUDA_TRY(cudaMemsetAsync(zeros, 0, 1024, st));
+        // image of M[n = layer-1 index][k = layer-2 index] = W2[k][n], read from the k-major fp32 copy w2n
+        int rc = tc_rows_image_pack(pk + P.w2n, NP, d1, d2, NP, duimg, st);
+        if (rc != NPLDA_OK) return rc;
+    }
 
     for (int64_t c0 = 0; c0 < n; c0 += CHUNK_PAIRS) {
         const int64_t nc = std::min(CHUNK_PAIRS, n - c0);
@@ -645,8 +690,19 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
             rc = score_tc_dplda_emit(a.x1, a.x2, nc, FL, fpack, 1, nullptr, PMU, cap, st);
             if (rc != NPLDA_OK) return rc;
         }
-        kern<<<(int)std::min<int64_t>(ntiles, sm_count()), NTHREADS, BWD_SMEM_BYTES, st>>>(a);
-        NPLDA_LAUNCH_CHECK();
+        if (du_tc) {
+            const int grid = (int)std::min<int64_t>(ntiles, sm_count());
+            kern1<<<grid, NTHREADS, BWD_SMEM_BYTES, st>>>(a);
+            NPLDA_LAUNCH_CHECK();
+            const uint8_t *img2 = (const uint8_t *)fpack + FL.tc + (tc_rows_image_bytes(d_in) + 255) / 256 * 256;   // W2 image of the forward pack
+            int rc = score_tc_rows_emit(G, G + cap * NP, nc, NP, duimg, img2, round_up(d1, 16) / 16, zeros, PMU, cap, st);
+            if (rc != NPLDA_OK) return rc;
+            kern2<<<grid, NTHREADS, BWD_SMEM_BYTES, st>>>(a);
+            NPLDA_LAUNCH_CHECK();
+        } else {
+            kern<<<(int)std::min<int64_t>(ntiles, sm_count()), NTHREADS, BWD_SMEM_BYTES, st>>>(a);
+            NPLDA_LAUNCH_CHECK();
+        }
 
         // Row ranges in the workspace: side 0 rows [0, nc), side 1 rows [cap, cap + nc).
         int rc = NPLDA_OK;

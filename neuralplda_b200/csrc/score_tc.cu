@@ -681,8 +681,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
 // a chunk = 22 core matrices of 8 rows x 8 k (128 B each); element (row n, k) of a chunk sits at
 // (n/8)*128 + (n%8)*16 + (k%8)*2.
 // sym: pack W + W^T (square W) -- DPlda's Pm = Wb + Wb^T and R = Ww + Ww^T.
+// sn, sk: element strides of W along n and k (0, 0 = row-major [N][K]).
 __global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ksteps, uint8_t *__restrict__ img,
-                               float *__restrict__ hdr_invalidate, int sym = 0) {
+                               float *__restrict__ hdr_invalidate, int sym = 0, int64_t sn = 0, int64_t sk = 0) {
+    if (sn == 0 && sk == 0) { sn = K; sk = 1; }
     // hdr[2] = 0 marks the MODE 1 image as not built (pack flag NPLDA_PACK_MIXED off): the mixed kernel then flags
     // every tile for the bf16x3 pass behind it
     if (hdr_invalidate && blockIdx.x == 0 && threadIdx.x == 0) { hdr_invalidate[0] = 1.f; hdr_invalidate[1] = 1.f; hdr_invalidate[2] = 0.f; }
@@ -693,8 +695,8 @@ __global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ks
         const int c = (int)(((e >> 3) / NPAD) & 1);
         const int s = (int)(((e >> 3) / NPAD) >> 1);
         const int k = s * 16 + c * 8 + kk;
-        float w = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
-        if (sym && n < N && k < K) w += W[(int64_t)k * K + n];
+        float w = (n < N && k < K) ? W[n * sn + k * sk] : 0.f;
+        if (sym && n < N && k < K) w += W[k * sn + n * sk];
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
         uint8_t *st = img + (size_t)s * B_STEP;
@@ -996,6 +998,37 @@ int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackL
     a.b2 = (const float *)(pack + L.p);                // zeros
     a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.p);
     a.scores = nullptr; a.aout = aout; a.yout = yout; a.emit_cap = emit_cap;
+    a.trace = nullptr; a.dbg = 0;
+    const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
+    return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
+}
+
+// Rows-in / rows-out product on the tensor cores, used by the backward for dL/du = dL/dy . W2: an EMIT pass whose
+// "x" are fp32 rows of width d_in (a multiple of 32; row pitch = d_in floats) and whose "layer 1" is the image
+// built by tc_rows_image_pack; out[r][0..176) = X[r] . M^T (no bias: `zeros` holds >= 176 zero floats).  Layer 2 of
+// the pass runs on an arbitrary valid image (w2img_any) and its result is discarded.
+int64_t tc_rows_image_bytes(int d_in) { return tcg::image_bytes(round_up(d_in, 16) / 16); }
+
+// M[n][k] = Wkn[k * ldk + n] (a k-major fp32 matrix), n < N, k < K, zero padded to the image's K.
+int tc_rows_image_pack(const float *Wkn, int64_t ldk, int N, int K, int d_in, uint8_t *img, cudaStream_t st) {
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Wkn, N, K, round_up(d_in, 16) / 16, img, nullptr, 0, 1, ldk);
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
+}
+
+int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int d_in, const uint8_t *w1img, const uint8_t *w2img_any,
+                       int ksteps2, const float *zeros, float *aout, int64_t emit_cap, cudaStream_t st) {
+    if (d_in % tcg::KST != 0 || d_in < tcg::KST || !aout) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n >= (int64_t)1 << 31 || emit_cap < (n + tcg::TP - 1) / tcg::TP * tcg::TP) return NPLDA_ERR_BAD_ARG;
+    CUtensorMap m1, m2;
+    if (!tcg::make_x_map(&m1, xa, n, d_in) || !tcg::make_x_map(&m2, xb, n, d_in)) return NPLDA_ERR_NO_DEVICE;
+    tcg::Args a;
+    a.x1 = xa; a.x2 = xb; a.n = n;
+    a.nst1 = d_in / tcg::KST; a.ksteps2 = ksteps2;
+    a.w1img = w1img; a.w2img = w2img_any;
+    a.hdr = zeros; a.guard = nullptr;
+    a.b1 = zeros; a.b2 = zeros; a.p = zeros; a.q = zeros;
+    a.scores = nullptr; a.aout = aout; a.yout = nullptr; a.emit_cap = emit_cap;
     a.trace = nullptr; a.dbg = 0;
     const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
     return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);

@@ -959,3 +959,23 @@ def test_emitted_activations_vs_reference_autograd(ref_out, kaldi_params, cfg1, 
     monkeypatch.setenv("NPLDA_BWD_EMIT", "1")
     monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
     test_nplda_training_step_gradients(ref_out, kaldi_params, cfg1, lossname)
+
+
+@pytest.mark.parametrize("d_in", [32, 64, 192, 1024])
+def test_tc_kernel_other_input_widths(d_in):
+    """The tcgen05 kernel takes any input width that is a multiple of 32 (1 .. 32 layer-1 stages per tile; the backward
+    runs it with 192-wide rows for dL/du = dL/dy . W2): against the oracle on random parameters, ragged batch."""
+    class C(NC):
+        xvector_dim = d_in
+    torch.manual_seed(d_in)
+    m = npl.NeuralPlda(C).to(DEV)
+    m.impl = npl.IMPL_TC
+    g = torch.Generator().manual_seed(d_in + 1)
+    x1, x2 = torch.randn(3000 + 13, d_in, generator=g), torch.randn(3000 + 13, d_in, generator=g)
+    with torch.no_grad():
+        s = m(x1.to(DEV), x2.to(DEV))
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref = O.nplda_score(x1, x2, sd["centering_and_LDA.weight"], sd["centering_and_LDA.bias"],
+                        sd["centering_and_wccn_plda.weight"], sd["centering_and_wccn_plda.bias"], sd["P_sqrt"], sd["Q"])
+    ok, worst = parity_ok(s, ref, rel=1e-4)
+    assert ok, worst
