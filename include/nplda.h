@@ -233,6 +233,28 @@ int dplda_score_bwd(const float *x1, const float *x2, int64_t n, int d_in, int d
                     float *dW1, float *db1, float *dw_lr, float *dc_lr, float *dx1, float *dx2,
                     void *workspace, int64_t workspace_bytes, void *stream);
 
+/* Training with saved activations.  nplda_score_fwd_train / dplda_score_fwd_train compute the scores like
+ * nplda_score_fwd / dplda_score_fwd_ws and also leave, in the caller-owned buffer `act` of
+ * nplda_act_floats(n, is_dplda) floats, the rows the backward needs (NeuralPlda: a = W1 x + b1 and y;
+ * DPlda: a, (Ww + Ww^T) u and (Wb + Wb^T) u; each [2 n][192] fp32, side 1 of pair p n rows after side 0).
+ * Passing that buffer to nplda_score_bwd_act / dplda_score_bwd_act (otherwise identical to the functions above;
+ * act == NULL makes them the same) saves the backward its passes of the tensor-core forward kernel.  `act` is
+ * only read.  NPLDA_ERR_UNSUPPORTED_DIM for shapes the tcgen05 kernel does not take: use the plain entries. */
+int64_t nplda_act_floats(int64_t n, int is_dplda);
+int nplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2, const void *pack,
+                          float *scores, float *act, void *stream);
+int dplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
+                          float *scores, float *act, void *stream);
+int nplda_score_bwd_act(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2,
+                        const float *W1, const float *b1, const float *W2, const float *b2,
+                        const float *p_sqrt, const float *q, const float *dscores, float *dW1,
+                        float *db1, float *dW2, float *db2, float *dp_sqrt, float *dq, float *dx1,
+                        float *dx2, const float *act, void *workspace, int64_t workspace_bytes, void *stream);
+int dplda_score_bwd_act(const float *x1, const float *x2, int64_t n, int d_in, int d1,
+                        const float *W1, const float *b1, const float *w_lr, const float *dscores,
+                        float *dW1, float *db1, float *dw_lr, float *dc_lr, float *dx1, float *dx2,
+                        const float *act, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------
  * minC threshold sweep.  Replaces the O(N_t * N) Python loop of
  * NeuralPlda.minc (models.py:406-421) given the two score populations already

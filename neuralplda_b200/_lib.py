@@ -20,6 +20,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8 = 0, 1, 2, 3
 LOSS_SOFTCDET, LOSS_CROSSENTROPY = 0, 1
 PACK_MIXED, PACK_EPOCH_ODD, PREPARE_IF_CHANGED = 1, 2, 1
+ERR_UNSUPPORTED_DIM = -2
 MAX_BETAS = 8
 
 _lib = None
@@ -62,6 +63,13 @@ SIGNATURES = {
                         + [c_vp, c_i64, c_vp]),
     "dplda_score_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int] + [c_vp] * 3 + [c_vp] + [c_vp] * 6
                         + [c_vp, c_i64, c_vp]),
+    "nplda_score_bwd_act": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int] + [c_vp] * 6 + [c_vp] + [c_vp] * 8
+                            + [c_vp, c_vp, c_i64, c_vp]),
+    "dplda_score_bwd_act": (c_int, [c_vp, c_vp, c_i64, c_int, c_int] + [c_vp] * 3 + [c_vp] + [c_vp] * 6
+                            + [c_vp, c_vp, c_i64, c_vp]),
+    "nplda_act_floats": (c_i64, [c_i64, c_int]),
+    "nplda_score_fwd_train": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "dplda_score_fwd_train": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "nplda_minc_sweep": (c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
                                  ctypes.POINTER(ctypes.c_double), c_int, c_vp, c_vp, c_vp]),
     "nplda_score_grid": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),

@@ -35,6 +35,9 @@ bool tc_dplda_ok(const PackLayout &L);   // score_tc.cu
 int dplda_score_tc(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
                    void *workspace, int64_t workspace_bytes, cudaStream_t st);   // dplda_tc.cu
 
+int dplda_score_tc_train(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+                         float *act, cudaStream_t st);   // dplda_tc.cu
+
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
              float *out, int64_t ld_out, cudaStream_t st, const unsigned long long *fp_cur = nullptr,
              const unsigned long long *fp_built = nullptr);   // score_simt.cu
@@ -109,6 +112,31 @@ extern "C" int nplda_score_fwd(const float *x1, const float *x2, int64_t n, int 
 extern "C" int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,
                                const void *pack, float *scores, int impl, void *stream) {
     return score_dispatch(true, x1, x2, nullptr, nullptr, 0, nullptr, n, d_in, d1, d1, pack, scores, impl, stream);
+}
+
+// Training forwards: scores plus the activations the backward needs, kept by the caller (act), so that the backward
+// does not run the tensor-core kernel again.  NPLDA_ERR_UNSUPPORTED_DIM for shapes the tcgen05 kernel does not take.
+extern "C" int64_t nplda_act_floats(int64_t n, int is_dplda) { return n < 0 ? NPLDA_ERR_BAD_ARG : (is_dplda ? 6 : 4) * n * NP; }
+
+extern "C" int nplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2, const void *pack,
+                                     float *scores, float *act, void *stream) {
+    if (n < 0 || !pack || (n > 0 && (!x1 || !x2 || !scores || !act))) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n == 0) return NPLDA_OK;
+    const PackLayout L = make_pack_layout(d_in, d1, d2);
+    if (!tc_shape_ok(false, L, false) || (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)act) & 15) != 0) return NPLDA_ERR_UNSUPPORTED_DIM;
+    return score_tc(false, x1, x2, nullptr, nullptr, 0, nullptr, n, L, (const char *)pack, scores, 0, (cudaStream_t)stream,
+                    act, act + 2 * n * NP, n);
+}
+
+extern "C" int dplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
+                                     float *scores, float *act, void *stream) {
+    if (n < 0 || !pack || (n > 0 && (!x1 || !x2 || !scores || !act))) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n == 0) return NPLDA_OK;
+    const PackLayout L = make_pack_layout(d_in, d1, d1);
+    if (!tc_dplda_ok(L) || (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)act) & 15) != 0) return NPLDA_ERR_UNSUPPORTED_DIM;
+    return dplda_score_tc_train(x1, x2, n, L, (const char *)pack, scores, act, (cudaStream_t)stream);
 }
 
 extern "C" int dplda_score_fwd_ws(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,

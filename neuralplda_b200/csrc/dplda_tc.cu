@@ -24,7 +24,7 @@ constexpr int LD = NP;                   // 192 floats per emitted row, 176 of t
 __global__ void __launch_bounds__(256) dplda_finish_kernel(const float *__restrict__ A, const float *__restrict__ V,
                                                            const float *__restrict__ Z, int64_t cap, int64_t nc,
                                                            const float *__restrict__ ws, const float *__restrict__ c,
-                                                           float *__restrict__ scores) {
+                                                           float *__restrict__ scores, float vscale) {
     const int lane = threadIdx.x & 31;
     const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t p = w0; p < nc; p += nw) {
@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(256) dplda_finish_kernel(const float *__restri
             const float4 x1 = a1[k], x2 = a2[k], y1 = v1[k], y2 = v2[k], zz = z2[k], w = w4[k];
             n1 += x1.x * x1.x + x1.y * x1.y + x1.z * x1.z + x1.w * x1.w;
             n2 += x2.x * x2.x + x2.y * x2.y + x2.z * x2.z + x2.w * x2.w;
-            t1 += x1.x * (zz.x + y1.x + w.x) + x1.y * (zz.y + y1.y + w.y) + x1.z * (zz.z + y1.z + w.z) + x1.w * (zz.w + y1.w + w.w);
-            t2 += x2.x * (y2.x + w.x) + x2.y * (y2.y + w.y) + x2.z * (y2.z + w.z) + x2.w * (y2.w + w.w);
+            // vscale = 1 with V = Ww u;  1/2 with V = (Ww + Ww^T) u: a quadratic form only sees the symmetric part
+            t1 += x1.x * (zz.x + vscale * y1.x + w.x) + x1.y * (zz.y + vscale * y1.y + w.y) + x1.z * (zz.z + vscale * y1.z + w.z) +
+                  x1.w * (zz.w + vscale * y1.w + w.w);
+            t2 += x2.x * (vscale * y2.x + w.x) + x2.y * (vscale * y2.y + w.y) + x2.z * (vscale * y2.z + w.z) + x2.w * (vscale * y2.w + w.w);
         }
         n1 = warp_sum(n1); n2 = warp_sum(n2); t1 = warp_sum(t1); t2 = warp_sum(t2);
         if (lane == 0) scores[p] = t1 / fmaxf(sqrtf(n1), 1e-12f) + t2 / fmaxf(sqrtf(n2), 1e-12f) + c[0];
@@ -65,9 +67,26 @@ int dplda_score_tc(const float *x1, const float *x2, int64_t n, const PackLayout
         if (rc != NPLDA_OK) return rc;
         const int grid = (int)std::min<int64_t>((nc + 7) / 8, 16 * (int64_t)sm_count());
         dtc::dplda_finish_kernel<<<grid, 256, 0, st>>>(A, V, Z, cap, nc, (const float *)(pack + L.b2),
-                                                        (const float *)(pack + L.c), scores + c0);
+                                                        (const float *)(pack + L.c), scores + c0, 1.f);
         NPLDA_LAUNCH_CHECK();
     }
+    return NPLDA_OK;
+}
+
+// Training forward: the rows the backward needs -- a, R u (R = Ww + Ww^T) and Pm u, each [2 n][192], side 1 n rows
+// after side 0 -- are produced for the whole batch and kept by the caller; the score uses u^T Ww u = u^T R u / 2.
+int dplda_score_tc_train(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+                         float *act, cudaStream_t st) {
+    if (!tc_dplda_ok(L)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    float *A = act, *RU = act + 2 * n * dtc::LD, *Z = act + 4 * n * dtc::LD;
+    int rc = score_tc_dplda_emit(x1, x2, n, L, pack, 2, A, RU, n, st);
+    if (rc != NPLDA_OK) return rc;
+    rc = score_tc_dplda_emit(x1, x2, n, L, pack, 1, nullptr, Z, n, st);
+    if (rc != NPLDA_OK) return rc;
+    const int grid = (int)std::min<int64_t>((n + 7) / 8, 16 * (int64_t)sm_count());
+    dtc::dplda_finish_kernel<<<grid, 256, 0, st>>>(A, RU, Z, n, n, (const float *)(pack + L.b2), (const float *)(pack + L.c),
+                                                    scores, 0.5f);
+    NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }
 

@@ -125,7 +125,10 @@ struct Args {
     int d_in, d1, d2, k1p, k2p, k2q;
     const float *w1t, *b1, *w2t, *w2n, *b2, *p, *q, *psq2, *rp, *ws;
     float *U, *G, *DA;         // [2*cap][NP]; G = DY (NeuralPlda) or g*U (DPlda)
-    const float *PMU;          // DPlda PRE: Pm u rows emitted by the tensor-core kernel
+    float *PMU;                // workspace rows: dL/du from the tensor-core pass (NeuralPlda PHASE 2)
+    const float *Apre, *Ypre, *Zpre;   // PRE: rows of a, y (DPlda: R u) and (DPlda) Pm u -- areas DA / G / PMU of the
+    int64_t pre_cap;                   //      workspace (EMIT passes in the backward) or activations saved by a training
+                                       //      forward; side 1 of pair p sits pre_cap rows after side 0
     float *db1, *db2, *dq, *dpsqrt, *dws, *dc;   // may be null
 };
 
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
         if (PRE) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float *arow = g.DA + ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+                const float *arow = g.Apre + ((int64_t)(i & 1) * g.pre_cap + min(pair0 + ty + 16 * (i >> 1), g.nc - 1)) * NP + 4 * tx;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     float4 v = *reinterpret_cast<const float4 *>(arow + 64 * j);
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
             if (PRE) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float *yrow = g.G + ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+                    const float *yrow = g.Ypre + ((int64_t)(i & 1) * g.pre_cap + min(pair0 + ty + 16 * (i >> 1), g.nc - 1)) * NP + 4 * tx;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         float4 v = *reinterpret_cast<const float4 *>(yrow + 64 * j);
@@ -338,12 +341,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
             if (PRE) {                       // R u rows sit in the G area, Pm u rows in PMU (EMIT passes of score_tc.cu)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int64_t rself = ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
-                    const int64_t roth = ((int64_t)((i & 1) ^ 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+                    const int64_t prow = min(pair0 + ty + 16 * (i >> 1), g.nc - 1);
+                    const int64_t rself = ((int64_t)(i & 1) * g.pre_cap + prow) * NP + 4 * tx;
+                    const int64_t roth = ((int64_t)((i & 1) ^ 1) * g.pre_cap + prow) * NP + 4 * tx;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        float4 v = *reinterpret_cast<const float4 *>(g.G + rself + 64 * j);
-                        const float4 w = *reinterpret_cast<const float4 *>(g.PMU + roth + 64 * j);
+                        float4 v = *reinterpret_cast<const float4 *>(g.Ypre + rself + 64 * j);
+                        const float4 w = *reinterpret_cast<const float4 *>(g.Zpre + roth + 64 * j);
                         v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
                         if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);
                         acc[i][2 * j] = make_float2(v.x, v.y);
@@ -610,7 +614,7 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
                const float *b1, const float *W2, const float *b2, const float *ps, const float *q,
                const float *w_lr, const float *dscores, float *dW1, float *db1, float *dW2, float *db2,
                float *dps, float *dq, float *dw_lr, float *dc, float *dx1, float *dx2, void *workspace,
-               int64_t workspace_bytes_, cudaStream_t st) {
+               int64_t workspace_bytes_, cudaStream_t st, const float *act = nullptr) {
     if (n < 0 || !workspace) return NPLDA_ERR_BAD_ARG;
     if (n == 0) return NPLDA_OK;
     if (!x1 || !x2 || !W1 || !b1 || !dscores) return NPLDA_ERR_BAD_ARG;
@@ -637,10 +641,12 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
     if (vec && (DPLDA ? tc_dplda_ok(FL) : tc_shape_ok(false, FL, false)) && FL.total <= fwd_pack_room(d_in, d1, d2)) {
         const char *e = getenv("NPLDA_BWD_EMIT");
         pre = e ? e[0] == '1' : n >= 4096;
+        if (act) pre = true;               // activations saved by the training forward: nothing to emit here
     }
+    if (act && !pre) return NPLDA_ERR_UNSUPPORTED_DIM;
     float *PMU = DA + 2 * cap * NP;                        // DPlda EMIT only
     char *fpack = (char *)(PMU + 2 * cap * NP);
-    if (pre) {
+    if (pre && (!act || !DPLDA)) {         // (NeuralPlda keeps the W2 image for the dL/du pass)
         int rc = DPLDA ? dplda_pack_weights(W1, b1, w_lr, nullptr, d_in, d1, fpack, FL.total, 0, st)
                        : nplda_pack_weights(W1, b1, W2, b2, ps, q, d_in, d1, d2, fpack, FL.total, 0, st);
         if (rc != NPLDA_OK) return rc;
@@ -680,11 +686,16 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
         a.dws = dw_lr ? dw_lr + 2 * (int64_t)d1 * d1 : nullptr; a.dc = dc;
         const int64_t ntiles = (nc + TILE_PAIRS - 1) / TILE_PAIRS;
         a.PMU = PMU;
-        if (pre && !DPLDA) {
+        if (act) {      // [a | y or R u | Pm u], each [2 n][NP], side 1 n rows after side 0
+            a.Apre = act + c0 * NP; a.Ypre = act + (2 * n + c0) * NP; a.Zpre = act + (4 * n + c0) * NP; a.pre_cap = n;
+        } else {
+            a.Apre = DA; a.Ypre = G; a.Zpre = PMU; a.pre_cap = cap;
+        }
+        if (pre && !act && !DPLDA) {
             int rc = score_tc(false, a.x1, a.x2, nullptr, nullptr, 0, nullptr, nc, FL, fpack, nullptr, 0, st, DA, G, cap);
             if (rc != NPLDA_OK) return rc;
         }
-        if (pre && DPLDA) {                 // a and R u (image 2), then Pm u (image 1)
+        if (pre && !act && DPLDA) {         // a and R u (image 2), then Pm u (image 1)
             int rc = score_tc_dplda_emit(a.x1, a.x2, nc, FL, fpack, 2, DA, G, cap, st);
             if (rc != NPLDA_OK) return rc;
             rc = score_tc_dplda_emit(a.x1, a.x2, nc, FL, fpack, 1, nullptr, PMU, cap, st);
@@ -754,6 +765,27 @@ extern "C" int nplda_score_bwd(const float *x1, const float *x2, int64_t n, int 
     return bwd::run<false>(x1, x2, n, d_in, d1, d2, W1, b1, W2, b2, p_sqrt, q, nullptr, dscores, dW1, db1, dW2,
                            db2, dp_sqrt, dq, nullptr, nullptr, dx1, dx2, workspace, workspace_bytes,
                            (cudaStream_t)stream);
+}
+
+extern "C" int nplda_score_bwd_act(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2,
+                                   const float *W1, const float *b1, const float *W2, const float *b2,
+                                   const float *p_sqrt, const float *q, const float *dscores, float *dW1,
+                                   float *db1, float *dW2, float *db2, float *dp_sqrt, float *dq, float *dx1,
+                                   float *dx2, const float *act, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (n > 0 && (!W2 || !b2 || !p_sqrt || !q)) return NPLDA_ERR_BAD_ARG;
+    return bwd::run<false>(x1, x2, n, d_in, d1, d2, W1, b1, W2, b2, p_sqrt, q, nullptr, dscores, dW1, db1, dW2,
+                           db2, dp_sqrt, dq, nullptr, nullptr, dx1, dx2, workspace, workspace_bytes,
+                           (cudaStream_t)stream, act);
+}
+
+extern "C" int dplda_score_bwd_act(const float *x1, const float *x2, int64_t n, int d_in, int d1,
+                                   const float *W1, const float *b1, const float *w_lr, const float *dscores,
+                                   float *dW1, float *db1, float *dw_lr, float *dc_lr, float *dx1, float *dx2,
+                                   const float *act, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (n > 0 && !w_lr) return NPLDA_ERR_BAD_ARG;
+    return bwd::run<true>(x1, x2, n, d_in, d1, d1, W1, b1, nullptr, nullptr, nullptr, nullptr, w_lr, dscores,
+                          dW1, db1, nullptr, nullptr, nullptr, nullptr, dw_lr, dc_lr, dx1, dx2, workspace,
+                          workspace_bytes, (cudaStream_t)stream, act);
 }
 
 extern "C" int dplda_score_bwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,

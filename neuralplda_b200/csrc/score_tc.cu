@@ -87,8 +87,8 @@ struct Args {
                             //         guard != nullptr: run only if guard[0] is set (fallback pass), then clear it
 
     float *scores;
-    float *aout, *yout;     // EMIT (backward, score_bwd.cu): a = W1 x + b1 and y rows, [2 * emit_cap][EMIT_LD] fp32,
-    int64_t emit_cap;       //       side 0 of pair p in row p, side 1 in row emit_cap + p; no scores are written
+    float *aout, *yout;     // EMIT (training, score_bwd.cu): a = W1 x + b1 and y rows, [2 * emit_cap][EMIT_LD] fp32,
+    int64_t emit_cap;       //       side 0 of pair p in row p, side 1 in row emit_cap + p; scores only if non-null
     long long *trace;       // cycle-accounting buffer (env NPLDA_TC_PROF), CTA 0 only
     int dbg;                // bottleneck experiments (env NPLDA_TC_DEBUG): 1 no x loads, 2 no weight copies, 4 no MMAs
 };
@@ -237,7 +237,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             ss[0] = fmaf(a02, a02, ss[0]); ss[1] = fmaf(a03, a03, ss[1]);
             ss[2] = fmaf(a10, a10, ss[2]); ss[3] = fmaf(a11, a11, ss[3]);
             ss[2] = fmaf(a12, a12, ss[2]); ss[3] = fmaf(a13, a13, ss[3]);
-            if (EMIT && g.aout != nullptr) {
+            if (EMIT && ea0 != nullptr) {
                 *reinterpret_cast<float2 *>(ea0 + c0 + 2 * cq) = make_float2(a00, a01);
                 *reinterpret_cast<float2 *>(ea0 + c0 + 8 + 2 * cq) = make_float2(a02, a03);
                 *reinterpret_cast<float2 *>(ea1 + c0 + 2 * cq) = make_float2(a10, a11);
@@ -265,7 +265,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const float y10 = fmaf(__uint_as_float(v[2]), r1, ba.x), y11 = fmaf(__uint_as_float(v[3]), r1, ba.y);
             const float y02 = fmaf(__uint_as_float(v[4]), r0, bb.x), y03 = fmaf(__uint_as_float(v[5]), r0, bb.y);
             const float y12 = fmaf(__uint_as_float(v[6]), r1, bb.x), y13 = fmaf(__uint_as_float(v[7]), r1, bb.y);
-            if (EMIT && g.yout != nullptr) {
+            if (EMIT && ey0 != nullptr) {
                 *reinterpret_cast<float2 *>(ey0 + c0 + 2 * cq) = make_float2(y00, y01);
                 *reinterpret_cast<float2 *>(ey0 + c0 + 8 + 2 * cq) = make_float2(y02, y03);
                 *reinterpret_cast<float2 *>(ey1 + c0 + 2 * cq) = make_float2(y10, y11);
@@ -281,10 +281,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const int d = (int)(i & 1);
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
             const uint32_t taddr = tbase + d * NPAD;
-            if (EMIT) {
-                const int64_t pe = min((blockIdx.x + i * gridDim.x) * TP + pl, g.emit_cap - 1);
-                if (g.aout != nullptr) { ea0 = g.aout + pe * EMIT_LD; ea1 = g.aout + (g.emit_cap + pe) * EMIT_LD; }
-                if (g.yout != nullptr) { ey0 = g.yout + pe * EMIT_LD; ey1 = g.yout + (g.emit_cap + pe) * EMIT_LD; }
+            if (EMIT) {                                              // pairs past emit_cap (tile tail) are not stored
+                const int64_t pe = (blockIdx.x + i * gridDim.x) * TP + pl;
+                const bool ok = pe < g.emit_cap;
+                ea0 = (ok && g.aout != nullptr) ? g.aout + pe * EMIT_LD : nullptr;
+                ea1 = ea0 ? g.aout + (g.emit_cap + pe) * EMIT_LD : nullptr;
+                ey0 = (ok && g.yout != nullptr) ? g.yout + pe * EMIT_LD : nullptr;
+                ey1 = ey0 ? g.yout + (g.emit_cap + pe) * EMIT_LD : nullptr;
             }
             // ---- layer-1 accumulator: a = D + b1, |a|, bf16 hi/lo of a -> U (normalised after layer 2) ----
             PMARK(5);
@@ -346,7 +349,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + pl;
-            if (!EMIT && cq == 0 && pr < g.n) g.scores[pr] = s;
+            if ((!EMIT || g.scores != nullptr) && cq == 0 && pr < g.n) g.scores[pr] = s;
         }
         if (warp == 0 && lane == 0) PFLUSH(0);
     } else if (warp < WARP_MMA) {
@@ -917,7 +920,7 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
     a.scores = scores;
     a.aout = aout; a.yout = yout; a.emit_cap = emit_cap;
     if (aout != nullptr) {      // backward: a and y rows for the SIMT tile kernel, bf16x3 kernel, no scores
-        if (!yout || emit_cap < (n + tcg::TP - 1) / tcg::TP * tcg::TP) return NPLDA_ERR_BAD_ARG;
+        if (!yout || emit_cap < n) return NPLDA_ERR_BAD_ARG;
         a.guard = nullptr; a.dbg = 0; a.trace = nullptr;
         const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
         return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
@@ -984,7 +987,7 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
 int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, int which,
                         float *aout, float *yout, int64_t emit_cap, cudaStream_t st) {
     if (!tc_dplda_ok(L) || !yout || which < 0 || which > 2) return NPLDA_ERR_UNSUPPORTED_DIM;
-    if (n >= (int64_t)1 << 31 || emit_cap < (n + tcg::TP - 1) / tcg::TP * tcg::TP) return NPLDA_ERR_BAD_ARG;
+    if (n >= (int64_t)1 << 31 || emit_cap < n) return NPLDA_ERR_BAD_ARG;
     CUtensorMap m1, m2;
     if (!tcg::make_x_map(&m1, x1, n, L.d_in) || !tcg::make_x_map(&m2, x2, n, L.d_in)) return NPLDA_ERR_NO_DEVICE;
     tcg::Args a;
@@ -1019,7 +1022,7 @@ int tc_rows_image_pack(const float *Wkn, int64_t ldk, int N, int K, int d_in, ui
 int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int d_in, const uint8_t *w1img, const uint8_t *w2img_any,
                        int ksteps2, const float *zeros, float *aout, int64_t emit_cap, cudaStream_t st) {
     if (d_in % tcg::KST != 0 || d_in < tcg::KST || !aout) return NPLDA_ERR_UNSUPPORTED_DIM;
-    if (n >= (int64_t)1 << 31 || emit_cap < (n + tcg::TP - 1) / tcg::TP * tcg::TP) return NPLDA_ERR_BAD_ARG;
+    if (n >= (int64_t)1 << 31 || emit_cap < n) return NPLDA_ERR_BAD_ARG;
     CUtensorMap m1, m2;
     if (!tcg::make_x_map(&m1, xa, n, d_in) || !tcg::make_x_map(&m2, xb, n, d_in)) return NPLDA_ERR_NO_DEVICE;
     tcg::Args a;

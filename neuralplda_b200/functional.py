@@ -97,6 +97,17 @@ def _zero_grads(params, need):
     return out
 
 
+SAVE_ACTIVATIONS_MIN_PAIRS = 4096
+
+
+def _wants_activations(ctx, packed, impl, n):
+    """A forward whose backward will run keeps the activations the backward needs (3 KB per pair for NeuralPlda,
+    4.6 KB for DPlda -- about the size of the inputs; PyTorch's autograd in the reference keeps far more) instead of
+    recomputing them in the backward.  `module.packed.save_activations = False` restores recomputation."""
+    return (n >= SAVE_ACTIVATIONS_MIN_PAIRS and impl in (_lib.IMPL_AUTO, _lib.IMPL_TC) and any(ctx.needs_input_grad)
+            and getattr(packed, "save_activations", True))
+
+
 def _check_pair_inputs(x1, x2, d_in):
     require_cuda(x1, x2)
     if x1.dim() != 2 or x2.dim() != 2 or x1.shape != x2.shape:
@@ -119,9 +130,20 @@ class NpldaScoreFn(torch.autograd.Function):
         n = x1c.shape[0]
         pack = packed.get("nplda", (W1, b1, W2, b2, P_sqrt, Q), d_in, d1, d2, mixed=(impl == _lib.IMPL_TC_F8))
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
+        ctx.act = None
         with on_device(x1c.device):
-            check(lib().nplda_score_fwd(ptr(x1c), ptr(x2c), n, d_in, d1, d2, ptr(pack), ptr(scores), impl,
-                                        stream_ptr()), "nplda_score_fwd")
+            rc = _lib.ERR_UNSUPPORTED_DIM
+            if _wants_activations(ctx, packed, impl, n):
+                act = torch.empty(int(lib().nplda_act_floats(n, 0)), dtype=torch.float32, device=x1c.device)
+                rc = lib().nplda_score_fwd_train(ptr(x1c), ptr(x2c), n, d_in, d1, d2, ptr(pack), ptr(scores), ptr(act),
+                                                 stream_ptr())
+                if rc == 0:
+                    ctx.act = act
+                elif rc != _lib.ERR_UNSUPPORTED_DIM:
+                    check(rc, "nplda_score_fwd_train")
+            if rc != 0:
+                check(lib().nplda_score_fwd(ptr(x1c), ptr(x2c), n, d_in, d1, d2, ptr(pack), ptr(scores), impl,
+                                            stream_ptr()), "nplda_score_fwd")
         ctx.save_for_backward(x1c, x2c, W1, b1, W2, b2, P_sqrt, Q)
         return scores
 
@@ -144,9 +166,9 @@ class NpldaScoreFn(torch.autograd.Function):
                 if wsb < 0:
                     check(wsb, "nplda_bwd_workspace_bytes")
                 ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=dev)
-                check(lib().nplda_score_bwd(ptr(x1), ptr(x2), n, d_in, d1, d2, *[ptr(p) for p in params],
-                                            ptr(ds), *[ptr(g) for g in grads], ptr(dx1), ptr(dx2), ptr(ws),
-                                            ws.numel(), stream_ptr()), "nplda_score_bwd")
+                check(lib().nplda_score_bwd_act(ptr(x1), ptr(x2), n, d_in, d1, d2, *[ptr(p) for p in params],
+                                                ptr(ds), *[ptr(g) for g in grads], ptr(dx1), ptr(dx2), ptr(ctx.act),
+                                                ptr(ws), ws.numel(), stream_ptr()), "nplda_score_bwd")
         return (dx1, dx2, *grads, None, None)
 
 
@@ -163,6 +185,18 @@ class DpldaScoreFn(torch.autograd.Function):
         n = x1c.shape[0]
         pack = packed.get("dplda", (W1, b1, w_lr, c_lr), d_in, d1, d1)
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
+        ctx.act = None
+        if _wants_activations(ctx, packed, impl, n):
+            with on_device(x1c.device):
+                act = torch.empty(int(lib().nplda_act_floats(n, 1)), dtype=torch.float32, device=x1c.device)
+                rc = lib().dplda_score_fwd_train(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), ptr(act),
+                                                 stream_ptr())
+            if rc == 0:
+                ctx.act = act
+                ctx.save_for_backward(x1c, x2c, W1, b1, w_lr)
+                return scores
+            if rc != _lib.ERR_UNSUPPORTED_DIM:
+                check(rc, "dplda_score_fwd_train")
         with on_device(x1c.device):
             wsb = lib().dplda_fwd_workspace_bytes(n, d_in, d1) if impl in (_lib.IMPL_AUTO, _lib.IMPL_TC) else 0
             if wsb < 0:
@@ -191,9 +225,9 @@ class DpldaScoreFn(torch.autograd.Function):
                 if wsb < 0:
                     check(wsb, "nplda_bwd_workspace_bytes")
                 ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=dev)
-                check(lib().dplda_score_bwd(ptr(x1), ptr(x2), n, d_in, d1, ptr(W1c), ptr(b1c), ptr(wc), ptr(ds),
-                                            ptr(dW1), ptr(db1), ptr(dw), ptr(dc), ptr(dx1), ptr(dx2), ptr(ws),
-                                            ws.numel(), stream_ptr()), "dplda_score_bwd")
+                check(lib().dplda_score_bwd_act(ptr(x1), ptr(x2), n, d_in, d1, ptr(W1c), ptr(b1c), ptr(wc), ptr(ds),
+                                                ptr(dW1), ptr(db1), ptr(dw), ptr(dc), ptr(dx1), ptr(dx2), ptr(ctx.act),
+                                                ptr(ws), ws.numel(), stream_ptr()), "dplda_score_bwd")
         return (dx1, dx2, dW1, db1, dw, dc, None, None)
 
 

@@ -712,10 +712,12 @@ def test_config3_10m_grid_kernel(kaldi_params):
     np.testing.assert_allclose(st.t().cpu().numpy(), s.cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("batch", [512, 4608])
 @pytest.mark.parametrize("lossname", ["SoftCdet", "crossentropy"])
-def test_training_trajectory_matches_oracle(kaldi_params, lossname):
-    """The reference's training-loop body (xvector_NeuralPlda_pytorch.py:35-43) for 12 Adam steps on fresh
-    512-pair batches: forward -> loss -> backward -> optimizer.step through the drop-in module on the GPU vs
+def test_training_trajectory_matches_oracle(kaldi_params, lossname, batch):
+    """The reference's training-loop body (xvector_NeuralPlda_pytorch.py:35-43) for 12 Adam steps on fresh batches
+    (512 pairs: all-fp32 backward; 4608 pairs: activations saved by the tensor-core forward, tile phases around the
+    tensor-core dL/du pass): forward -> loss -> backward -> optimizer.step through the drop-in module on the GPU vs
     the oracle port under torch autograd on the CPU, same parameter order.  Loss values within 1e-4 relative at
     every step, parameters within 1e-4 of the update scale at the end."""
     kp = kaldi_params
@@ -726,7 +728,7 @@ def test_training_trajectory_matches_oracle(kaldi_params, lossname):
     thx = torch.nn.Parameter(torch.zeros(1))
     copt = torch.optim.Adam([W["P_sqrt"], W["Q"]] + th + [thx, W["W1"], W["b1"], W["W2"], W["b2"]], lr=1e-4)
     for step in range(12):
-        x1, x2, t = O.synth_pairs(512, 40, seed=300 + step, mean=kp["mean"])
+        x1, x2, t = O.synth_pairs(batch, 40, seed=300 + step, mean=kp["mean"])
         opt.zero_grad()
         loss = m.loss(m(x1.to(DEV), x2.to(DEV)), t.to(DEV))
         loss.backward()
@@ -928,29 +930,52 @@ def test_config5_dplda_training_step_shard(ref_out, kaldi_params):
 
 @pytest.mark.parametrize("kind", ["nplda", "dplda"])
 def test_backward_with_emitted_activations(ref_out, kaldi_params, cfg1, kind):
-    """Backward with a = W1 x + b1 and y (DPlda: R u and Pm u) emitted by the tcgen05 forward kernel (EMIT mode) instead
-    of being recomputed in fp32 by the tile kernel: all parameter gradients and the input gradients within 1e-4 of their
-    largest entry of the all-fp32 path, on a ragged batch spanning a partial tile."""
+    """Backward fed by the tensor cores -- a = W1 x + b1 and y (DPlda: R u and Pm u) either saved by the training
+    forward (default for batches >= 4096 pairs) or emitted again by the tcgen05 kernel inside the backward
+    (`packed.save_activations = False`) -- against the all-fp32 backward that recomputes them in the tile kernel:
+    all parameter gradients and the input gradients within 1e-4 of their largest entry, scores identical in kind,
+    on a ragged batch spanning a partial tile."""
     x1, x2, t = cfg1
     n = 9000 + 37
     y = t[:n].to(DEV)
     grads = {}
-    for emit in ("0", "1"):
-        os.environ["NPLDA_BWD_EMIT"] = emit
+    for variant, save, emit in (("fp32", False, "0"), ("emit_in_backward", False, "1"), ("saved_by_forward", True, None)):
+        if emit is not None:
+            os.environ["NPLDA_BWD_EMIT"] = emit
         os.environ["NPLDA_BWD_GEMM"] = "simt"
         try:
             m = make_nplda(kaldi_params, loss="SoftCdet") if kind == "nplda" else make_dplda(kaldi_params, ref_out)
+            m.packed.save_activations = save
             a, b = x1[:n].to(DEV).requires_grad_(True), x2[:n].to(DEV).requires_grad_(True)
-            m.loss(m(a, b), y).backward()
+            out = m(a, b)
+            m.loss(out, y).backward()
             torch.cuda.synchronize()
-            grads[emit] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
-            grads[emit]["x1"], grads[emit]["x2"] = a.grad.clone(), b.grad.clone()
+            grads[variant] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+            grads[variant]["x1"], grads[variant]["x2"], grads[variant]["scores"] = a.grad.clone(), b.grad.clone(), out.detach().clone()
         finally:
             os.environ.pop("NPLDA_BWD_EMIT", None)
             os.environ.pop("NPLDA_BWD_GEMM", None)
-    for k, g0 in grads["0"].items():
-        scale = float(g0.abs().max()) + 1e-30
-        assert float((grads["1"][k] - g0).abs().max()) <= 1e-4 * scale, k
+    for variant in ("emit_in_backward", "saved_by_forward"):
+        for k, g0 in grads["fp32"].items():
+            scale = float(g0.abs().max()) + 1e-30
+            assert float((grads[variant][k] - g0).abs().max()) <= 1e-4 * scale, (variant, k)
+
+
+def test_saved_activations_survive_retain_graph(kaldi_params, cfg1):
+    """The backward only READS the activations the training forward saved: a second backward through the same graph
+    (retain_graph=True) gives the same gradients."""
+    x1, x2, t = cfg1
+    n = 5000
+    m = make_nplda(kaldi_params, loss="crossentropy")
+    loss = m.loss(m(x1[:n].to(DEV), x2[:n].to(DEV)), t[:n].to(DEV))
+    loss.backward(retain_graph=True)
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    loss.backward()
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            scale = float(g1[k].abs().max()) + 1e-30
+            assert float((p.grad - g1[k]).abs().max()) <= 1e-6 * scale, k       # atomics reorder the fp32 sums
 
 
 @pytest.mark.parametrize("lossname", ["SoftCdet", "crossentropy"])
@@ -979,3 +1004,20 @@ def test_tc_kernel_other_input_widths(d_in):
                         sd["centering_and_wccn_plda.weight"], sd["centering_and_wccn_plda.bias"], sd["P_sqrt"], sd["Q"])
     ok, worst = parity_ok(s, ref, rel=1e-4)
     assert ok, worst
+
+
+@pytest.mark.parametrize("lossname", ["SoftCdet", "crossentropy"])
+def test_saved_activations_vs_reference_autograd(ref_out, kaldi_params, cfg1, lossname, monkeypatch):
+    """The golden .grad of the unmodified reference (2048 pairs) through the default large-batch training path:
+    activations saved by the tensor-core forward, tensor-core dL/du pass and weight gradients."""
+    monkeypatch.setattr(F_, "SAVE_ACTIVATIONS_MIN_PAIRS", 1)
+    monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
+    launches0 = _lib.launch_count()
+    test_nplda_training_step_gradients(ref_out, kaldi_params, cfg1, lossname)
+    assert _lib.launch_count() > launches0
+
+
+def test_dplda_saved_activations_vs_reference_autograd(ref_out, kaldi_params, cfg1, monkeypatch):
+    monkeypatch.setattr(F_, "SAVE_ACTIVATIONS_MIN_PAIRS", 1)
+    monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
+    test_dplda_training_step_gradients(ref_out, kaldi_params, cfg1)
