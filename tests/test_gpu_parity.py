@@ -1021,3 +1021,43 @@ def test_dplda_saved_activations_vs_reference_autograd(ref_out, kaldi_params, cf
     monkeypatch.setattr(F_, "SAVE_ACTIVATIONS_MIN_PAIRS", 1)
     monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
     test_dplda_training_step_gradients(ref_out, kaldi_params, cfg1)
+
+
+@pytest.mark.parametrize("lossname", ["crossentropy", "SoftCdet"])
+def test_graphed_train_step_matches_eager(kaldi_params, lossname):
+    """neuralplda_b200.graphs.GraphedTrainStep (gather + forward + loss + backward + Adam captured in one CUDA graph)
+    against the same loop run eagerly: same losses step by step, same parameters after 10 steps (fp32 atomics reorder
+    sums: 1e-5 of the update), including a short last batch that falls back to the eager body."""
+    from neuralplda_b200.graphs import GraphedTrainStep
+    from neuralplda_b200.sv_trials_loaders import load_xvec_trials_from_numbatch
+    kp = kaldi_params
+    table, i1, i2, lab = O.synth_grid(60, 90, 6, seed=21, mean=kp["mean"])
+    mega = {"u%04d" % k: table[k].numpy() for k in range(table.shape[0])}
+    n2i = dict(enumerate(mega))
+    B = 128
+    g = torch.Generator().manual_seed(3)
+    batches = [torch.randperm(i1.numel(), generator=g)[:B] for _ in range(10)] + [torch.randperm(i1.numel(), generator=g)[:50]]
+    dev = torch.device(DEV)
+
+    m_e = make_nplda(kp, loss=lossname)
+    opt_e = torch.optim.Adam(m_e.parameters(), lr=1e-3, capturable=True)
+    eager = []
+    for b in batches:
+        opt_e.zero_grad()
+        x1, x2 = load_xvec_trials_from_numbatch(mega, n2i, i1[b].to(dev), i2[b].to(dev), dev)
+        loss = m_e.loss(m_e(x1, x2), lab[b].to(dev))
+        loss.backward()
+        opt_e.step()
+        eager.append(loss.item())
+
+    m_g = make_nplda(kp, loss=lossname)
+    opt_g = torch.optim.Adam(m_g.parameters(), lr=1e-3, capturable=True)
+    step = GraphedTrainStep(m_g, opt_g, mega, n2i, batch_size=B)
+    graphed = [float(step(i1[b], i2[b], lab[b])) for b in batches]
+    assert step.graph is not None
+    np.testing.assert_allclose(graphed, eager, rtol=2e-4, atol=1e-6)
+    scale = len(batches) * 1e-3                                   # Adam moves an entry by ~lr per step
+    for (k, pe), (_, pg) in zip(m_e.named_parameters(), m_g.named_parameters()):
+        assert float((pe.detach() - pg.detach()).abs().max()) <= 2e-3 * scale, k
+    with pytest.raises(RuntimeError):
+        GraphedTrainStep(m_g, torch.optim.Adam(m_g.parameters(), lr=1e-3), mega, n2i, batch_size=B)
