@@ -640,7 +640,7 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
     bool pre = false;
     if (vec && (DPLDA ? tc_dplda_ok(FL) : tc_shape_ok(false, FL, false)) && FL.total <= fwd_pack_room(d_in, d1, d2)) {
         const char *e = getenv("NPLDA_BWD_EMIT");
-        pre = e ? e[0] == '1' : n >= 4096;
+        pre = e ? e[0] == '1' : n >= 64;
         if (act) pre = true;               // activations saved by the training forward: nothing to emit here
     }
     if (act && !pre) return NPLDA_ERR_UNSUPPORTED_DIM;

@@ -97,7 +97,7 @@ def _zero_grads(params, need):
     return out
 
 
-SAVE_ACTIVATIONS_MIN_PAIRS = 4096
+SAVE_ACTIVATIONS_MIN_PAIRS = 64       # one tile of the tensor-core kernel; below, the all-fp32 tile kernel does everything
 
 
 def _wants_activations(ctx, packed, impl, n):
