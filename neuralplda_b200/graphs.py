@@ -12,7 +12,7 @@ gather from the device-resident x-vector table, the module's forward, `model.los
 
 It is opt-in and changes nothing else: same kernels, same arithmetic, parameters and optimiser state are updated in
 place.  Requirements of CUDA-graph capture: a fixed batch size (a short last batch runs eagerly through the same
-code), an optimiser whose step is capturable (`torch.optim.Adam(..., capturable=True)` or `fused=True`), and no
+code), an optimiser whose step is capturable (`torch.optim.Adam(..., capturable=True)`, optionally `fused=True`), and no
 host reads inside the step (the loss comes back as a device tensor).
 """
 from __future__ import annotations
@@ -30,9 +30,9 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep needs the module on a CUDA device")
         self.device = dev
         d = optimizer.defaults
-        if not (d.get("capturable") or d.get("fused")):
+        if not d.get("capturable"):
             raise RuntimeError("GraphedTrainStep needs an optimiser whose step can be captured in a CUDA graph: "
-                               "torch.optim.Adam(..., capturable=True) or fused=True")
+                               "torch.optim.Adam(..., capturable=True), optionally with fused=True")
         self.mega_dict, self.num_to_id = mega_dict, num_to_id_dict
         self.tab = get_table(mega_dict, dev)
         self.batch_size = int(batch_size)

@@ -47,13 +47,13 @@ for lossname, fused in (("crossentropy", False), ("crossentropy", True), ("SoftC
 from neuralplda_b200.graphs import GraphedTrainStep
 class CX(bench.NC):
     loss = "crossentropy"
-for B in (128, 2048):
+for B, fused in ((128, False), (2048, False), (128, True), (2048, True)):
     m = npl.NeuralPlda(CX).to(dev)
     sd = m.state_dict()
     for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias", "b1"), ("centering_and_wccn_plda.weight", "W2"),
                       ("centering_and_wccn_plda.bias", "b2"), ("P_sqrt", "P_sqrt"), ("Q", "Q")):
         sd[name].copy_(kp[key])
-    opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True, fused=fused)
     gstep = GraphedTrainStep(m, opt, mega, num_to_id, batch_size=B)
     perm = torch.randperm(i1.numel())[:B]
     d1, d2, tg = i1[perm], i2[perm], lab[perm]
@@ -64,7 +64,7 @@ for B in (128, 2048):
     for _ in range(n): v = gstep(d1, d2, tg).item()              # .item() every step, like the reference's loop
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n
-    print(f"graphed step crossentropy B={B}: {dt * 1e3:.3f} ms/step ({B / dt / 1e3:.1f} k pairs/s), loss {v:.5f}")
+    print(f"graphed step crossentropy fused_adam={fused} B={B}: {dt * 1e3:.3f} ms/step ({B / dt / 1e3:.1f} k pairs/s), loss {v:.5f}")
 # the same loop on the CPU with the oracle port (reference arithmetic, torch autograd), B = 128
 W = {k: torch.nn.Parameter(kp[k].clone()) for k in ("W1", "b1", "W2", "b2", "P_sqrt", "Q")}
 thx = torch.nn.Parameter(torch.zeros(1))
