@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import torch
 
-from .sv_trials_loaders import _device_rows, _gather, get_table
+from .sv_trials_loaders import _device_rows, _gather, _rows_from_nums, get_table
 
 
 class GraphedTrainStep:
@@ -36,9 +36,14 @@ class GraphedTrainStep:
         self.mega_dict, self.num_to_id = mega_dict, num_to_id_dict
         self.tab = get_table(mega_dict, dev)
         self.batch_size = int(batch_size)
-        self.i1 = torch.zeros(self.batch_size, dtype=torch.int64, device=dev)
-        self.i2 = torch.zeros(self.batch_size, dtype=torch.int64, device=dev)
-        self.t = torch.zeros(self.batch_size, dtype=torch.float32, device=dev)
+        B = self.batch_size
+        self.i12 = torch.zeros(2 * B, dtype=torch.int64, device=dev)       # static inputs of the graph
+        self.i1, self.i2 = self.i12[:B], self.i12[B:]
+        self.t = torch.zeros(B, dtype=torch.float32, device=dev)
+        # batches that arrive on the host (DataLoader output) are staged in pinned memory: two asynchronous copies
+        self.h_i12 = torch.zeros(2 * B, dtype=torch.int64).pin_memory()
+        self.h_t = torch.zeros(B, dtype=torch.float32).pin_memory()
+        self._staged = torch.cuda.Event()
         self.loss = None
         self.graph = None
         self._warmup = int(warmup)
@@ -60,12 +65,22 @@ class GraphedTrainStep:
 
     def __call__(self, data1, data2, target):
         dev = self.device
-        r1 = _device_rows(self.tab, self.num_to_id, data1.to(dev) if not data1.is_cuda else data1, dev)
-        r2 = _device_rows(self.tab, self.num_to_id, data2.to(dev) if not data2.is_cuda else data2, dev)
-        target = target.to(dev, torch.float32)
-        if r1.numel() != self.batch_size:                           # short last batch: same code, eagerly
-            return self._body(r1, r2, target)
-        self.i1.copy_(r1); self.i2.copy_(r2); self.t.copy_(target)
+        B = self.batch_size
+        if not (data1.is_cuda or data2.is_cuda or target.is_cuda) and data1.numel() == B:
+            r1 = _rows_from_nums(self.tab, self.num_to_id, data1)   # host int64 rows, range-checked (KeyError)
+            r2 = _rows_from_nums(self.tab, self.num_to_id, data2)
+            self._staged.synchronize()                              # the previous batch has left the staging buffers
+            self.h_i12[:B].copy_(r1); self.h_i12[B:].copy_(r2); self.h_t.copy_(target)
+            self.i12.copy_(self.h_i12, non_blocking=True)
+            self.t.copy_(self.h_t, non_blocking=True)
+            self._staged.record(torch.cuda.current_stream(dev))
+        else:
+            r1 = _device_rows(self.tab, self.num_to_id, data1.to(dev) if not data1.is_cuda else data1, dev)
+            r2 = _device_rows(self.tab, self.num_to_id, data2.to(dev) if not data2.is_cuda else data2, dev)
+            target = target.to(dev, torch.float32)
+            if r1.numel() != B:                                     # short last batch: same code, eagerly
+                return self._body(r1, r2, target)
+            self.i1.copy_(r1); self.i2.copy_(r2); self.t.copy_(target)
         if self.graph is None:
             if self._seen < self._warmup:                           # eager warm-up steps (real training steps) on a side stream
                 self._seen += 1

@@ -53,7 +53,7 @@ for B, fused in ((128, False), (2048, False), (128, True), (2048, True)):
     for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias", "b1"), ("centering_and_wccn_plda.weight", "W2"),
                       ("centering_and_wccn_plda.bias", "b2"), ("P_sqrt", "P_sqrt"), ("Q", "Q")):
         sd[name].copy_(kp[key])
-    opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True, fused=fused)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True, fused=True if fused else None)
     gstep = GraphedTrainStep(m, opt, mega, num_to_id, batch_size=B)
     perm = torch.randperm(i1.numel())[:B]
     d1, d2, tg = i1[perm], i2[perm], lab[perm]
