@@ -236,7 +236,7 @@ int dplda_score_bwd(const float *x1, const float *x2, int64_t n, int d_in, int d
 /* Training with saved activations.  nplda_score_fwd_train / dplda_score_fwd_train compute the scores like
  * nplda_score_fwd / dplda_score_fwd_ws and also leave, in the caller-owned buffer `act` of
  * nplda_act_floats(n, is_dplda) floats, the rows the backward needs (NeuralPlda: a = W1 x + b1 and y;
- * DPlda: a, (Ww + Ww^T) u and (Wb + Wb^T) u; each [2 n][192] fp32, side 1 of pair p n rows after side 0).
+ * DPlda: a, (Ww + Ww^T) u and (Wb + Wb^T) u; each [2 n][176] fp32, side 1 of pair p n rows after side 0).
  * Passing that buffer to nplda_score_bwd_act / dplda_score_bwd_act (otherwise identical to the functions above;
  * act == NULL makes them the same) saves the backward its passes of the tensor-core forward kernel.  `act` is
  * only read.  NPLDA_ERR_UNSUPPORTED_DIM for shapes the tcgen05 kernel does not take: use the plain entries. */

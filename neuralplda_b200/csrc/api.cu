@@ -116,7 +116,8 @@ extern "C" int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int 
 
 // Training forwards: scores plus the activations the backward needs, kept by the caller (act), so that the backward
 // does not run the tensor-core kernel again.  NPLDA_ERR_UNSUPPORTED_DIM for shapes the tcgen05 kernel does not take.
-extern "C" int64_t nplda_act_floats(int64_t n, int is_dplda) { return n < 0 ? NPLDA_ERR_BAD_ARG : (is_dplda ? 6 : 4) * n * NP; }
+constexpr int ACT_LD = 176;   // floats per saved activation row (EMIT_LD of score_tc.cu, the backward's row pitch)
+extern "C" int64_t nplda_act_floats(int64_t n, int is_dplda) { return n < 0 ? NPLDA_ERR_BAD_ARG : (is_dplda ? 6 : 4) * n * ACT_LD; }
 
 extern "C" int nplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2, const void *pack,
                                      float *scores, float *act, void *stream) {
@@ -126,7 +127,7 @@ extern "C" int nplda_score_fwd_train(const float *x1, const float *x2, int64_t n
     const PackLayout L = make_pack_layout(d_in, d1, d2);
     if (!tc_shape_ok(false, L, false) || (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)act) & 15) != 0) return NPLDA_ERR_UNSUPPORTED_DIM;
     return score_tc(false, x1, x2, nullptr, nullptr, 0, nullptr, n, L, (const char *)pack, scores, 0, (cudaStream_t)stream,
-                    act, act + 2 * n * NP, n);
+                    act, act + 2 * n * ACT_LD, n);
 }
 
 extern "C" int dplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,

@@ -5,7 +5,7 @@
 // tcgen05 score kernel in EMIT mode (score_tc.cu) leave, per row, a = W1 x + b1, V = Ww u and Z = Pm u in a
 // workspace (layer 1 is evaluated in both passes: the kernel is bound by its x stream either way), and one
 // warp per pair finishes  S = (a1.Z2 + a1.V1 + ws.a1) / |a1| + (a2.V2 + ws.a2) / |a2| + c.
-// Pairs are processed in chunks so that the workspace stays at 3 x [2 * chunk][192] fp32.
+// Pairs are processed in chunks so that the workspace stays at 3 x [2 * chunk][176] fp32.
 #include <algorithm>
 
 #include "common.cuh"
@@ -19,7 +19,7 @@ int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackL
 namespace dtc {
 
 constexpr int64_t CHUNK_PAIRS = 131072;
-constexpr int LD = NP;                   // 192 floats per emitted row, 176 of them written
+constexpr int LD = 176;                  // floats per emitted row (EMIT_LD of score_tc.cu)
 
 __global__ void __launch_bounds__(256) dplda_finish_kernel(const float *__restrict__ A, const float *__restrict__ V,
                                                            const float *__restrict__ Z, int64_t cap, int64_t nc,
@@ -73,8 +73,8 @@ int dplda_score_tc(const float *x1, const float *x2, int64_t n, const PackLayout
     return NPLDA_OK;
 }
 
-// Training forward: the rows the backward needs -- a, R u (R = Ww + Ww^T) and Pm u, each [2 n][192], side 1 n rows
-// after side 0 -- are produced for the whole batch and kept by the caller; the score uses u^T Ww u = u^T R u / 2.
+// Training forward: the rows the backward needs -- a, R u (R = Ww + Ww^T) and Pm u, each [2 n][176], side 1 n rows
+// after side 0 (176 floats per row) -- are produced for the whole batch and kept by the caller; the score uses u^T Ww u = u^T R u / 2.
 int dplda_score_tc_train(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
                          float *act, cudaStream_t st) {
     if (!tc_dplda_ok(L)) return NPLDA_ERR_UNSUPPORTED_DIM;

@@ -32,8 +32,8 @@ int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackL
 
 int64_t tc_rows_image_bytes(int d_in);   // score_tc.cu
 int tc_rows_image_pack(const float *Wkn, int64_t ldk, int N, int K, int d_in, uint8_t *img, cudaStream_t st);
-int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int d_in, const uint8_t *w1img, const uint8_t *w2img_any,
-                       int ksteps2, const float *zeros, float *aout, int64_t emit_cap, cudaStream_t st);
+int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int row_width, int d_in, const uint8_t *w1img,
+                       const uint8_t *w2img_any, int ksteps2, const float *zeros, float *aout, int64_t emit_cap, cudaStream_t st);
 
 namespace bwd {
 
@@ -122,6 +122,8 @@ struct Args {
     const float *ds;           // chunk base
     int64_t nc;                // pairs in this chunk
     int64_t cap;               // workspace rows per side
+    int rw;                    // floats per workspace / activation row: 176 (what the tensor-core kernels emit) when the
+                               // layer widths fit, else NP; rows stay 16-byte aligned, columns >= rw are never touched
     int d_in, d1, d2, k1p, k2p, k2q;
     const float *w1t, *b1, *w2t, *w2n, *b2, *p, *q, *psq2, *rp, *ws;
     float *U, *G, *DA;         // [2*cap][NP]; G = DY (NeuralPlda) or g*U (DPlda)
@@ -182,11 +184,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
         if (PRE) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float *arow = g.Apre + ((int64_t)(i & 1) * g.pre_cap + min(pair0 + ty + 16 * (i >> 1), g.nc - 1)) * NP + 4 * tx;
+                const float *arow = g.Apre + ((int64_t)(i & 1) * g.pre_cap + min(pair0 + ty + 16 * (i >> 1), g.nc - 1)) * g.rw + 4 * tx;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    float4 v = *reinterpret_cast<const float4 *>(arow + 64 * j);
-                    if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);   // the emitted rows are 176 wide
+                    const float4 v = 4 * tx + 64 * j < g.rw ? *reinterpret_cast<const float4 *>(arow + 64 * j)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                     acc[i][2 * j] = make_float2(v.x, v.y);
                     acc[i][2 * j + 1] = make_float2(v.z, v.w);
                 }
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
                 rden[i] = nrm > 1e-12f ? 1.f / den : -1e12f;   // sign flags the clamped branch
                 const int jp = i >> 1, side = i & 1;
                 float *urow = Us + (ty + 16 * i) * LDU + 4 * tx;
-                float *grow = g.U + ((int64_t)side * g.cap + pair0 + ty + 16 * jp) * NP + 4 * tx;
+                float *grow = g.U + ((int64_t)side * g.cap + pair0 + ty + 16 * jp) * g.rw + 4 * tx;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     float4 u;
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
                     u.w = acc[i][2 * j + 1].y / den;
                     if (PHASE != 2) {
                         *reinterpret_cast<float4 *>(urow + 64 * j) = u;
-                        if (live[jp]) *reinterpret_cast<float4 *>(grow + 64 * j) = u;
+                        if (live[jp] && 4 * tx + 64 * j < g.rw) *reinterpret_cast<float4 *>(grow + 64 * j) = u;
                     }
                 }
             }
@@ -262,11 +264,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
             // dL/du rows from the tensor-core pass
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float *drow = g.PMU + ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * NP + 4 * tx;
+                const float *drow = g.PMU + ((int64_t)(i & 1) * g.cap + pair0 + ty + 16 * (i >> 1)) * g.rw + 4 * tx;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    float4 v = *reinterpret_cast<const float4 *>(drow + 64 * j);
-                    if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v = 4 * tx + 64 * j < g.rw ? *reinterpret_cast<const float4 *>(drow + 64 * j)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                     acc[i][2 * j] = make_float2(v.x, v.y);
                     acc[i][2 * j + 1] = make_float2(v.z, v.w);
                 }
@@ -276,11 +278,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
             if (PRE) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float *yrow = g.Ypre + ((int64_t)(i & 1) * g.pre_cap + min(pair0 + ty + 16 * (i >> 1), g.nc - 1)) * NP + 4 * tx;
+                    const float *yrow = g.Ypre + ((int64_t)(i & 1) * g.pre_cap + min(pair0 + ty + 16 * (i >> 1), g.nc - 1)) * g.rw + 4 * tx;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        float4 v = *reinterpret_cast<const float4 *>(yrow + 64 * j);
-                        if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 v = 4 * tx + 64 * j < g.rw ? *reinterpret_cast<const float4 *>(yrow + 64 * j)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                         acc[i][2 * j] = make_float2(v.x, v.y);
                         acc[i][2 * j + 1] = make_float2(v.z, v.w);
                     }
@@ -325,12 +327,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
             for (int i = 0; i < 8; ++i) {
                 const int jp = i >> 1, side = i & 1;
                 float *urow = Us + (ty + 16 * i) * LDU + 4 * tx;
-                float *grow = g.G + ((int64_t)side * g.cap + pair0 + ty + 16 * jp) * NP + 4 * tx;
+                float *grow = g.G + ((int64_t)side * g.cap + pair0 + ty + 16 * jp) * g.rw + 4 * tx;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     float4 v = make_float4(acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y);
                     *reinterpret_cast<float4 *>(urow + 64 * j) = v;
-                    if (live[jp]) *reinterpret_cast<float4 *>(grow + 64 * j) = v;
+                    if (live[jp] && 4 * tx + 64 * j < g.rw) *reinterpret_cast<float4 *>(grow + 64 * j) = v;
                 }
             }
             if (PHASE == 1) continue;                                 // du = dy W2 runs on the tensor cores
@@ -342,14 +344,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int64_t prow = min(pair0 + ty + 16 * (i >> 1), g.nc - 1);
-                    const int64_t rself = ((int64_t)(i & 1) * g.pre_cap + prow) * NP + 4 * tx;
-                    const int64_t roth = ((int64_t)((i & 1) ^ 1) * g.pre_cap + prow) * NP + 4 * tx;
+                    const int64_t rself = ((int64_t)(i & 1) * g.pre_cap + prow) * g.rw + 4 * tx;
+                    const int64_t roth = ((int64_t)((i & 1) ^ 1) * g.pre_cap + prow) * g.rw + 4 * tx;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        float4 v = *reinterpret_cast<const float4 *>(g.Ypre + rself + 64 * j);
-                        const float4 w = *reinterpret_cast<const float4 *>(g.Zpre + roth + 64 * j);
-                        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-                        if (4 * tx + 64 * j >= 176) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (4 * tx + 64 * j < g.rw) {
+                            v = *reinterpret_cast<const float4 *>(g.Ypre + rself + 64 * j);
+                            const float4 w = *reinterpret_cast<const float4 *>(g.Zpre + roth + 64 * j);
+                            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                        }
                         acc[i][2 * j] = make_float2(v.x, v.y);
                         acc[i][2 * j + 1] = make_float2(v.z, v.w);
                     }
@@ -372,8 +376,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
                     const float gg = gs[jp];
                     float4 u = *reinterpret_cast<const float4 *>(Us + (ty + 16 * i) * LDU + 4 * tx + 64 * j);
                     float4 gu = make_float4(gg * u.x, gg * u.y, gg * u.z, gg * u.w);
-                    if (live[jp])
-                        *reinterpret_cast<float4 *>(g.G + ((int64_t)side * g.cap + pair0 + ty + 16 * jp) * NP +
+                    if (live[jp] && 4 * tx + 64 * j < g.rw)
+                        *reinterpret_cast<float4 *>(g.G + ((int64_t)side * g.cap + pair0 + ty + 16 * jp) * g.rw +
                                                     4 * tx + 64 * j) = gu;
                     sw[0] += gu.x; sw[1] += gu.y; sw[2] += gu.z; sw[3] += gu.w;
                     acc[i][2 * j].x = gg * (acc[i][2 * j].x + wv[0]);
@@ -393,13 +397,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int jp = i >> 1, side = i & 1;
-            const int64_t grow = ((int64_t)side * g.cap + pair0 + ty + 16 * jp) * NP + 4 * tx;
+            const int64_t grow = ((int64_t)side * g.cap + pair0 + ty + 16 * jp) * g.rw + 4 * tx;
             float4 u[3];
             float dot = 0.f;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 if (DPLDA) u[j] = *reinterpret_cast<const float4 *>(Us + (ty + 16 * i) * LDU + 4 * tx + 64 * j);
-                else u[j] = live[jp] ? *reinterpret_cast<const float4 *>(g.U + grow + 64 * j) : make_float4(0, 0, 0, 0);
+                else u[j] = (live[jp] && 4 * tx + 64 * j < g.rw) ? *reinterpret_cast<const float4 *>(g.U + grow + 64 * j)
+                                                                 : make_float4(0, 0, 0, 0);
                 dot += u[j].x * acc[i][2 * j].x + u[j].y * acc[i][2 * j].y + u[j].z * acc[i][2 * j + 1].x +
                        u[j].w * acc[i][2 * j + 1].y;
             }
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_tile_kernel(Args g) {
                 d.y = (acc[i][2 * j].y - u[j].y * dot) * r;
                 d.z = (acc[i][2 * j + 1].x - u[j].z * dot) * r;
                 d.w = (acc[i][2 * j + 1].y - u[j].w * dot) * r;
-                if (live[jp]) {
+                if (live[jp] && 4 * tx + 64 * j < g.rw) {
                     *reinterpret_cast<float4 *>(g.DA + grow + 64 * j) = d;
                     sb1[4 * j + 0] += d.x; sb1[4 * j + 1] += d.y; sb1[4 * j + 2] += d.z; sb1[4 * j + 3] += d.w;
                 }
@@ -574,11 +579,11 @@ static int gemm_tn(const float *A, int lda, int M, const float *B, int ldb, int 
 }
 
 // dx[r, :] = DA[r, :d1] . W1   (rows x d_in); only when the inputs require grad (rare)
-__global__ void dx_kernel(const float *__restrict__ DA, const float *__restrict__ W1, int d1, int d_in,
+__global__ void dx_kernel(const float *__restrict__ DA, int ldda, const float *__restrict__ W1, int d1, int d_in,
                           int64_t R, float *__restrict__ dx) {
     extern __shared__ float da[];
     for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
-        for (int a = threadIdx.x; a < d1; a += blockDim.x) da[a] = DA[r * NP + a];
+        for (int a = threadIdx.x; a < d1; a += blockDim.x) da[a] = DA[r * ldda + a];
         __syncthreads();
         for (int k = threadIdx.x; k < d_in; k += blockDim.x) {
             float s = 0.f;
@@ -626,6 +631,7 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
     float *pk = (float *)workspace;
     const int64_t cap = (std::min(n, CHUNK_PAIRS) + TILE_PAIRS - 1) / TILE_PAIRS * TILE_PAIRS;
     float *U = pk + (P.total + 63) / 64 * 64;
+    const int rw = std::max(d1, d2) <= 176 ? 176 : NP;      // row pitch of U / G / DA / PMU and of saved activations
     float *G = U + 2 * cap * NP;
     float *DA = G + 2 * cap * NP;
 
@@ -678,7 +684,7 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
         const int64_t nc = std::min(CHUNK_PAIRS, n - c0);
         Args a;
         a.x1 = x1 + c0 * d_in; a.x2 = x2 + c0 * d_in; a.ds = dscores + c0; a.nc = nc; a.cap = cap;
-        a.d_in = d_in; a.d1 = d1; a.d2 = d2; a.k1p = P.k1p; a.k2p = P.k2p; a.k2q = P.k2q;
+        a.rw = rw; a.d_in = d_in; a.d1 = d1; a.d2 = d2; a.k1p = P.k1p; a.k2p = P.k2p; a.k2q = P.k2q;
         a.w1t = pk + P.w1t; a.b1 = pk + P.b1; a.w2t = pk + P.w2t; a.w2n = pk + P.w2n; a.b2 = pk + P.b2;
         a.p = pk + P.p; a.q = pk + P.q; a.psq2 = pk + P.psq2; a.rp = pk + P.rp; a.ws = pk + P.ws;
         a.U = U; a.G = G; a.DA = DA;
@@ -687,7 +693,7 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
         const int64_t ntiles = (nc + TILE_PAIRS - 1) / TILE_PAIRS;
         a.PMU = PMU;
         if (act) {      // [a | y or R u | Pm u], each [2 n][NP], side 1 n rows after side 0
-            a.Apre = act + c0 * NP; a.Ypre = act + (2 * n + c0) * NP; a.Zpre = act + (4 * n + c0) * NP; a.pre_cap = n;
+            a.Apre = act + c0 * rw; a.Ypre = act + (2 * n + c0) * rw; a.Zpre = act + (4 * n + c0) * rw; a.pre_cap = n;
         } else {
             a.Apre = DA; a.Ypre = G; a.Zpre = PMU; a.pre_cap = cap;
         }
@@ -706,7 +712,7 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
             kern1<<<grid, NTHREADS, BWD_SMEM_BYTES, st>>>(a);
             NPLDA_LAUNCH_CHECK();
             const uint8_t *img2 = (const uint8_t *)fpack + FL.tc + (tc_rows_image_bytes(d_in) + 255) / 256 * 256;   // W2 image of the forward pack
-            int rc = score_tc_rows_emit(G, G + cap * NP, nc, NP, duimg, img2, round_up(d1, 16) / 16, zeros, PMU, cap, st);
+            int rc = score_tc_rows_emit(G, G + cap * rw, nc, rw, NP, duimg, img2, round_up(d1, 16) / 16, zeros, PMU, cap, st);
             if (rc != NPLDA_OK) return rc;
             kern2<<<grid, NTHREADS, BWD_SMEM_BYTES, st>>>(a);
             NPLDA_LAUNCH_CHECK();
@@ -717,28 +723,28 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
 
         // Row ranges in the workspace: side 0 rows [0, nc), side 1 rows [cap, cap + nc).
         int rc = NPLDA_OK;
-        const float *U0 = U, *U1 = U + cap * NP, *G0 = G, *G1 = G + cap * NP, *DA0 = DA, *DA1 = DA + cap * NP;
+        const float *U0 = U, *U1 = U + cap * rw, *G0 = G, *G1 = G + cap * rw, *DA0 = DA, *DA1 = DA + cap * rw;
         if (dW1) {
-            if ((rc = gemm_tn_auto(DA0, NP, d1, a.x1, d_in, d_in, nc, dW1, d_in, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn_auto(DA1, NP, d1, a.x2, d_in, d_in, nc, dW1, d_in, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(DA0, rw, d1, a.x1, d_in, d_in, nc, dW1, d_in, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(DA1, rw, d1, a.x2, d_in, d_in, nc, dW1, d_in, st)) != NPLDA_OK) return rc;
         }
         if (!DPLDA && dW2) {
-            if ((rc = gemm_tn_auto(G0, NP, d2, U0, NP, d1, nc, dW2, d1, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn_auto(G1, NP, d2, U1, NP, d1, nc, dW2, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G0, rw, d2, U0, rw, d1, nc, dW2, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G1, rw, d2, U1, rw, d1, nc, dW2, d1, st)) != NPLDA_OK) return rc;
         }
         if (DPLDA && dw_lr) {
             float *dWb = dw_lr, *dWw = dw_lr + (int64_t)d1 * d1;
-            if ((rc = gemm_tn_auto(G0, NP, d1, U0, NP, d1, nc, dWw, d1, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn_auto(G1, NP, d1, U1, NP, d1, nc, dWw, d1, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn_auto(G0, NP, d1, U1, NP, d1, nc, dWb, d1, st)) != NPLDA_OK) return rc;
-            if ((rc = gemm_tn_auto(G1, NP, d1, U0, NP, d1, nc, dWb, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G0, rw, d1, U0, rw, d1, nc, dWw, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G1, rw, d1, U1, rw, d1, nc, dWw, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G0, rw, d1, U1, rw, d1, nc, dWb, d1, st)) != NPLDA_OK) return rc;
+            if ((rc = gemm_tn_auto(G1, rw, d1, U0, rw, d1, nc, dWb, d1, st)) != NPLDA_OK) return rc;
         }
         if (dx1) {
-            dx_kernel<<<(int)std::min<int64_t>(nc, 8 * sm_count()), 256, d1 * 4, st>>>(DA0, W1, d1, d_in, nc, dx1 + c0 * d_in);
+            dx_kernel<<<(int)std::min<int64_t>(nc, 8 * sm_count()), 256, d1 * 4, st>>>(DA0, rw, W1, d1, d_in, nc, dx1 + c0 * d_in);
             NPLDA_LAUNCH_CHECK();
         }
         if (dx2) {
-            dx_kernel<<<(int)std::min<int64_t>(nc, 8 * sm_count()), 256, d1 * 4, st>>>(DA1, W1, d1, d_in, nc, dx2 + c0 * d_in);
+            dx_kernel<<<(int)std::min<int64_t>(nc, 8 * sm_count()), 256, d1 * 4, st>>>(DA1, rw, W1, d1, d_in, nc, dx2 + c0 * d_in);
             NPLDA_LAUNCH_CHECK();
         }
     }

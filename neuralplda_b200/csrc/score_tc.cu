@@ -165,7 +165,7 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
 // fails already parks the warp for ~60 cycles), so these are plain polling waits.
 #define WAIT_OFFPATH(bar, par) mbar_wait(bar, par)
 
-constexpr int EMIT_LD = 192;   // row stride of the emitted a / y rows = NP of the SIMT backward workspace
+constexpr int EMIT_LD = NPAD;  // 176: row stride of the emitted a / y rows (= the backward's row pitch for these shapes)
 
 template <bool PROF, int MODE, bool EMIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -783,11 +783,12 @@ static EncodeTiledFn encode_fn() {
     }
     return fn;
 }
-static bool make_x_map(CUtensorMap *m, const float *x, int64_t n, int d_in) {
+// rows of `d_in` floats, `pitch` floats apart (columns of a box past d_in are zero-filled by the TMA unit)
+static bool make_x_map(CUtensorMap *m, const float *x, int64_t n, int d_in, int pitch = 0) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)d_in, (cuuint64_t)n};
-    cuuint64_t strides[1] = {(cuuint64_t)d_in * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)(pitch ? pitch : d_in) * 4};
     cuuint32_t box[2] = {KST, TP}, es[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1019,12 +1020,13 @@ int tc_rows_image_pack(const float *Wkn, int64_t ldk, int N, int K, int d_in, ui
     return NPLDA_OK;
 }
 
-int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int d_in, const uint8_t *w1img, const uint8_t *w2img_any,
-                       int ksteps2, const float *zeros, float *aout, int64_t emit_cap, cudaStream_t st) {
-    if (d_in % tcg::KST != 0 || d_in < tcg::KST || !aout) return NPLDA_ERR_UNSUPPORTED_DIM;
+int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int row_width, int d_in, const uint8_t *w1img,
+                       const uint8_t *w2img_any, int ksteps2, const float *zeros, float *aout, int64_t emit_cap, cudaStream_t st) {
+    // the rows hold row_width floats (their pitch); the image covers K = d_in >= row_width, the excess reads as zeros
+    if (d_in % tcg::KST != 0 || d_in < tcg::KST || row_width > d_in || row_width % 4 != 0 || !aout) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n >= (int64_t)1 << 31 || emit_cap < n) return NPLDA_ERR_BAD_ARG;
     CUtensorMap m1, m2;
-    if (!tcg::make_x_map(&m1, xa, n, d_in) || !tcg::make_x_map(&m2, xb, n, d_in)) return NPLDA_ERR_NO_DEVICE;
+    if (!tcg::make_x_map(&m1, xa, n, row_width, row_width) || !tcg::make_x_map(&m2, xb, n, row_width, row_width)) return NPLDA_ERR_NO_DEVICE;
     tcg::Args a;
     a.x1 = xa; a.x2 = xb; a.n = n;
     a.nst1 = d_in / tcg::KST; a.ksteps2 = ksteps2;
