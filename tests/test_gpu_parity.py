@@ -1061,3 +1061,31 @@ def test_graphed_train_step_matches_eager(kaldi_params, lossname):
         assert float((pe.detach() - pg.detach()).abs().max()) <= 2e-3 * scale, k
     with pytest.raises(RuntimeError):
         GraphedTrainStep(m_g, torch.optim.Adam(m_g.parameters(), lr=1e-3), mega, n2i, batch_size=B)
+
+
+@pytest.mark.parametrize("kind", ["nplda", "dplda"])
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 130, 1000])
+def test_backward_ragged_small_batches(ref_out, kaldi_params, cfg1, kind, n):
+    """The default training path at the reference's batch sizes and around the 64-pair tile boundary (below it the
+    all-fp32 tile kernel does everything; from it on the tensor-core forward saves the activations) against the forced
+    all-fp32 path: gradients within 1e-4 of their largest entry, loss within 1e-5."""
+    x1, x2, t = cfg1
+    a, b, y = x1[:n].to(DEV), x2[:n].to(DEV), t[:n].clone().to(DEV)
+    y[0] = 1.0                                                    # at least one target, or softCdet is 0/0 as in the reference
+    res = {}
+    for variant in ("default", "fp32"):
+        if variant == "fp32":
+            os.environ["NPLDA_BWD_EMIT"] = "0"; os.environ["NPLDA_BWD_GEMM"] = "simt"
+        try:
+            m = make_nplda(kaldi_params, loss="crossentropy") if kind == "nplda" else make_dplda(kaldi_params, ref_out)
+            m.packed.save_activations = variant == "default"
+            loss = m.loss(m(a, b), y)
+            loss.backward()
+            torch.cuda.synchronize()
+            res[variant] = (loss.item(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+        finally:
+            os.environ.pop("NPLDA_BWD_EMIT", None); os.environ.pop("NPLDA_BWD_GEMM", None)
+    assert res["default"][0] == pytest.approx(res["fp32"][0], rel=1e-5, abs=1e-7)
+    for k, g0 in res["fp32"][1].items():
+        scale = float(g0.abs().max()) + 1e-30
+        assert float((res["default"][1][k] - g0).abs().max()) <= 1e-4 * scale, (k, n)
