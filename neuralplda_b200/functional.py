@@ -104,8 +104,16 @@ def _wants_activations(ctx, packed, impl, n):
     """A forward whose backward will run keeps the activations the backward needs (3 KB per pair for NeuralPlda,
     4.6 KB for DPlda -- about the size of the inputs; PyTorch's autograd in the reference keeps far more) instead of
     recomputing them in the backward.  `module.packed.save_activations = False` restores recomputation."""
-    return (n >= SAVE_ACTIVATIONS_MIN_PAIRS and impl in (_lib.IMPL_AUTO, _lib.IMPL_TC) and any(ctx.needs_input_grad)
-            and getattr(packed, "save_activations", True))
+    if not (n >= SAVE_ACTIVATIONS_MIN_PAIRS and impl in (_lib.IMPL_AUTO, _lib.IMPL_TC) and any(ctx.needs_input_grad)
+            and getattr(packed, "save_activations", True)):
+        return False
+    nbytes = 6 * n * 176 * 4                          # upper bound (DPlda); only worth a driver query when it is large
+    if nbytes > (1 << 30):
+        free, _ = torch.cuda.mem_get_info()
+        cached = torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+        if nbytes > (free + cached) // 2:             # huge batch: recompute in the backward rather than risk OOM
+            return False
+    return True
 
 
 def _check_pair_inputs(x1, x2, d_in):
