@@ -100,7 +100,7 @@ def _zero_grads(params, need):
 SAVE_ACTIVATIONS_MIN_PAIRS = 64       # one tile of the tensor-core kernel; below, the all-fp32 tile kernel does everything
 
 
-def _wants_activations(ctx, packed, impl, n):
+def _wants_activations(ctx, packed, impl, n, dev):
     """A forward whose backward will run keeps the activations the backward needs (3 KB per pair for NeuralPlda,
     4.6 KB for DPlda -- about the size of the inputs; PyTorch's autograd in the reference keeps far more) instead of
     recomputing them in the backward.  `module.packed.save_activations = False` restores recomputation."""
@@ -109,8 +109,8 @@ def _wants_activations(ctx, packed, impl, n):
         return False
     nbytes = 6 * n * 176 * 4                          # upper bound (DPlda); only worth a driver query when it is large
     if nbytes > (1 << 30):
-        free, _ = torch.cuda.mem_get_info()
-        cached = torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+        free, _ = torch.cuda.mem_get_info(dev)
+        cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
         if nbytes > (free + cached) // 2:             # huge batch: recompute in the backward rather than risk OOM
             return False
     return True
@@ -141,7 +141,7 @@ class NpldaScoreFn(torch.autograd.Function):
         ctx.act = None
         with on_device(x1c.device):
             rc = _lib.ERR_UNSUPPORTED_DIM
-            if _wants_activations(ctx, packed, impl, n):
+            if _wants_activations(ctx, packed, impl, n, x1c.device):
                 act = torch.empty(int(lib().nplda_act_floats(n, 0)), dtype=torch.float32, device=x1c.device)
                 rc = lib().nplda_score_fwd_train(ptr(x1c), ptr(x2c), n, d_in, d1, d2, ptr(pack), ptr(scores), ptr(act),
                                                  stream_ptr())
@@ -194,7 +194,7 @@ class DpldaScoreFn(torch.autograd.Function):
         pack = packed.get("dplda", (W1, b1, w_lr, c_lr), d_in, d1, d1)
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
         ctx.act = None
-        if _wants_activations(ctx, packed, impl, n):
+        if _wants_activations(ctx, packed, impl, n, x1c.device):
             with on_device(x1c.device):
                 act = torch.empty(int(lib().nplda_act_floats(n, 1)), dtype=torch.float32, device=x1c.device)
                 rc = lib().dplda_score_fwd_train(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), ptr(act),
