@@ -153,3 +153,38 @@ def test_sharded_accumulators_reduce_to_the_global_loss_gloo():
         assert bce == pytest.approx(float(O.crossentropy(s, t, 0.0)), rel=1e-6)
         assert hard == pytest.approx(float(O.cdet(s, t, [0.1, -0.2], [99.0, 199.0])), rel=1e-6)
     assert abs(np.mean([r[4] for r in res]) - full) > 1e-4 * full      # the naive mean of rank losses differs
+
+
+def _gloo_grad_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = npl.NeuralPlda(NC)                                   # parameters only: no kernel runs on the CPU
+    m.Th99.requires_grad_(False)                             # a parameter without a gradient must be skipped
+    params = [p for p in m.parameters() if p.requires_grad]
+    # gradients as the backward returns them: views of ONE flat buffer (functional._zero_grads)
+    flat = torch.arange(sum(p.numel() for p in params), dtype=torch.float32) * (rank + 1)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    D.allreduce_gradients(m)
+    want = torch.arange(off, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    got = torch.cat([p.grad.reshape(-1) for p in params])
+    q.put((rank, bool(torch.equal(got, want)), m.Th99.grad is None))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo():
+    """Training on trial-list shards: parameter gradients are summed across ranks, DDP-style; gradients
+    that are views of one flat buffer and parameters without gradient are handled."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(60) for p in procs]
+    assert res == [(0, True, True), (1, True, True)]
