@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_kernel(
         wn[k] = k < K ? (float)((double)alpha * betas.v[k] / (K * nn)) : 0.f;
     }
     const float thx = th_xent ? th_xent[0] : 0.f;
-    const float inv_n = (float)(1.0 / (double)n);
+    // mean over ALL trials of the loss: acc[4K+3] is the trial count the accumulators were built from -- the global one
+    // after the all-reduce when the trial list is sharded across ranks (n is only this rank's share)
+    const double n_all = acc[4 * K + 3];
+    const float inv_n = (float)(1.0 / (n_all > 0.0 ? n_all : (double)n));
     double dk[MAXK], dx = 0.0;
 #pragma unroll
     for (int k = 0; k < MAXK; ++k) dk[k] = 0.0;

@@ -1089,3 +1089,22 @@ def test_backward_ragged_small_batches(ref_out, kaldi_params, cfg1, kind, n):
     for k, g0 in res["fp32"][1].items():
         scale = float(g0.abs().max()) + 1e-30
         assert float((res["default"][1][k] - g0).abs().max()) <= 1e-4 * scale, (k, n)
+
+
+def test_sharded_training_two_ranks(tmp_path):
+    """BASELINE.json configs[4] in miniature (tools/dist_train_check.py): two ranks, each forward + BCE + backward on its
+    contiguous trial range with the raw loss accumulators all-reduced (model.process_group) and the parameter gradients
+    summed (dist.allreduce_gradients), against the whole batch in one process: same loss, gradients within 1e-4 -- for
+    NeuralPlda and DPlda.  (The BCE backward once divided by the rank's trial count instead of the global one.)
+    Runs under torchrun with the gloo backend so that both ranks can share this box's GPU."""
+    import socket, subprocess, sys
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DIST_BACKEND="gloo")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "tools", "dist_train_check.py")],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=420)
+    lines = [l for l in r.stdout.splitlines() if l.startswith(("nplda:", "dplda:"))]
+    assert r.returncode == 0 and len(lines) == 2 and all(l.endswith("OK") for l in lines), (r.stdout[-2000:], r.stderr[-2000:])
