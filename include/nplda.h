@@ -77,6 +77,7 @@ int64_t nplda_launch_count(void);
  * ------------------------------------------------------------------------- */
 #define NPLDA_PACK_MIXED 1
 #define NPLDA_PACK_EPOCH_ODD 2
+#define NPLDA_PACK_PAIR 4      /* also build the CTA-pair weight images nplda_score_fwd_split reads (two more kernels) */
 int64_t nplda_pack_bytes(int d_in, int d1, int d2);
 
 /* NeuralPlda parameters (models.py:349-363): W1 [d1,d_in], b1 [d1], W2 [d2,d1],
@@ -138,6 +139,25 @@ int nplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *i
 int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *idx1,
                             const int64_t *idx2, int64_t n, int d_in, int d1, const void *pack,
                             float *scores, int32_t *bad_index_flag, int impl, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * K1x: the same scores from a PRE-SPLIT table, on the tensor cores (csrc/score_tcx.cu).
+ * The reference's callers hold a static x-vector table (the pickled dict,
+ * xvector_NeuralPlda_pytorch.py:117) and index batches (sv_trials_loaders.py:418-426).
+ * nplda_table_split converts the fp32 table ONCE into the tensor cores' operand format
+ * (bf16 hi/lo, x = hi + lo + O(2^-17 |x|); nplda_split_bytes(n_rows, d_in) = n_rows * d_in * 4 bytes, 128-byte
+ * aligned); nplda_score_fwd_split then scores trials (table[idx1[k]], table[idx2[k]]): TMA row gather
+ * (tile::gather4) straight into the shared-memory A operand, tcgen05.mma.cta_group::2 over CTA pairs, no
+ * conversion work per call.  Replaces load_xvec_trials_from_numbatch (sv_trials_loaders.py:418-426) +
+ * NeuralPlda.forward (models.py:378-382) for index batches.  Needs a pack built with NPLDA_PACK_PAIR and
+ * d_in % 32 == 0, d_in >= 64, d1, d2 <= 176 (NPLDA_ERR_UNSUPPORTED_DIM otherwise: use nplda_score_fwd_indexed).
+ * Out-of-range indices set *bad_index_flag (device int32) and never fault.
+ * ------------------------------------------------------------------------- */
+int64_t nplda_split_bytes(int64_t n_rows, int d_in);
+int nplda_table_split(const float *table, int64_t n_rows, int d_in, void *split, void *stream);
+int nplda_score_fwd_split(const void *split, int64_t n_rows, const int64_t *idx1, const int64_t *idx2, int64_t n,
+                          int d_in, int d1, int d2, const void *pack, float *scores, int32_t *bad_index_flag,
+                          void *stream);
 
 /* Batch gather alone (the device half of load_xvec_trials_from_numbatch / _from_idbatch,
  * sv_trials_loaders.py:418-437, for callers that want the materialised [n, d] pair the

@@ -19,7 +19,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8 = 0, 1, 2, 3
 LOSS_SOFTCDET, LOSS_CROSSENTROPY = 0, 1
-PACK_MIXED, PACK_EPOCH_ODD, PREPARE_IF_CHANGED = 1, 2, 1
+PACK_MIXED, PACK_EPOCH_ODD, PACK_PAIR, PREPARE_IF_CHANGED = 1, 2, 4, 1
 ERR_UNSUPPORTED_DIM = -2
 MAX_BETAS = 8
 
@@ -45,6 +45,9 @@ SIGNATURES = {
                                         c_vp, c_int, c_vp]),
     "dplda_score_fwd_indexed": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
                                         c_int, c_vp]),
+    "nplda_split_bytes": (c_i64, [c_i64, c_int]),
+    "nplda_table_split": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    "nplda_score_fwd_split": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "dplda_fwd_workspace_bytes": (c_i64, [c_i64, c_int, c_int]),
     "dplda_score_fwd_ws": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
     "nplda_gather_pairs": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),

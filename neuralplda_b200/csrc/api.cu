@@ -31,6 +31,10 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
              float *scores, int mode, cudaStream_t st, float *aout = nullptr, float *yout = nullptr,
              int64_t emit_cap = 0);   // score_tc.cu
 
+int table_split(const float *table, int64_t n_rows, int d_in, void *split, cudaStream_t st);   // score_tcx.cu
+int score_tcx(const void *split, int64_t n_rows, const int64_t *i1, const int64_t *i2, int64_t n, const PackLayout &L,
+              const char *pack, float *scores, int32_t *bad_flag, cudaStream_t st);   // score_tcx.cu
+
 bool tc_dplda_ok(const PackLayout &L);   // score_tc.cu
 int dplda_score_tc(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
                    void *workspace, int64_t workspace_bytes, cudaStream_t st);   // dplda_tc.cu
@@ -169,6 +173,30 @@ extern "C" int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const
                                        int impl, void *stream) {
     if (!idx1 || !idx2) return n == 0 ? NPLDA_OK : NPLDA_ERR_BAD_ARG;
     return score_dispatch(true, table, table, idx1, idx2, n_rows, bad_index_flag, n, d_in, d1, d1, pack, scores, impl, stream);
+}
+
+extern "C" int64_t nplda_split_bytes(int64_t n_rows, int d_in) {
+    if (n_rows < 0 || d_in <= 0) return NPLDA_ERR_BAD_ARG;
+    if (d_in % 32 != 0) return NPLDA_ERR_UNSUPPORTED_DIM;
+    return n_rows * (int64_t)d_in * 4;
+}
+
+extern "C" int nplda_table_split(const float *table, int64_t n_rows, int d_in, void *split, void *stream) {
+    if (n_rows < 0 || (n_rows > 0 && (!table || !split))) return NPLDA_ERR_BAD_ARG;
+    if ((((uintptr_t)table) & 15) != 0 || (((uintptr_t)split) & 127) != 0) return NPLDA_ERR_BAD_ARG;
+    if (n_rows == 0) return NPLDA_OK;
+    return table_split(table, n_rows, d_in, split, (cudaStream_t)stream);
+}
+
+extern "C" int nplda_score_fwd_split(const void *split, int64_t n_rows, const int64_t *idx1, const int64_t *idx2, int64_t n,
+                                     int d_in, int d1, int d2, const void *pack, float *scores, int32_t *bad_index_flag,
+                                     void *stream) {
+    if (n < 0 || !pack || (n > 0 && (!split || !idx1 || !idx2 || !scores || !bad_index_flag || n_rows <= 0))) return NPLDA_ERR_BAD_ARG;
+    if ((((uintptr_t)split) & 127) != 0) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n == 0) return NPLDA_OK;
+    const PackLayout L = make_pack_layout(d_in, d1, d2);
+    return score_tcx(split, n_rows, idx1, idx2, n, L, (const char *)pack, scores, bad_index_flag, (cudaStream_t)stream);
 }
 
 extern "C" int nplda_embed_fwd(const float *x, int64_t n, int d_in, int d1, int d2, const void *pack,

@@ -28,10 +28,13 @@ struct PackLayout {
     int64_t fp;    // 2 x u64         content fingerprint of the packed parameters, slot = pack epoch parity (pack.cu)
     int64_t tc;    // tensor-core images (bf16 hi/lo, tcgen05 smem layout), see score_tc.cu
     int64_t tc_bytes;
+    int64_t tcx;   // CTA-pair weight images of the pre-split-table kernel, see score_tcx.cu (built with NPLDA_PACK_PAIR)
+    int64_t tcx_bytes;
     int64_t total;
 };
 
 int64_t tc_image_bytes(int d_in, int d1, int d2);   // score_tc.cu
+int64_t tcx_image_bytes(int d_in, int d1, int d2);  // score_tcx.cu
 
 inline PackLayout make_pack_layout(int d_in, int d1, int d2) {
     PackLayout L;
@@ -51,6 +54,8 @@ inline PackLayout make_pack_layout(int d_in, int d1, int d2) {
     L.fp = take(16);
     L.tc_bytes = tc_image_bytes(d_in, d1, d2);
     L.tc = take(L.tc_bytes);
+    L.tcx_bytes = tcx_image_bytes(d_in, d1, d2);
+    L.tcx = take(L.tcx_bytes);
     L.total = o;
     return L;
 }

@@ -3,7 +3,8 @@
 // Python loop over dict lookups + np.asarray + a host->device copy of 4 KB per trial every batch.
 // One warp per output row, 16-byte loads/stores; both sides of the batch in one launch.  Rows outside the table
 // are reported through *bad_index_flag (which may live in pinned host memory, so that the host can look at it
-// without a synchronising copy) and come back zero-filled -- never a fault.
+// without a synchronising copy) and come back filled with NaN -- never a fault, and never a silently wrong score:
+// whatever is computed from such a row (scores, losses, gradients) is NaN until the host has seen the flag.
 #include <algorithm>
 
 #include "common.cuh"
@@ -27,11 +28,12 @@ __global__ void __launch_bounds__(256) gather_pairs_kernel(const float *__restri
         const float *src = table + (bad ? 0 : row) * (int64_t)d;
         if (VEC) {
             for (int k = lane; k < d / 4; k += 32) {
-                const float4 v = bad ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4 *>(src)[k];
+                const float qn = __int_as_float(0x7fc00000);
+                const float4 v = bad ? make_float4(qn, qn, qn, qn) : reinterpret_cast<const float4 *>(src)[k];
                 reinterpret_cast<float4 *>(dst)[k] = v;
             }
         } else {
-            for (int k = lane; k < d; k += 32) dst[k] = bad ? 0.f : src[k];
+            for (int k = lane; k < d; k += 32) dst[k] = bad ? __int_as_float(0x7fc00000) : src[k];
         }
     }
 }

@@ -71,5 +71,32 @@ __device__ __forceinline__ void mma2_commit_mc(uint64_t *bar, uint16_t cta_mask)
                  : "memory");
 }
 
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 bytes, 8-row atoms of 1024 bytes (sbo),
+// 16-byte chunk c of row r stored at chunk c ^ (r & 7) -- what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B when the
+// tile base is 1024-byte aligned.  A K step of 16 bf16 (32 bytes) inside the row is taken by adding 2 to the
+// descriptor (start address is in 16-byte units): the hardware applies the XOR to the absolute address bits.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                  // lbo: unused for swizzled K-major operands
+    d |= (uint64_t)(1024 >> 4) << 32;        // sbo: 8 rows x 128 bytes
+    d |= (uint64_t)1 << 46;                  // descriptor version 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                  // layout type 2 = SWIZZLE_128B
+    return d;
+}
+
+// TMA row gather (tile::gather4): four rows r0..r3 of a 2-D tensor, `box` columns starting at column c0, land as four
+// consecutive rows at dst (measured on B200, tools/gather4_probe.cu: the tensor map's box must be {cols, 1}; the
+// swizzle follows the destination address).  .cta_group::2: the bytes are posted on the LEADER CTA's mbarrier
+// (tools/gather4_pair_probe.cu).
+__device__ __forceinline__ void tma_gather4_pair(void *dst, const CUtensorMap *map, int c0, int r0, int r1, int r2, int r3,
+                                                 uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_addr(dst)),
+        "l"(map), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_addr(bar) & 0xFEFFFFFFu)
+        : "memory");
+}
+
 }  // namespace tc
 }  // namespace nplda

@@ -27,18 +27,31 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
                  : "memory");
 }
+// Bounded wait: a protocol bug traps (the launch fails with an error) after ~10 s of wall clock instead of hanging the
+// device.  The timer is only read every 256 failed polls (a failing try_wait already parks the warp for a while).
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_addr(bar);
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((++spins & 255u) == 0) {
+            const uint64_t t = global_timer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 10000000000ull) __trap();
+        }
+    }
 }
 
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05.mma operand reads)

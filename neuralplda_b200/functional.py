@@ -6,6 +6,7 @@ every arithmetic step of the hot path runs in libnplda.so.
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import torch
 
@@ -33,7 +34,7 @@ class PackedWeights:
         self.buf = None
         self.epoch = 0
 
-    def get(self, kind, params, d_in, d1, d2, mixed=False):
+    def get(self, kind, params, d_in, d1, d2, mixed=False, pair=False):
         dev = params[0].device
         nbytes = lib().nplda_pack_bytes(d_in, d1, d2)
         if nbytes < 0:
@@ -42,7 +43,8 @@ class PackedWeights:
             self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
             self.rowtab_key = None
         self.epoch ^= 1
-        flags = (_lib.PACK_MIXED if mixed else 0) | (_lib.PACK_EPOCH_ODD if self.epoch else 0)
+        flags = ((_lib.PACK_MIXED if mixed else 0) | (_lib.PACK_EPOCH_ODD if self.epoch else 0)
+                 | (_lib.PACK_PAIR if pair else 0))
         ps = [_f32c(p.detach()) for p in params]
         with on_device(dev):
             if kind == "nplda":
@@ -56,14 +58,19 @@ class PackedWeights:
 
     rowtab = None
     rowtab_key = None
+    rowtab_table = None       # strong reference to the table the cached rows were built from
 
     @staticmethod
     def _table_key(kind, table, d_in, d1, d2):
-        return (kind, d_in, d1, d2, table.data_ptr(), table._version, tuple(table.shape), table.device)
+        """Identity of a caller-owned table: the tensor OBJECT (held strongly in `rowtab_table` while its rows are
+        cached, so neither its id nor its storage address can be recycled by another table), its version counter and
+        shape.  Writes that bypass the version counter (`table.data.copy_()`) need `invalidate_table_caches()`."""
+        return (kind, d_in, d1, d2, id(table), table._version, tuple(table.shape), table.device)
 
     def rowtab_valid(self, kind, table, d_in, d1, d2):
         """Rows of THIS table are in the cache (whether they match the current parameters is checked on the device)."""
-        return self.rowtab_key == self._table_key(kind, table, d_in, d1, d2)
+        return (self.rowtab_table is table and self.rowtab_key is not None
+                and self.rowtab_key == self._table_key(kind, table, d_in, d1, d2))
 
     def get_rowtab(self, kind, table, params, d_in, d1, d2):
         """Per-utterance score operands of `table` (nplda_table_prepare).  The table is identified on the host
@@ -71,18 +78,85 @@ class PackedWeights:
         the parameters by the fingerprint of the fresh pack, on the device: the prepare call is a few empty
         launches when nothing changed."""
         pack = self.get(kind, params, d_in, d1, d2)
-        key = self._table_key(kind, table, d_in, d1, d2)
+        src = table
+        table = _f32c(table)
+        # a converted / compacted copy is a temporary: its rows are never cached (the next temporary may reuse its address)
+        key = self._table_key(kind, src, d_in, d1, d2) if table is src else None
         n_rows = table.shape[0]
         nbytes = lib().nplda_rowtab_bytes(n_rows)
         if self.rowtab is None or self.rowtab.numel() * 4 < nbytes or self.rowtab.device != table.device:
             self.rowtab = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=table.device)
             self.rowtab_key = None
-        flags = (_lib.PREPARE_IF_CHANGED if key == self.rowtab_key else 0) | (_lib.PACK_EPOCH_ODD if self.epoch else 0)
+        same = key is not None and self.rowtab_table is src and key == self.rowtab_key
+        flags = (_lib.PREPARE_IF_CHANGED if same else 0) | (_lib.PACK_EPOCH_ODD if self.epoch else 0)
         with on_device(table.device):
             check(lib().nplda_table_prepare(ptr(table), n_rows, d_in, d1, d2, ptr(pack), 0 if kind == "nplda" else 1,
                                             ptr(self.rowtab), flags, stream_ptr()), "nplda_table_prepare")
         self.rowtab_key = key
+        self.rowtab_table = src if key is not None else None
         return self.rowtab
+
+
+# ---- pre-split tables (csrc/score_tcx.cu) ----------------------------------------------------------------------
+# The split image of a table depends on the table only, not on any module's parameters: one cache for the process,
+# keyed by the table tensor OBJECT.  Entries die with their table (weakref finaliser), so a recycled id never finds a
+# stale entry; the version counter covers in-place updates through tensor ops.
+_split_cache = {}
+
+
+def _drop_split(key):
+    _split_cache.pop(key, None)
+
+
+def invalidate_table_caches(packed=None):
+    """Forget every cached per-table product (split images; the row table of `packed` if given).  Needed only after
+    writing into a table behind autograd's back (`table.data.copy_()` does not bump the version counter)."""
+    _split_cache.clear()
+    if packed is not None:
+        packed.rowtab_key = None
+        packed.rowtab_table = None
+
+
+def split_table(table):
+    """bf16 hi/lo operand image of a [rows, d_in] fp32 CUDA table (nplda_table_split), cached per table object."""
+    require_cuda(table)
+    src = table
+    table = _f32c(table)
+    cacheable = table is src
+    ent = _split_cache.get(id(src)) if cacheable else None
+    if ent is not None and ent[0]() is src and ent[1] == src._version and ent[2].device == src.device:
+        return ent[2]
+    n_rows, d_in = table.shape
+    nbytes = lib().nplda_split_bytes(n_rows, d_in)
+    if nbytes < 0:
+        check(int(nbytes), "nplda_split_bytes")
+    split = torch.empty(max(int(nbytes), 128), dtype=torch.uint8, device=table.device)
+    with on_device(table.device):
+        check(lib().nplda_table_split(ptr(table), n_rows, d_in, ptr(split), stream_ptr()), "nplda_table_split")
+    if cacheable:
+        key = id(src)
+        _split_cache[key] = (weakref.ref(src), src._version, split)
+        weakref.finalize(src, _drop_split, key)
+    return split
+
+
+def split_supported(kind, d_in, d1, d2):
+    return kind == "nplda" and d_in % 32 == 0 and d_in >= 64 and max(d1, d2) <= 176
+
+
+def score_split(table, split, i1, i2, params, dims, packed):
+    """NeuralPlda scores of trials (table[i1[k]], table[i2[k]]) from the pre-split image of the table
+    (nplda_score_fwd_split: TMA row gather + tcgen05 CTA-pair MMAs)."""
+    d_in, d1, d2 = dims
+    n = i1.numel()
+    dev = split.device
+    scores = torch.empty(n, dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    pack = packed.get("nplda", params, d_in, d1, d2, pair=True)
+    with on_device(dev):
+        check(lib().nplda_score_fwd_split(ptr(split), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1, d2, ptr(pack),
+                                          ptr(scores), ptr(flag), stream_ptr()), "nplda_score_fwd_split")
+    return scores, flag
 
 
 def _zero_grads(params, need):
@@ -283,34 +357,53 @@ def score_from_embeddings(kind, e1, e2, params, dims, packed):
     return scores
 
 
-def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO, embed_once=None):
+SPLIT_MIN_TRIALS = 128       # one CTA-pair tile; below, the fp32 kernels are launch-bound either way
+
+
+def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO, embed_once=None, use_split=None):
     """Scores of trials (table[i1[k]], table[i2[k]]) (replaces sv_trials_loaders.load_xvec_trials_from_numbatch
-    + forward).  Two device paths: `embed_once` transforms every table row once (nplda_table_prepare, cached
-    per table / parameter version) and scores a trial as r[i] + r[j] + A[i].B[j] (nplda_score_pairs); the other
-    fuses the gather into the full score kernel and recomputes both sides per trial.  Default: embed once when
-    the row table is already valid or the table has at most twice as many rows as this call has trials."""
+    + forward).  Three device paths:
+      * embed once: every table row is transformed ONCE (nplda_table_prepare, cached per table object / parameter
+        fingerprint) and a trial is r[i] + r[j] + A[i].B[j] (nplda_score_pairs) -- default when the row table is
+        already valid or the table has at most twice as many rows as this call has trials;
+      * split: both sides of every trial go through both layers on the tensor cores, rows gathered by TMA from the
+        pre-split image of the table (nplda_score_fwd_split) -- default otherwise (e.g. training-sized batches over
+        a large table) for NeuralPlda shapes the kernel takes;
+      * the fp32 kernel with the gather fused in (any shape, DPlda)."""
     require_cuda(table, i1, i2)
     d_in, d1, d2 = dims
     if table.dim() != 2 or table.shape[1] != d_in:
         raise RuntimeError(f"table must be [rows, {d_in}]")
-    table = _f32c(table)
     i1 = i1.to(torch.int64).contiguous()
     i2 = i2.to(torch.int64).contiguous()
     if i1.shape != i2.shape or i1.dim() != 1:
         raise RuntimeError("index tensors must be 1-D and the same length")
     n = i1.numel()
     dev = table.device
-    scores = torch.empty(n, dtype=torch.float32, device=dev)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
     if embed_once is None:
-        embed_once = max(d1, d2) < 176 and table.shape[0] > 0 and (packed.rowtab_valid(kind, table, d_in, d1, d2) or table.shape[0] <= 2 * n)
+        embed_once = (not use_split) and max(d1, d2) < 176 and table.shape[0] > 0 and (
+            packed.rowtab_valid(kind, table, d_in, d1, d2) or table.shape[0] <= 2 * n)
     if embed_once:
+        scores = torch.empty(n, dtype=torch.float32, device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
         rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
         with on_device(dev):
             check(lib().nplda_score_pairs(ptr(rowtab), table.shape[0], ptr(i1), ptr(i2), n, ptr(scores), ptr(flag),
                                           stream_ptr()), "nplda_score_pairs")
         return scores, flag
+    if use_split is None:
+        use_split = (split_supported(kind, d_in, d1, d2) and impl in (_lib.IMPL_AUTO, _lib.IMPL_TC)
+                     and n >= SPLIT_MIN_TRIALS and table.shape[0] > 0)
+    if use_split:
+        if not split_supported(kind, d_in, d1, d2):
+            raise RuntimeError("the pre-split tensor-core path takes NeuralPlda shapes with d_in % 32 == 0, widths <= 176")
+        return score_split(table, split_table(table), i1, i2, params, dims, packed)
+    table = _f32c(table)
+    scores = torch.empty(n, dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
     pack = packed.get(kind, params, d_in, d1, d2, mixed=(impl == _lib.IMPL_TC_F8))
+    if impl in (_lib.IMPL_TC, _lib.IMPL_TC_F8):
+        impl = _lib.IMPL_AUTO                     # the materialised-pair tcgen05 kernel has no gather; fp32 kernel
     with on_device(dev):
         if kind == "nplda":
             rc = lib().nplda_score_fwd_indexed(ptr(table), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1, d2,
@@ -331,7 +424,6 @@ def score_grid(kind, table, enrol_rows, test_rows, params, dims, packed):
         raise RuntimeError(f"table must be [rows, {d_in}]")
     if max(d1, d2) >= 176:
         raise RuntimeError("grid scoring supports layer widths up to 175")
-    table = _f32c(table)
     er = enrol_rows.to(torch.int64).contiguous()
     tr = test_rows.to(torch.int64).contiguous()
     if er.dim() != 1 or tr.dim() != 1:

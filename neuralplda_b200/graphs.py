@@ -49,6 +49,12 @@ class GraphedTrainStep:
         self._warmup = int(warmup)
         self._seen = 0
 
+    def flush(self):
+        """Synchronise and report a trial of ANY earlier batch (the last one included) that referred to a row outside
+        the x-vector table -- the reference raises KeyError from its dict lookup at once."""
+        from .sv_trials_loaders import check_pending_errors
+        check_pending_errors()
+
     def _body(self, i1, i2, t):
         self.optimizer.zero_grad(set_to_none=False)                 # static .grad buffers: the graph accumulates into them
         x1, x2 = _gather(self.tab, i1, i2)

@@ -154,7 +154,9 @@ class _PldaBase(nn.Module):
             scores_nontarget, _ = torch.sort(output[target < 0.5])
             if scores_target.numel() == 0:
                 raise RuntimeError("minc: no target trials (the reference fails in torch.min on an empty tensor)")
-            sums = torch.stack((target.sum(), (1 - target).sum())).tolist()
+            sums = torch.stack((target.sum(), (1 - target).sum())).tolist()          # synchronises ...
+            from .sv_trials_loaders import check_pending_errors
+            check_pending_errors()                                                    # ... so this is free here
             out_min, out_arg = F_.minc_sweep(scores_target, scores_nontarget, sums[0], sums[1], self.beta)
             minc_threshold = {}
             for k, beta in enumerate(self.beta):
@@ -194,13 +196,14 @@ class NeuralPlda(_PldaBase):
     def forward(self, x1, x2):
         return F_.NpldaScoreFn.apply(x1, x2, *self._params(), self.packed, self.impl)
 
-    def forward_indexed(self, table, idx1, idx2, embed_once=None):
+    def forward_indexed(self, table, idx1, idx2, embed_once=None, use_split=None):
         """Scores for trials given as row indices into a device-resident x-vector table (no gradient).
-        Every table row is transformed once and cached (F_.score_indexed); `embed_once=False` forces the
-        kernel that gathers and recomputes both sides per trial."""
+        Every table row is transformed once and cached (F_.score_indexed); `embed_once=False` recomputes both sides
+        per trial -- on the tensor cores from the pre-split image of the table (`use_split`, the default for shapes
+        the CTA-pair kernel takes) or with the fp32 kernel that fuses the gather."""
         with torch.no_grad():
             scores, flag = F_.score_indexed("nplda", table, idx1, idx2, self._params(), self._dims(),
-                                            self.packed, self.impl, embed_once)
+                                            self.packed, self.impl, embed_once, use_split)
         return scores, flag
 
     def forward_grid(self, table, enrol_rows, test_rows):

@@ -37,22 +37,67 @@ class XvectorTable:
         return torch.tensor([self.row_of[u] for u in ids], dtype=torch.int64)
 
 
-_tables = {}   # id(mega_dict) -> (weakref-ish guard, {device: XvectorTable})
+# (mega_dict object, {device: XvectorTable}), most recently used last.  Plain dicts cannot be weakly referenced, so an
+# entry holds its dict STRONGLY: while an entry exists its dict's id cannot be recycled by another dict (the failure
+# mode of a cache keyed on id()).  The cache is small (`MAX_TABLES` dicts; the reference uses one) and
+# `release_tables()` empties it.  A cached table is re-uploaded when the dict's length, its first / last key or the
+# array OBJECTS stored under them changed; vectors overwritten in place inside the same numpy arrays are not
+# detectable without reading every vector -- call `refresh_table(mega_dict)` after doing that.
+_tables = []
+MAX_TABLES = 4
+
+
+def _signature(mega_dict):
+    n = len(mega_dict)
+    if n == 0:
+        return (0,)
+    first = next(iter(mega_dict))
+    last = next(reversed(mega_dict))
+    return (n, first, last, id(mega_dict[first]), id(mega_dict[last]))
 
 
 def get_table(mega_dict, device):
-    """One upload per (dict object, device); re-uploaded if the dict grew."""
+    """One upload per (dict object, device); re-uploaded when the dict's signature changed."""
     device = torch.device(device)
-    key = id(mega_dict)
-    ent = _tables.get(key)
-    if ent is None or ent[0] != len(mega_dict):
-        ent = (len(mega_dict), {})
-        _tables[key] = ent
-    tab = ent[1].get(str(device))
+    sig = _signature(mega_dict)
+    ent = None
+    for i, e in enumerate(_tables):
+        if e[0] is mega_dict:
+            ent = _tables.pop(i)
+            break
+    if ent is None or ent[1] != sig:
+        ent = (mega_dict, sig, {})
+    _tables.append(ent)
+    del _tables[:-MAX_TABLES]
+    tab = ent[2].get(str(device))
     if tab is None:
         tab = XvectorTable(mega_dict, device)
-        ent[1][str(device)] = tab
+        ent[2][str(device)] = tab
     return tab
+
+
+def refresh_table(mega_dict):
+    """Forget the device copies of this dict (after its vectors were modified in place)."""
+    _tables[:] = [e for e in _tables if e[0] is not mega_dict]
+
+
+def release_tables():
+    """Drop every cached device table (and the references to their dicts)."""
+    del _tables[:]
+
+
+def check_pending_errors():
+    """Synchronise and raise the KeyError of any gather that met a row outside its table.  The per-batch path
+    reports such a row at the NEXT loader call (no host round trip per batch); call this after the last batch of a
+    loop -- `GraphedTrainStep.flush()` and `minc()` do -- so that the final batch cannot slip through.  Until it is
+    reported the affected rows are NaN, so nothing computed from them can pass for a result."""
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    for e in _tables:
+        for tab in e[2].values():
+            flag = tab.__dict__.get("_bad_flag")
+            if flag is not None:
+                flag.check()
 
 
 def _rows_from_nums(tab, num_to_id_dict, data):
@@ -75,7 +120,8 @@ def _rows_from_nums(tab, num_to_id_dict, data):
 class _BadIndexFlag:
     """int32 flag in pinned host memory that the gather kernel raises for rows outside the table.  The host reads
     it without a synchronising copy: a raised flag is seen at the next loader call after the kernel ran (the
-    reference's loop reads loss.item() every step, so at the next batch at the latest)."""
+    reference's loop reads loss.item() every step, so at the next batch at the latest) or by check_pending_errors();
+    the rows themselves come back as NaN."""
 
     def __init__(self):
         self.t = torch.zeros(1, dtype=torch.int32).pin_memory()

@@ -839,15 +839,20 @@ def test_loader_gather_bit_exact(ref_out):
     Y1, Y2 = L.load_xvec_trials_from_idbatch(mega, trials, torch.device(DEV))
     assert torch.equal(Y1.cpu(), R1[:7]) and torch.equal(Y2.cpu(), R2[:7])
     # unknown rows: CPU indices raise at once (the reference's dict lookup raises KeyError); GPU indices are not read
-    # back -- the gather kernel zero-fills the row and raises a pinned flag that the next loader call reports
+    # back -- the gather kernel fills the row with NaN and raises a pinned flag that the next loader call (or
+    # check_pending_errors(), e.g. after the last batch of a loop) reports
     with pytest.raises(KeyError):
         L.load_xvec_trials_from_numbatch(mega, num_to_id, torch.tensor([len(ids)]), torch.tensor([0]), torch.device(DEV))
     bad = torch.tensor([0, len(ids) + 3], device=DEV)
     B1, B2 = L.load_xvec_trials_from_numbatch(mega, num_to_id, bad, bad, torch.device(DEV))
     torch.cuda.synchronize()
-    assert torch.equal(B1[0].cpu(), torch.from_numpy(z["vecs"][0]).float()) and float(B1[1].abs().sum()) == 0.0
+    assert torch.equal(B1[0].cpu(), torch.from_numpy(z["vecs"][0]).float()) and bool(torch.isnan(B1[1]).all())
     with pytest.raises(KeyError):
         L.load_xvec_trials_from_numbatch(mega, num_to_id, d1.to(DEV), d2.to(DEV), torch.device(DEV))
+    L.load_xvec_trials_from_numbatch(mega, num_to_id, bad, bad, torch.device(DEV))      # "last batch of an epoch"
+    with pytest.raises(KeyError):
+        L.check_pending_errors()
+    L.check_pending_errors()                                                            # reported once
     X1, _ = L.load_xvec_trials_from_numbatch(mega, num_to_id, d1.to(DEV), d2.to(DEV), torch.device(DEV))   # flag cleared
     assert torch.equal(X1.cpu(), R1)
 
