@@ -3,33 +3,47 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one pass of the hot path over one batch of synthetic trial pairs:
-the fused score kernel K1 over all pairs, the loss-accumulator kernel K2 over
-the scores, the all-reduce of the 4K+4 fp64 accumulators (N > 1) and the
-finalisation of softCdet / BCE / Cdet.  Workload at every N: BASELINE.json
-configs[1], 1M synthetic 512-d trial pairs PER GPU (weak scaling: the trial
-list is sharded by contiguous ranges, per-GPU work fixed), NeuralPlda with
-sre_config.cfg dims (512 -> 170 -> 170, K = 2 betas), Kaldi-init parameters.
+A "step" is one pass of the hot path over one batch of synthetic trial pairs: the fused score kernel K1 over all pairs,
+the loss-accumulator kernel K2 over the scores, the all-reduce of the 4K+4 fp64 accumulators (N > 1) and the
+finalisation of softCdet / BCE / Cdet.  Workload of `value` at every N: BASELINE.json configs[1], 1M synthetic 512-d
+trial pairs PER GPU (weak scaling: contiguous trial-list ranges, per-GPU work fixed), NeuralPlda with sre_config.cfg
+dims (512 -> 170 -> 170, K = 2 betas), Kaldi-init parameters.
 
-Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM;
-`e2e` = the same through the public module API from pinned HOST buffers (H2D of
-the pairs and labels and the D2H of the loss inside the timed region);
-`roofline` = K1's algorithmic bytes (4100 B/pair) / its CUDA-event duration
-against the measured HBM copy bandwidth; `cpu_baseline` = the CPU oracle port
-of the reference forward timed on this box's host cores.
+Prints ONE JSON line (rank 0):
+  value      pairs/s with the materialised [N,512] x2 pairs resident in HBM (K1's layout, 4100 B per pair);
+  roofline   K1's algorithmic bytes / its CUDA-event duration against the measured HBM copy bandwidth, plus a
+             `sustained` object (>= 3 s of back-to-back launches with NVML power / clock samples);
+  e2e        the REFERENCE'S OWN CALL PATH for the same 1M trials (xvector_NeuralPlda_pytorch.py:36-41): a host
+             x-vector dict (uploaded once, amortisation stated) + host (int64, int64, float32) index batches ->
+             load_xvec_trials_from_numbatch -> model(x1, x2) -> model.loss(...).item(); host->device copies of the
+             batch and the device->host read of the loss inside the timed region;
+  cpu_baseline  the unmodified reference (baseline/_ref, kind "reference"; the oracle port if it is absent) forward on
+             this box's host cores, bounded sample;
+  scoring_loop  generate_voices_scores on a 200k-trial file (scorefile_generator.py:41-56), this package;
+  indexed_split / trial_list / train_step  separately-labelled legs (never mixed into value / roofline);
+  N > 1: cfg3_strong (BASELINE configs[3]: 50M trials sharded by contiguous trial ranges, one all-reduce of the loss
+         accumulators) and cfg4_dplda_train (configs[4]: DPlda, 10M trials split over the ranks, forward + BCE +
+         backward + NCCL all-reduce of the parameter gradients).
+
+`--impl reference` runs the UNMODIFIED reference from baseline/_ref on the host cores through the same call paths
+(forward in scorefile_generator.py's 102400-pair chunks; the loop body of xvector_NeuralPlda_pytorch.py:36-41;
+generate_voices_scores) on bounded samples of the same workload.
 """
 import argparse
 import json
 import os
 import sys
+import tempfile
 import threading
 import time
+import types
 
 import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF = os.path.join(ROOT, "baseline", "_ref")
 
 PAIRS_PER_GPU = 1_000_000
 D_IN, D1, D2 = 512, 170, 170
@@ -37,6 +51,9 @@ BETAS = [99.0, 199.0]
 ALPHA = 15.0
 BYTES_PER_PAIR = 2 * D_IN * 4 + 4          # 4100 B algorithmic per pair
 REF_CHUNK = 102_400                         # scorefile_generator.py:22 default scoring batch
+TABLE_UTTS, TABLE_SPK = 100_000, 2_000      # the x-vector dict of the e2e / scoring-loop legs
+SCORING_TRIALS = 200_000                    # "generate_voices_scores ... on a 200 k-trial file"
+FLOPS_PER_PAIR_BF16X3 = 2 * 3 * 2 * (D_IN * 176 + 176 * 176)   # 2 sides x 3 bf16 products x 2 flop x padded MACs = 1,453,056
 
 
 class NC:
@@ -49,6 +66,18 @@ def kaldi_params():
     return {k: torch.from_numpy(z[k].copy()) for k in z.files}
 
 
+PARAM_KEYS = (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias", "b1"),
+              ("centering_and_wccn_plda.weight", "W2"), ("centering_and_wccn_plda.bias", "b2"),
+              ("P_sqrt", "P_sqrt"), ("Q", "Q"))
+
+
+def load_kaldi_init(model, kp):
+    sd = model.state_dict()
+    for name, key in PARAM_KEYS:
+        sd[name].copy_(kp[key])
+    return model
+
+
 def measured_traffic():
     """DRAM bytes per K1 launch from the committed `ncu --set full` capture of this workload (profiles/)."""
     p = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -59,19 +88,22 @@ def measured_traffic():
     return None
 
 
-def measured_peak():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        j = json.load(open(p))
+        return {"hbm": float(j["hbm_gbs"]), "bf16": float(j["bf16_tflops"]), "bf16_sustained": float(j["bf16_tflops_sustained"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML during the timed region."""
+    """Samples SM clock, power and throttle reasons through NVML during a timed region."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.index, self.period, self.stop_flag = index, period, False
+        self.samples, self.power, self.reasons, self.max_mhz = [], [], set(), None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -95,6 +127,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -103,12 +139,22 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
+
+    def finish(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        return self.summary()
 
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        out = {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.power:
+            out["power_w_median"] = float(np.median(self.power))
+            out["power_w_max"] = float(np.max(self.power))
+        if self.samples:
+            out["sm_mhz_min"] = float(np.min(self.samples))
+        return out
 
 
 def synth_on_device(n, seed, mean, dev):
@@ -129,30 +175,103 @@ def synth_on_device(n, seed, mean, dev):
     return x1, x2, tgt.float()
 
 
-def cpu_forward_timing(kp, n_chunks, repeats, threads=None, min_seconds=0.0):
-    """The reference's CPU forward restated by the oracle, in chunks of 102,400
-    pairs as scorefile_generator.py scores, under no_grad, all host threads.
-    Repeats passes of `n_chunks` chunks until `repeats` passes are done AND at least
-    `min_seconds` of CPU work has been timed; returns the best pass."""
+def synth_corpus(kp, n_utts=TABLE_UTTS, n_spk=TABLE_SPK, seed=4242):
+    """The host-side x-vector dict of the reference's drivers (xvector_NeuralPlda_pytorch.py:117-119): utt id ->
+    np.float32[512], speaker-structured like SURVEY 8d; plus the speaker of every utterance."""
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.randn(n_spk, D_IN, generator=g)
+    spk = torch.arange(n_utts) % n_spk
+    vecs = (kp["mean"] + centers[spk] + 0.7 * torch.randn(n_utts, D_IN, generator=g)).numpy()
+    mega = {f"utt{i:06d}": vecs[i] for i in range(n_utts)}
+    return mega, spk
+
+
+def synth_trials(spk, n, seed, p_target=0.1):
+    """(int64 idx1[n], int64 idx2[n], float32 label[n]): the batch layout of sv_trials_loaders.py:384-392."""
+    g = torch.Generator().manual_seed(seed)
+    n_utts = spk.numel()
+    n_spk = int(spk.max()) + 1
+    per = n_utts // n_spk
+    i1 = torch.randint(0, n_utts, (n,), generator=g)
+    tgt = torch.rand(n, generator=g) < p_target
+    same = (i1 % n_spk) + n_spk * torch.randint(0, per, (n,), generator=g)          # another utterance of the same speaker
+    i2 = torch.where(tgt, same, torch.randint(0, n_utts, (n,), generator=g))
+    return i1, i2, (spk[i1] == spk[i2]).float()
+
+
+def write_trial_file(path, ids, i1, i2, lab):
+    with open(path, "w") as f:
+        f.write("".join(f"{ids[a]}\t{ids[b]}.wav\t{int(c)}\n" for a, b, c in zip(i1.tolist(), i2.tolist(), lab.tolist())))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The reference itself (baseline/_ref, verbatim copies) and the oracle port, on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+
+def reference_available():
+    """baseline/_ref holds the verbatim reference files (sha256 manifest written by baseline/install_reference.py)."""
+    import importlib.util
+    try:
+        spec = importlib.util.spec_from_file_location("install_reference", os.path.join(ROOT, "baseline", "install_reference.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return bool(mod.verify())
+    except Exception:
+        return False
+
+
+def load_reference():
+    """utils.models / utils.sv_trials_loaders / utils.scorefile_generator of the unmodified reference.  matplotlib and
+    kaldi_io are imported at module level there and never used on this path: empty stand-ins when not installed."""
+    for name in ("matplotlib", "matplotlib.pyplot", "kaldi_io"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import utils.models as M
+    import utils.sv_trials_loaders as L
+    import utils.scorefile_generator as S
+    assert os.path.samefile(os.path.dirname(M.__file__), os.path.join(REF, "utils")), "utils.* is not the reference"
+    return M, L, S
+
+
+def cpu_forward_timing(kp, n_chunks, repeats, threads=None, min_seconds=0.0, use_reference=True):
+    """The reference's CPU forward in chunks of 102,400 pairs as scorefile_generator.py scores, under no_grad, all host
+    threads: `NeuralPlda.forward` of the unmodified reference (baseline/_ref) or, when that is absent, the oracle port.
+    Repeats passes of `n_chunks` chunks until `repeats` passes are done AND `min_seconds` of CPU work has been timed;
+    returns the best pass."""
     from oracle import nplda_oracle as O
     if threads:
         torch.set_num_threads(threads)
     x1, x2, _ = O.synth_pairs(REF_CHUNK, 2000, seed=1002, mean=kp["mean"])
-    args = (kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    kind = "port"
+    if use_reference and reference_available():
+        M, _, _ = load_reference()
+        model = load_kaldi_init(M.NeuralPlda(NC), kp).eval()
+        fwd = lambda: model.forward(x1, x2)
+        kind = "reference"
+    else:
+        args = (kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+        fwd = lambda: O.nplda_score(x1, x2, *args)
     with torch.no_grad():
-        O.nplda_score(x1[:4096], x2[:4096], *args)   # warm the thread pool
+        fwd()                                            # warm the thread pool
         best, total, passes = None, 0.0, 0
         while passes < repeats or total < min_seconds:
             t0 = time.perf_counter()
             for _ in range(n_chunks):
-                s = O.nplda_score(x1, x2, *args)
+                s = fwd()
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
             total += dt
             passes += 1
             if total > 30.0:
                 break
-    cpu_forward_timing.last = {"passes": passes, "total_s": total}
+    cpu_forward_timing.last = {"passes": passes, "total_s": total, "kind": kind}
     return n_chunks * REF_CHUNK / best, best, float(s[0])
 
 
@@ -162,29 +281,79 @@ def run_reference(args):
         return
     kp = kaldi_params()
     threads = os.cpu_count()
-    n_chunks = 10                                    # one step = the configs[1] workload: 1,024,000 pairs in scoring-loop chunks
     torch.set_num_threads(threads)
+    have_ref = reference_available()
+    n_chunks = 10                                    # one step = the configs[1] workload: 1,024,000 pairs in scoring-loop chunks
     for _ in range(args.warmup):
         cpu_forward_timing(kp, 1, 1, threads)
     t0 = time.perf_counter()
     rates = [cpu_forward_timing(kp, n_chunks, 1, threads)[0] for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     value = float(np.median(rates))
-    sample = f"{n_chunks} x {REF_CHUNK}-pair chunks per step (same synthetic chunk re-scored), oracle port of NeuralPlda.forward, no_grad"
+    kind = cpu_forward_timing.last["kind"]
+    what = "NeuralPlda.forward of the unmodified reference (baseline/_ref/utils/models.py)" if kind == "reference" else \
+        "oracle port of NeuralPlda.forward (baseline/_ref absent)"
+    sample = f"{n_chunks} x {REF_CHUNK}-pair chunks per step (same synthetic chunk re-scored), {what}, no_grad"
+    # ---- the reference's own call path, end to end (xvector_NeuralPlda_pytorch.py:36-41 without the backward) ----
+    e2e = {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    scoring = None
+    if have_ref:
+        M, L, S = load_reference()
+        mega, spk = synth_corpus(kp)
+        num_to_id = {i: j for i, j in enumerate(list(mega))}
+        model = load_kaldi_init(M.NeuralPlda(NC), kp).eval()
+        i1, i2, lab = synth_trials(spk, REF_CHUNK, seed=77)
+        dev = torch.device("cpu")
+
+        def loop_body():
+            with torch.no_grad():
+                d1, d2, tg = i1.to(dev), i2.to(dev), lab.to(dev)
+                x1, x2 = L.load_xvec_trials_from_numbatch(mega, num_to_id, d1, d2, dev)
+                out = model(x1, x2)
+                return model.loss(out, tg).item()
+
+        loop_body()
+        reps, t1 = max(1, min(args.steps, 3)), time.perf_counter()
+        for _ in range(reps):
+            loss = loop_body()
+        dt = (time.perf_counter() - t1) / reps
+        e2e = {"value": REF_CHUNK / dt, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "api": "reference: load_xvec_trials_from_numbatch -> NeuralPlda.forward -> .loss(...).item() on the CPU "
+                      "(xvector_NeuralPlda_pytorch.py:36-41), one 102400-trial batch per step over a 100k-utterance dict",
+               "sample_pairs_per_step": REF_CHUNK, "softcdet": loss}
+        with tempfile.TemporaryDirectory() as td:
+            ids = list(mega)
+            a, b, c = synth_trials(spk, SCORING_TRIALS, seed=78)
+            tf = os.path.join(td, "trials.tsv")
+            write_trial_file(tf, ids, a, b, c)
+            t1 = time.perf_counter()
+            S.generate_voices_scores(os.path.join(td, "scores.txt"), tf, mega, model, dev, REF_CHUNK)
+            dt = time.perf_counter() - t1
+            scoring = {"value": SCORING_TRIALS / dt, "unit": "trials/s", "seconds": dt, "trials": SCORING_TRIALS,
+                       "api": "reference generate_voices_scores (scorefile_generator.py:41-56) on the CPU, batch 102400"}
     out = {
         "impl": "reference", "metric": "trial-pairs scored/sec (512-d xvec)", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * n_chunks * REF_CHUNK / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1M synthetic 512-d trial pairs per GPU, NeuralPlda 512-170-170 forward",
-                   "sample_pairs_per_step": n_chunks * REF_CHUNK},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample,
+        "config": {"workload": WORKLOAD, "sample_pairs_per_step": n_chunks * REF_CHUNK},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample,
                          "torch_threads": torch.get_num_threads(), "wall_s": wall},
-        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": e2e,
         "gpu_launches": 0,
     }
+    if scoring is not None:
+        out["scoring_loop"] = scoring
     print(json.dumps(out), flush=True)
 
+
+WORKLOAD = ("configs[1]: 1M synthetic 512-d trial pairs per GPU, NeuralPlda 512-170-170 Kaldi-init, "
+            "score + softCdet/BCE/Cdet accumulators (K=2)")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# This package on the GPU
+# ----------------------------------------------------------------------------------------------------------------
 
 def run_ours(args):
     # libraries (NCCL's version banner) write to the C-level stdout: keep fd 1 for the ONE JSON line
@@ -202,10 +371,20 @@ def _emit(saved_stdout, obj):
     os.write(saved_stdout, (json.dumps(obj) + "\n").encode())
 
 
+def _event_time(fn, reps, stream):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def _run_ours(args, saved_stdout):
     import torch.distributed as dist
     import neuralplda_b200 as npl
-    from neuralplda_b200 import _lib, functional as F_
+    from neuralplda_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -219,12 +398,7 @@ def _run_ours(args, saved_stdout):
     group = True if world > 1 else None
 
     kp = kaldi_params()
-    model = npl.NeuralPlda(NC).to(dev)
-    sd = model.state_dict()
-    for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias", "b1"),
-                      ("centering_and_wccn_plda.weight", "W2"), ("centering_and_wccn_plda.bias", "b2"),
-                      ("P_sqrt", "P_sqrt"), ("Q", "Q")):
-        sd[name].copy_(kp[key])
+    model = load_kaldi_init(npl.NeuralPlda(NC).to(dev), kp)
     model.impl = {"auto": npl.IMPL_AUTO, "simt": npl.IMPL_SIMT, "tc": npl.IMPL_TC, "f8": npl.IMPL_TC_F8}[args.kernel]
     model.process_group = group
     model.eval()
@@ -234,6 +408,7 @@ def _run_ours(args, saved_stdout):
     lib = _lib.lib()
     pack = model.packed.get("nplda", model._params(), D_IN, D1, D2)
     scores = torch.empty(n, device=dev)
+    buf = {"x1": x1, "x2": x2, "scores": scores}      # the closures below read the buffers through this dict
     thresholds = torch.cat([model.threshold[b].detach() for b in BETAS])
     thx = model.threshold_Xent.detach()
     acc = torch.zeros(4 * len(BETAS) + 4, dtype=torch.float64, device=dev)
@@ -242,8 +417,8 @@ def _run_ours(args, saved_stdout):
     stream = torch.cuda.current_stream()
 
     def k1():
-        _lib.check(lib.nplda_score_fwd(_lib.ptr(x1), _lib.ptr(x2), n, D_IN, D1, D2, _lib.ptr(pack), _lib.ptr(scores),
-                                       model.impl, _lib.stream_ptr()), "nplda_score_fwd")
+        _lib.check(lib.nplda_score_fwd(_lib.ptr(buf["x1"]), _lib.ptr(buf["x2"]), n, D_IN, D1, D2, _lib.ptr(pack),
+                                       _lib.ptr(buf["scores"]), model.impl, _lib.stream_ptr()), "nplda_score_fwd")
 
     def step(ev=None):
         if ev:
@@ -252,7 +427,7 @@ def _run_ours(args, saved_stdout):
         if ev:
             ev[1].record(stream)
         acc.zero_()
-        _lib.check(lib.nplda_loss_accum(_lib.ptr(scores), _lib.ptr(t), n, _lib.ptr(thresholds), len(BETAS), ALPHA,
+        _lib.check(lib.nplda_loss_accum(_lib.ptr(buf["scores"]), _lib.ptr(t), n, _lib.ptr(thresholds), len(BETAS), ALPHA,
                                         _lib.ptr(thx), _lib.ptr(acc), _lib.stream_ptr()), "nplda_loss_accum")
         if world > 1:
             dist.all_reduce(acc)
@@ -282,84 +457,284 @@ def _run_ours(args, saved_stdout):
     launches = _lib.launch_count() - launches0
     total_ms = e0.elapsed_time(e1)
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1_events]))
-    sampler.stop_flag = True
-    sampler.join(timeout=1.0)
+    clocks = sampler.finish()
     loss_vals = out.tolist()
 
-    # ---- end to end through the module API from pinned host buffers ----------------
-    e2e_steps = max(3, min(args.steps, 10))
     if args.skip_e2e:                                # profiling runs (ncu) only: never a bench line
         if rank == 0:
             _emit(saved_stdout, {"profiling_only": True, "k1_ms": k1_ms, "ms_per_step": total_ms / args.steps})
         if world > 1:
             dist.destroy_process_group()
         return
-    h1 = torch.empty(n, D_IN, pin_memory=True); h1.copy_(x1)
-    h2 = torch.empty(n, D_IN, pin_memory=True); h2.copy_(x2)
-    ht = torch.empty(n, pin_memory=True); ht.copy_(t)
-    d1_, d2_, dt_ = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(t)
+
+    # ---- sustained regime of K1: >= 3 s of back-to-back launches, NVML power / clock sampled (rank 0 reports) ----
+    sustained = None
+    if not args.skip_sustained:
+        s_sampler = ClockSampler(local, period=0.02)
+        reps = max(200, int(3.2 / (k1_ms * 1e-3)))
+        barrier()
+        s_sampler.start()
+        sus_ms = _event_time(k1, reps, stream)
+        s_clk = s_sampler.finish()
+        sustained = {"launches": reps, "seconds": sus_ms * reps * 1e-3, "k1_ms": sus_ms, "clocks": s_clk}
+
+    # ---- end to end: the reference's own call path from HOST data (xvector_NeuralPlda_pytorch.py:36-41) ----------
+    from neuralplda_b200 import sv_trials_loaders as L
+    e2e_steps = max(3, min(args.steps, 10))
+    mega, spk = synth_corpus(kp)
+    num_to_id = {i: j for i, j in enumerate(list(mega))}
+    hi1, hi2, hlab = (v.pin_memory() for v in synth_trials(spk, n, seed=77 + rank))
+    t0 = time.perf_counter()
+    tab = L.get_table(mega, dev)                       # one-off: the x-vector dict goes to the GPU once per process
+    torch.cuda.synchronize()
+    upload_s = time.perf_counter() - t0
 
     def e2e_step():
-        d1_.copy_(h1, non_blocking=True); d2_.copy_(h2, non_blocking=True); dt_.copy_(ht, non_blocking=True)
         with torch.no_grad():
-            s = model(d1_, d2_)                      # NeuralPlda.forward, the reference-facing call
-            return model.loss(s, dt_).item()         # softCdet incl. all-reduce; D2H of the scalar
+            d1, d2, tg = hi1.to(dev, non_blocking=True), hi2.to(dev, non_blocking=True), hlab.to(dev, non_blocking=True)
+            a, b = L.load_xvec_trials_from_numbatch(mega, num_to_id, d1, d2, dev)
+            s = model(a, b)                              # NeuralPlda.forward, the reference-facing call
+            return model.loss(s, tg).item()              # softCdet incl. all-reduce; D2H of the scalar
 
     e2e_step()
+    launches_e2e0 = _lib.launch_count()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_loss = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    launches_e2e = (_lib.launch_count() - launches_e2e0) / e2e_steps
+
+    # the round-1 number for comparison: materialised host pairs over PCIe (4.1 KB per pair)
+    e2e_mat = None
+    if not args.skip_e2e_materialised and world == 1:
+        h1 = torch.empty(n, D_IN, pin_memory=True); h1.copy_(x1)
+        h2 = torch.empty(n, D_IN, pin_memory=True); h2.copy_(x2)
+        ht = torch.empty(n, pin_memory=True); ht.copy_(t)
+        d1_, d2_, dt_ = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(t)
+
+        def e2e_mat_step():
+            d1_.copy_(h1, non_blocking=True); d2_.copy_(h2, non_blocking=True); dt_.copy_(ht, non_blocking=True)
+            with torch.no_grad():
+                return model.loss(model(d1_, d2_), dt_).item()
+
+        e2e_mat_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_mat_step()
+        torch.cuda.synchronize()
+        e2e_mat = {"value": n * 3 / (time.perf_counter() - t0), "unit": "pairs/s", "h2d_bytes_per_step": n * (2 * D_IN * 4 + 4),
+                   "d2h_bytes_per_step": 4, "api": "NeuralPlda.forward + .loss(...).item() on pinned host [N,512] pairs "
+                   "(a layout the reference never holds on the host; PCIe-bound)"}
+        del h1, h2, ht, d1_, d2_, dt_
 
     tm = torch.tensor([total_ms, k1_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     total_ms, k1_ms, e2e_s = tm.tolist()
 
+    multi = None
+    if world > 1 and not args.skip_multi:
+        buf.clear()
+        del x1, x2, scores
+        torch.cuda.empty_cache()
+        multi = multi_gpu_legs(model, kp, dev, world, rank)
+
     if rank == 0:
-        peak, peak_src = measured_peak()
+        pk = measured_peaks()
         value = world * n * args.steps / (total_ms * 1e-3)
         achieved = n * BYTES_PER_PAIR / (k1_ms * 1e-3) / 1e9
         cpu_rate, cpu_s, _ = (cpu_forward_timing(kp, 10, 3, os.cpu_count(), min_seconds=12.0)
                               if not args.no_cpu_baseline else (None, 0, 0))
-        tl = trial_list_leg(model, kp, dev) if (not args.skip_trial_list and world == 1) else None
-        tr = train_leg(kp, dev, x1, x2, t) if (not args.skip_trial_list and world == 1) else None
+        extra = world == 1 and not args.skip_trial_list
         res = {
             "metric": "trial-pairs scored/sec (512-d xvec)", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1M synthetic 512-d trial pairs per GPU (materialised [N,512] x2 fp32), "
-                                   "NeuralPlda 512-170-170 Kaldi-init, score + softCdet/BCE/Cdet accumulators (K=2)",
+            "config": {"workload": WORKLOAD, "layout": "materialised [N,512] x2 fp32 pairs resident in HBM",
                        "pairs_per_gpu": n, "kernel": args.kernel, "sharding": "contiguous trial-list ranges, "
                        "one all-reduce of 12 fp64 accumulators per step" if world > 1 else "single GPU",
                        "l2": "inputs (4.1 GB per step) larger than L2 (126 MB); no flush needed"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(), "kernel": "K1 fused score kernel", "k1_ms": k1_ms,
-                         "bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                         "traffic": measured_traffic(), "kernel": "K1 fused score kernel (score_tc_kernel)", "k1_ms": k1_ms,
+                         "bytes_per_pair": BYTES_PER_PAIR, "peak_source": pk["source"],
+                         "tensor": {"flops_per_pair_bf16x3": FLOPS_PER_PAIR_BF16X3,
+                                    "achieved_tflops": n * FLOPS_PER_PAIR_BF16X3 / (k1_ms * 1e-3) / 1e12,
+                                    "peak_tflops_burst": pk["bf16"], "peak_tflops_sustained": pk["bf16_sustained"]}},
             "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "pairs/s",
-                    "h2d_bytes_per_step": n * (2 * D_IN * 4 + 4), "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                    "api": "NeuralPlda.forward + .loss(...).item() on pinned host inputs"},
+                    "h2d_bytes_per_step": n * (8 + 8 + 4), "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                    "api": "host x-vector dict + pinned host (int64, int64, float32) index batch -> .to(device) -> "
+                           "load_xvec_trials_from_numbatch -> NeuralPlda.forward -> .loss(...).item() "
+                           "(the loop body of xvector_NeuralPlda_pytorch.py:36-41 under no_grad)",
+                    "table": {"utterances": TABLE_UTTS, "one_off_upload_bytes": TABLE_UTTS * D_IN * 4, "one_off_upload_s": upload_s,
+                              "amortisation": "uploaded once per (dict, device) and kept; not in the timed steps -- the "
+                                              "reference's loop gathers from the same dict for every batch of every epoch"},
+                    "libnplda_launches_per_step": launches_e2e},
             "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "loss": {"softcdet": loss_vals[0], "bce": loss_vals[1], "cdet": loss_vals[2], "e2e_softcdet": e2e_loss},
         }
+        if sustained is not None:
+            a_s = n * BYTES_PER_PAIR / (sustained["k1_ms"] * 1e-3) / 1e9
+            res["roofline"]["sustained"] = dict(sustained, achieved=a_s, frac_sustained=a_s / pk["hbm"],
+                                                achieved_tflops=n * FLOPS_PER_PAIR_BF16X3 / (sustained["k1_ms"] * 1e-3) / 1e12)
+        if e2e_mat is not None:
+            res["e2e_materialised"] = e2e_mat
         if cpu_rate is not None:
-            res["cpu_baseline"] = {"value": cpu_rate, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+            last = cpu_forward_timing.last
+            what = "NeuralPlda.forward of the unmodified reference (baseline/_ref)" if last["kind"] == "reference" else \
+                "oracle port of NeuralPlda.forward"
+            res["cpu_baseline"] = {"value": cpu_rate, "unit": "pairs/s", "cores": os.cpu_count(), "kind": last["kind"],
                                    "sample": f"passes of 10 x {REF_CHUNK}-pair chunks (1,024,000 pairs, same synthetic chunk "
-                                             f"re-scored) for {cpu_forward_timing.last['total_s']:.1f} s of CPU work "
-                                             f"({cpu_forward_timing.last['passes']} passes), best pass {cpu_s:.2f} s; oracle "
-                                             f"port of NeuralPlda.forward under no_grad",
+                                             f"re-scored) for {last['total_s']:.1f} s of CPU work ({last['passes']} passes), "
+                                             f"best pass {cpu_s:.2f} s; {what} under no_grad",
                                    "torch_threads": torch.get_num_threads()}
-        if tl is not None:
-            res["trial_list"] = tl
-        if tr is not None:
-            res["train_step"] = tr
+        if extra:
+            res["scoring_loop"] = scoring_loop_leg(model, mega, spk, dev)
+            res["indexed_split"] = split_leg(model, kp, dev, pk)
+            res["trial_list"] = trial_list_leg(model, kp, dev)
+            res["train_step"] = train_leg(kp, dev, x1, x2, t)
+        if multi is not None:
+            res.update(multi)
         _emit(saved_stdout, res)
     if world > 1:
         dist.destroy_process_group()
+
+
+def scoring_loop_leg(model, mega, spk, dev):
+    """SURVEY 8d end-to-end comparator: generate_voices_scores (scorefile_generator.py:41-56) on a 200k-trial file over
+    the 100k-utterance dict: native trial reader, id lookups, trial scoring from the device table, native score writer."""
+    from neuralplda_b200 import scorefile_generator as S
+    ids = list(mega)
+    a, b, c = synth_trials(spk, SCORING_TRIALS, seed=78)
+    with tempfile.TemporaryDirectory() as td:
+        tf, sf = os.path.join(td, "trials.tsv"), os.path.join(td, "scores.txt")
+        write_trial_file(tf, ids, a, b, c)
+        S.generate_voices_scores(sf, tf, mega, model, dev, REF_CHUNK)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            S.generate_voices_scores(sf, tf, mega, model, dev, REF_CHUNK)
+        dt = (time.perf_counter() - t0) / 3
+        nbytes = os.path.getsize(sf)
+    return {"value": SCORING_TRIALS / dt, "unit": "trials/s", "seconds": dt, "trials": SCORING_TRIALS, "score_file_bytes": nbytes,
+            "api": "neuralplda_b200.scorefile_generator.generate_voices_scores, batch 102400, model stays on the GPU"}
+
+
+def split_leg(model, kp, dev, pk):
+    """Separately-labelled: K1x, the pre-split-table CTA-pair kernel (nplda_score_fwd_split), device-resident: 1M random
+    trials over tables of 6,500 (L2-resident) and 100,000 (205 MB, beyond L2) utterances.  Tensor-bound: reported
+    against the measured bf16 peaks with its bf16x3 flop count."""
+    from neuralplda_b200 import _lib, functional as F_
+    lib = _lib.lib()
+    n = PAIRS_PER_GPU
+    stream = torch.cuda.current_stream()
+    out = {"kernel": "score_tcx_kernel (TMA gather4 + tcgen05.mma.cta_group::2)", "trials": n, "flops_per_pair_bf16x3": FLOPS_PER_PAIR_BF16X3}
+    g = torch.Generator(device=dev).manual_seed(5)
+    for rows in (6_500, 100_000):
+        tab = kp["mean"].to(dev) + torch.randn(rows, D_IN, generator=g, device=dev)
+        a = torch.randint(0, rows, (n,), generator=g, device=dev)
+        b = torch.randint(0, rows, (n,), generator=g, device=dev)
+        split = F_.split_table(tab)
+        pack = model.packed.get("nplda", model._params(), D_IN, D1, D2, pair=True)
+        sc, flag = torch.empty(n, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def k():
+            _lib.check(lib.nplda_score_fwd_split(_lib.ptr(split), rows, _lib.ptr(a), _lib.ptr(b), n, D_IN, D1, D2, _lib.ptr(pack),
+                                                 _lib.ptr(sc), _lib.ptr(flag), _lib.stream_ptr()), "nplda_score_fwd_split")
+        for _ in range(3):
+            k()
+        torch.cuda.synchronize()
+        time.sleep(0.5)
+        burst = _event_time(k, 10, stream)
+        sus = _event_time(k, max(200, int(2.0 / (burst * 1e-3))), stream)
+        with torch.no_grad():
+            ref = model(tab[a[:100_000]], tab[b[:100_000]])
+        out[f"table_{rows}"] = {"ms_burst": burst, "ms_sustained": sus, "value": n / (burst * 1e-3), "value_sustained": n / (sus * 1e-3),
+                                "unit": "pairs/s", "tflops_burst": n * FLOPS_PER_PAIR_BF16X3 / (burst * 1e-3) / 1e12,
+                                "frac_of_bf16_burst_peak": n * FLOPS_PER_PAIR_BF16X3 / (burst * 1e-3) / 1e12 / pk["bf16"],
+                                "frac_of_bf16_sustained_peak": n * FLOPS_PER_PAIR_BF16X3 / (sus * 1e-3) / 1e12 / pk["bf16_sustained"],
+                                "max_abs_diff_to_k1_on_100k": float((ref - sc[:100_000]).abs().max())}
+        del tab, split
+    return out
+
+
+def multi_gpu_legs(model, kp, dev, world, rank):
+    """N > 1 only.  BASELINE configs[3]: 50M trials (materialised pairs, 205 GB in total) sharded by contiguous trial
+    ranges, K1 + K2 per rank, ONE all-reduce of the raw loss accumulators, strong scaling.  configs[4]: DPlda, 10M
+    trials split over the ranks, forward + BCE + backward + NCCL all-reduce of the parameter gradients
+    (dist.allreduce_gradients), LDA frozen as in xvector_DPlda_pytorch.py:140-147."""
+    import torch.distributed as dist
+    import neuralplda_b200 as npl
+    from neuralplda_b200 import dist as ndist
+    stream = torch.cuda.current_stream()
+    res = {}
+
+    def sync_max(ms):
+        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm)
+
+    # ---- configs[3] ----
+    total = 50_000_000
+    lo, hi = ndist.shard_range(total, world, rank)
+    m = hi - lo
+    x1, x2, t = synth_on_device(m, 3000 + rank, kp["mean"].to(dev), dev)
+    model.process_group = True
+
+    def step3():
+        with torch.no_grad():
+            return model.softcdet(model(x1, x2), t)        # K1 + K2 + all-reduce of the 12 fp64 accumulators + finalize
+
+    for _ in range(2):
+        step3()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = sync_max(_event_time(step3, 5, stream))
+    loss3 = float(step3())
+    res["cfg3_strong"] = {"workload": "configs[3]: 50M synthetic trial pairs (materialised, 205 GB in total) sharded by contiguous "
+                                      "trial ranges, NeuralPlda score + softCdet with ONE NCCL all-reduce of the raw accumulators",
+                          "value": total / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "pairs_per_rank": m, "scaling": "strong",
+                          "gb_per_rank": m * 4096 / 1e9, "softcdet": loss3}
+    del x1, x2, t
+    torch.cuda.empty_cache()
+
+    # ---- configs[4] ----
+    class NCDP(NC):
+        loss = "crossentropy"
+        beta = [99.0]
+
+    total4 = 10_000_000
+    lo, hi = ndist.shard_range(total4, world, rank)
+    m4 = hi - lo
+    x1, x2, t = synth_on_device(m4, 4000 + rank, kp["mean"].to(dev), dev)
+    torch.manual_seed(1)
+    d = npl.DPlda(NCDP).to(dev)
+    sd = d.state_dict()
+    sd["centering_and_LDA.weight"].copy_(kp["W1"]); sd["centering_and_LDA.bias"].copy_(kp["b1"])
+    for p_ in (d.centering_and_LDA.weight, d.centering_and_LDA.bias):
+        p_.requires_grad_(False)                               # xvector_DPlda_pytorch.py:140-147
+    d.process_group = True
+
+    def step4():
+        d.zero_grad(set_to_none=True)
+        loss = d.loss(d(x1, x2), t)                            # BCE over ALL ranks' trials (accumulators all-reduced)
+        loss.backward()
+        ndist.allreduce_gradients(d)                           # NCCL sum of the 57 972 parameter gradients
+        return loss
+
+    for _ in range(2):
+        step4()
+    dist.barrier(); torch.cuda.synchronize()
+    ms4 = sync_max(_event_time(step4, 5, stream))
+    gnorm = float(torch.cat([p.grad.reshape(-1) for p in d.parameters() if p.grad is not None]).double().norm())
+    res["cfg4_dplda_train"] = {"workload": "configs[4]: DPlda 512-170 (LDA frozen), 10M synthetic trial pairs split over the ranks, "
+                                           "forward + BCE + backward + NCCL all-reduce of the parameter gradients",
+                               "value": total4 / (ms4 * 1e-3), "unit": "pairs/s", "ms_per_step": ms4, "pairs_per_rank": m4,
+                               "scaling": "strong", "bce": float(step4()), "grad_norm_after_allreduce": gnorm}
+    return res
 
 
 def train_leg(kp, dev, x1, x2, t):
@@ -388,12 +763,7 @@ def train_leg(kp, dev, x1, x2, t):
 
     n = x1.shape[0]
     out = {"pairs": n, "loss": "crossentropy", "api": "model(x1, x2) -> model.loss(...) -> .backward()"}
-    m = npl.NeuralPlda(NCX).to(dev)
-    sd = m.state_dict()
-    for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias", "b1"),
-                      ("centering_and_wccn_plda.weight", "W2"), ("centering_and_wccn_plda.bias", "b2"),
-                      ("P_sqrt", "P_sqrt"), ("Q", "Q")):
-        sd[name].copy_(kp[key])
+    m = load_kaldi_init(npl.NeuralPlda(NCX).to(dev), kp)
 
     def nstep():
         m.zero_grad(set_to_none=True)
@@ -441,14 +811,7 @@ def trial_list_leg(model, kp, dev):
     got = s[sub.to(dev)].cpu().double()
     worst = float(((got - ref).abs() / (1e-4 * torch.maximum(ref.abs(), ref.pow(2).mean().sqrt()))).max())
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record(stream)
-    for _ in range(reps):
-        full()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    ms = _event_time(full, 10, stream)
     ha, hb, hs = i1.pin_memory(), i2.pin_memory(), torch.empty(n, pin_memory=True)
 
     def e2e():
@@ -462,7 +825,7 @@ def trial_list_leg(model, kp, dev):
     for _ in range(5):
         e2e()
     dt = (time.perf_counter() - t0) / 5
-    # the same 10M trials as an enrol x test GRID (nplda_score_grid): no index pair per trial, one fp32 product
+    # the same 10M trials as an enrol x test GRID (nplda_score_grid): no index pair per trial
     er, tr = torch.arange(2500, device=dev), torch.arange(2500, 6500, device=dev)
 
     def grid_full():
@@ -476,12 +839,7 @@ def trial_list_leg(model, kp, dev):
     for name, fn in (("with_table_prepare", grid_full), ("rows_cached", lambda: model.forward_grid(t, er, tr)[0])):
         fn()
         torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(20):
-            fn()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        gms[name] = e0.elapsed_time(e1) / 20
+        gms[name] = _event_time(fn, 20, stream)
     hg = torch.empty(2500, 4000, pin_memory=True)
 
     def grid_e2e():
@@ -495,10 +853,9 @@ def trial_list_leg(model, kp, dev):
         grid_e2e()
     gdt = (time.perf_counter() - t0) / 5
     grid = {"workload": "configs[2] as an enrol x test grid: 2500 x 4000 over 6500 x-vectors, table prepare + one "
-                        "[2500,176] x [176,4000] fp32 grid product (nplda_score_grid) every step",
+                        "[2500,176] x [176,4000] grid product (nplda_score_grid) every step",
             "value": n / (gms["with_table_prepare"] * 1e-3), "unit": "trials/s", "ms_per_step": gms["with_table_prepare"],
             "ms_rows_cached": gms["rows_cached"], "value_rows_cached": n / (gms["rows_cached"] * 1e-3),
-            "fp32_tflops_rows_cached": 2 * 176 * n / (gms["rows_cached"] * 1e-3) / 1e12,
             "e2e": {"value": n / gdt, "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * n,
                     "api": "NeuralPlda.forward_grid, scores copied back to pinned host memory"},
             "bytes_per_trial": {"hbm_score": 4}, "parity_worst_over_bound_strided_sample": worst_g}
@@ -518,7 +875,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc", "f8"])
-    ap.add_argument("--skip-trial-list", action="store_true", help="skip the extra indexed trial-list measurement")
+    ap.add_argument("--skip-trial-list", action="store_true", help="skip the extra separately-labelled legs (N = 1)")
+    ap.add_argument("--skip-multi", action="store_true", help="skip the configs[3] / configs[4] legs (N > 1)")
+    ap.add_argument("--skip-sustained", action="store_true")
+    ap.add_argument("--skip-e2e-materialised", action="store_true")
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only; prints no bench line")

@@ -38,9 +38,14 @@ extern "C" {
 #define NPLDA_ERR_FORMAT (-6)         /* trial file rows with differing numbers of fields     */
 
 /* kernel selection for the score kernels */
-#define NPLDA_IMPL_AUTO 0   /* NPLDA_IMPL_TC when the shape allows, else SIMT */
+#define NPLDA_IMPL_AUTO 0   /* the tcgen05 kernel when the shape allows (NPLDA_IMPL_TC_BF16 arithmetic for the score-only
+                               entries -- the fastest, ~1e-5 of the fp32 reference; NPLDA_IMPL_TC arithmetic for the training
+                               forwards, whose activations feed the gradients), else SIMT */
 #define NPLDA_IMPL_SIMT 1   /* fp32 FFMA2 register-tiled kernel (any supported shape) */
-#define NPLDA_IMPL_TC 2     /* tcgen05 kernel, both layers as split bf16 (hi*hi + lo*hi + hi*lo); error if shape unsupported */
+#define NPLDA_IMPL_TC 2     /* tcgen05 kernel, both layers as split fp16 ("fp16x3": hi*hi + lo*hi + hi*lo, weights scaled into
+                               range at pack time; inputs outside fp16's range are detected on the device and the call is
+                               recomputed by the bf16x3 kernel on the same stream); error if shape unsupported */
+#define NPLDA_IMPL_TC_BF16 4 /* tcgen05 kernel, both layers as split bf16 (any fp32 range, ~8x the rounding error of fp16x3) */
 #define NPLDA_IMPL_TC_F8 3  /* tcgen05 kernel, layer 1 as fp16*fp16 + two e4m3*e4m3 correction products on the same
                                accumulator (same MAC count, 2/3 of the MMA instructions).  Inputs outside the range the
                                e4m3 terms cover (typical |x| in [2^-3, 2^8)) are detected on the device and the call is
@@ -145,7 +150,8 @@ int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const int64_t *i
  * The reference's callers hold a static x-vector table (the pickled dict,
  * xvector_NeuralPlda_pytorch.py:117) and index batches (sv_trials_loaders.py:418-426).
  * nplda_table_split converts the fp32 table ONCE into the tensor cores' operand format
- * (bf16 hi/lo, x = hi + lo + O(2^-17 |x|); nplda_split_bytes(n_rows, d_in) = n_rows * d_in * 4 bytes, 128-byte
+ * (fp16 hi/lo of x 2^kx, kx from the table's absolute maximum: x 2^kx = hi + lo + O(2^-22 |x|);
+ * nplda_split_bytes(n_rows, d_in) = n_rows * d_in * 4 + 128 bytes, 128-byte aligned, d_in % 32 == 0, rows 16-byte
  * aligned); nplda_score_fwd_split then scores trials (table[idx1[k]], table[idx2[k]]): TMA row gather
  * (tile::gather4) straight into the shared-memory A operand, tcgen05.mma.cta_group::2 over CTA pairs, no
  * conversion work per call.  Replaces load_xvec_trials_from_numbatch (sv_trials_loaders.py:418-426) +
@@ -347,6 +353,11 @@ int nplda_trials_col_float(const nplda_trials *t, int col, int64_t first_row, fl
 int nplda_scores_write(const char *path, const nplda_trials *t, int64_t first_row, int ncols_keep,
                        const float *scores, const char *header_line);
 int nplda_format_f32(float v, char *out24);   /* str(np.float32(v)) into out24 (not NUL-terminated); returns the length */
+
+/* Test hook: forces the pieces of the score backward for A/B comparisons -- weight-gradient contraction (gemm),
+ * activations from the tensor-core forward (emit), dL/du pass (du): 0 = automatic (the default), 1 = the all-fp32
+ * piece, 2 = the tensor-core piece.  Process-wide; production code never calls it. */
+void nplda_debug_backward_paths(int gemm, int emit, int du);
 
 #ifdef __cplusplus
 }

@@ -14,10 +14,10 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnplda.so")
+LIB_PATH = os.environ.get("NPLDA_LIB") or os.path.join(_HERE, "libnplda.so")    # NPLDA_LIB: an experiment build (csrc/Makefile)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8 = 0, 1, 2, 3
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8, IMPL_TC_BF16 = 0, 1, 2, 3, 4
 LOSS_SOFTCDET, LOSS_CROSSENTROPY = 0, 1
 PACK_MIXED, PACK_EPOCH_ODD, PACK_PAIR, PREPARE_IF_CHANGED = 1, 2, 4, 1
 ERR_UNSUPPORTED_DIM = -2
@@ -87,6 +87,7 @@ SIGNATURES = {
     "nplda_trials_col_float": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
     "nplda_scores_write": (c_int, [ctypes.c_char_p, c_vp, c_i64, c_int, c_vp, ctypes.c_char_p]),
     "nplda_format_f32": (c_int, [ctypes.c_float, ctypes.c_char_p]),
+    "nplda_debug_backward_paths": (None, [c_int, c_int, c_int]),
     "nplda_host_scratch_bytes": (c_i64, [c_i64, c_int]),
     "nplda_score_fwd_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_i64,
                                      c_int, c_int]),

@@ -70,7 +70,8 @@ static int score_dispatch(bool dplda, const float *x1, const float *x2, const in
     if (n < 0 || !pack || (n > 0 && (!x1 || !scores))) return NPLDA_ERR_BAD_ARG;
     if (indexed && (!i1 || !i2 || !bad_flag || n_rows <= 0)) return NPLDA_ERR_BAD_ARG;
     if (!indexed && n > 0 && !x2) return NPLDA_ERR_BAD_ARG;
-    if (impl != NPLDA_IMPL_AUTO && impl != NPLDA_IMPL_SIMT && impl != NPLDA_IMPL_TC && impl != NPLDA_IMPL_TC_F8)
+    if (impl != NPLDA_IMPL_AUTO && impl != NPLDA_IMPL_SIMT && impl != NPLDA_IMPL_TC && impl != NPLDA_IMPL_TC_F8 &&
+        impl != NPLDA_IMPL_TC_BF16)
         return NPLDA_ERR_BAD_ARG;
     if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n == 0) return NPLDA_OK;
@@ -78,10 +79,11 @@ static int score_dispatch(bool dplda, const float *x1, const float *x2, const in
     cudaStream_t st = (cudaStream_t)stream;
     const bool aligned = (((uintptr_t)x1 & 15) == 0) && (indexed || ((uintptr_t)x2 & 15) == 0);
     const bool tc_ok = tc_shape_ok(dplda, L, indexed) && aligned;
-    if ((impl == NPLDA_IMPL_TC || impl == NPLDA_IMPL_TC_F8) && !tc_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
-    if (impl == NPLDA_IMPL_TC || impl == NPLDA_IMPL_TC_F8 || (impl == NPLDA_IMPL_AUTO && tc_ok))
+    const bool want_tc = impl == NPLDA_IMPL_TC || impl == NPLDA_IMPL_TC_F8 || impl == NPLDA_IMPL_TC_BF16;
+    if (want_tc && !tc_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (want_tc || (impl == NPLDA_IMPL_AUTO && tc_ok))
         return score_tc(dplda, x1, x2, i1, i2, n_rows, bad_flag, n, L, (const char *)pack, scores,
-                        impl == NPLDA_IMPL_TC_F8 ? 1 : 0, st);
+                        impl == NPLDA_IMPL_TC_F8 ? 1 : (impl == NPLDA_IMPL_TC ? 2 : 0), st);   // AUTO: bf16x3 (fastest)
     return score_simt(dplda, x1, x2, i1, i2, n_rows, bad_flag, n, L, (const char *)pack, scores, st);
 }
 
@@ -130,7 +132,7 @@ extern "C" int nplda_score_fwd_train(const float *x1, const float *x2, int64_t n
     if (n == 0) return NPLDA_OK;
     const PackLayout L = make_pack_layout(d_in, d1, d2);
     if (!tc_shape_ok(false, L, false) || (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)act) & 15) != 0) return NPLDA_ERR_UNSUPPORTED_DIM;
-    return score_tc(false, x1, x2, nullptr, nullptr, 0, nullptr, n, L, (const char *)pack, scores, 0, (cudaStream_t)stream,
+    return score_tc(false, x1, x2, nullptr, nullptr, 0, nullptr, n, L, (const char *)pack, scores, 2, (cudaStream_t)stream,
                     act, act + 2 * n * ACT_LD, n);
 }
 
@@ -178,7 +180,7 @@ extern "C" int dplda_score_fwd_indexed(const float *table, int64_t n_rows, const
 extern "C" int64_t nplda_split_bytes(int64_t n_rows, int d_in) {
     if (n_rows < 0 || d_in <= 0) return NPLDA_ERR_BAD_ARG;
     if (d_in % 32 != 0) return NPLDA_ERR_UNSUPPORTED_DIM;
-    return n_rows * (int64_t)d_in * 4;
+    return n_rows * (int64_t)d_in * 4 + 128;     // rows + header {max|x|, 2^kx, 2^-kx}
 }
 
 extern "C" int nplda_table_split(const float *table, int64_t n_rows, int d_in, void *split, void *stream) {

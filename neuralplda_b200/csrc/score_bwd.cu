@@ -11,6 +11,7 @@
 //      done by a split-row SGEMM (gemm_tn) that adds its tiles atomically.
 // All gradient outputs are ADDED INTO.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -604,11 +605,14 @@ static int64_t workspace_bytes(int64_t n, int d_in, int d1, int d2) {
     return make_pack(d_in, d1, d2).total * 4 + 4 * 2 * cap * NP * 4 + 1024 + fwd_pack_room(d_in, d1, d2);
 }
 
-// C[M,N] += A^T B: the tcgen05 bf16x3 kernel for batches worth its launch (NPLDA_BWD_GEMM=simt|tc forces one)
+// Path selection of the backward, for A/B tests (nplda_debug_backward_paths): 0 = automatic, 1 = the fp32 piece,
+// 2 = the tensor-core piece.  Process-wide; the production default is automatic and nothing reads the environment.
+static std::atomic<int> g_force_gemm{0}, g_force_emit{0}, g_force_du{0};
+
+// C[M,N] += A^T B: the tcgen05 bf16x3 kernel for batches worth its launch
 static int gemm_tn_auto(const float *A, int lda, int M, const float *B, int ldb, int N, int64_t R, float *C,
                         int ldc, cudaStream_t st) {
-    const char *e = getenv("NPLDA_BWD_GEMM");
-    const int forced = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0));
+    const int forced = g_force_gemm.load(std::memory_order_relaxed);
     const bool tc_ok = M <= 176;
     if (tc_ok && (forced == 2 || (forced == 0 && R >= 8192))) return gemm_tn_tc(B, ldb, N, A, lda, M, R, C, ldc, st);
     return gemm_tn(A, lda, M, B, ldb, N, R, C, ldc, st);
@@ -641,12 +645,12 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
 
     const bool vec = (d_in % 4 == 0) && (((uintptr_t)x1 & 15) == 0) && (((uintptr_t)x2 & 15) == 0);
     // NeuralPlda at the tensor-core kernel's shapes and batches worth the extra launches: layer 1 and layer 2 are
-    // not recomputed in fp32 here but emitted by the tcgen05 forward kernel (NPLDA_BWD_EMIT=0|1 forces a side)
+    // not recomputed in fp32 here but emitted by the tcgen05 forward kernel (nplda_debug_backward_paths forces a side)
     const PackLayout FL = make_pack_layout(d_in, d1, d2);
     bool pre = false;
     if (vec && (DPLDA ? tc_dplda_ok(FL) : tc_shape_ok(false, FL, false)) && FL.total <= fwd_pack_room(d_in, d1, d2)) {
-        const char *e = getenv("NPLDA_BWD_EMIT");
-        pre = e ? e[0] == '1' : n >= 64;
+        const int f = g_force_emit.load(std::memory_order_relaxed);
+        pre = f ? f == 2 : n >= 64;
         if (act) pre = true;               // activations saved by the training forward: nothing to emit here
     }
     if (act && !pre) return NPLDA_ERR_UNSUPPORTED_DIM;
@@ -660,14 +664,14 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
     auto kern = pre ? bwd_tile_kernel<DPLDA, true, true>
                     : (vec ? bwd_tile_kernel<DPLDA, true, false> : bwd_tile_kernel<DPLDA, false, false>);
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));
-    // NeuralPlda with EMIT: dL/du = dL/dy . W2 also on the tensor cores (NPLDA_BWD_DU=0|1 forces a side): the tile
+    // NeuralPlda with EMIT: dL/du = dL/dy . W2 also on the tensor cores (nplda_debug_backward_paths forces a side): the tile
     // kernel runs as two elementwise phases around a rows-in / rows-out pass of the tcgen05 kernel over the DY rows
     bool du_tc = false;
     uint8_t *duimg = (uint8_t *)(fpack + (FL.total + 255) / 256 * 256);
     float *zeros = (float *)(duimg + (tc_rows_image_bytes(NP) + 255) / 256 * 256);
     if (pre && !DPLDA && d2 <= NP) {
-        const char *e = getenv("NPLDA_BWD_DU");
-        du_tc = e ? e[0] == '1' : true;
+        const int f = g_force_du.load(std::memory_order_relaxed);
+        du_tc = f ? f == 2 : true;
     }
     auto kern1 = bwd_tile_kernel<false, true, true, 1>;
     auto kern2 = bwd_tile_kernel<false, true, true, 2>;
@@ -698,7 +702,7 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
             a.Apre = DA; a.Ypre = G; a.Zpre = PMU; a.pre_cap = cap;
         }
         if (pre && !act && !DPLDA) {
-            int rc = score_tc(false, a.x1, a.x2, nullptr, nullptr, 0, nullptr, nc, FL, fpack, nullptr, 0, st, DA, G, cap);
+            int rc = score_tc(false, a.x1, a.x2, nullptr, nullptr, 0, nullptr, nc, FL, fpack, nullptr, 2, st, DA, G, cap);   // fp16x3 activations
             if (rc != NPLDA_OK) return rc;
         }
         if (pre && !act && DPLDA) {         // a and R u (image 2), then Pm u (image 1)
@@ -802,4 +806,10 @@ extern "C" int dplda_score_bwd(const float *x1, const float *x2, int64_t n, int 
     return bwd::run<true>(x1, x2, n, d_in, d1, d1, W1, b1, nullptr, nullptr, nullptr, nullptr, w_lr, dscores,
                           dW1, db1, nullptr, nullptr, nullptr, nullptr, dw_lr, dc_lr, dx1, dx2, workspace,
                           workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" void nplda_debug_backward_paths(int gemm, int emit, int du) {
+    bwd::g_force_gemm.store(gemm < 0 || gemm > 2 ? 0 : gemm, std::memory_order_relaxed);
+    bwd::g_force_emit.store(emit < 0 || emit > 2 ? 0 : emit, std::memory_order_relaxed);
+    bwd::g_force_du.store(du < 0 || du > 2 ? 0 : du, std::memory_order_relaxed);
 }

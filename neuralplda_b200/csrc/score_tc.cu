@@ -1,9 +1,12 @@
 // K1 (tensor cores): fused pairwise score kernel on tcgen05 / TMEM.
 //
-// Precision: every fp32 operand is split x = hi + lo into two bf16 values and each
-// product is evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM
-// ("bf16x3"; the dropped lo*lo term and the split residuals are O(2^-17)), which keeps
-// the scores within ~1e-5 of the fp32 reference (numerics).
+// Precision: every fp32 operand is split x = hi + lo into two 16-bit floats and each product is evaluated as
+// hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM.  MODE 2 ("fp16x3", the default): fp16 halves, 11-bit
+// significands, residual and dropped lo*lo term O(2^-22) -- scores within ~1e-6 of the fp64 value and training
+// activations good enough for gradients at fp32-autograd accuracy (tools/grad_diag.py: 2e-6 against 1e-4 for bf16);
+// the weights are scaled into fp16's range by a power of two at pack time, inputs are taken as they are and a range
+// guard (|x| >= 2048, |a| >= 32768, NaN) re-runs the call in MODE 0 on the same stream.  MODE 0 ("bf16x3"): bf16 halves,
+// O(2^-17), any fp32 range -- the fallback and the kernel of the backward's rows pass, whose inputs are tiny.
 //
 // One persistent CTA per SM, warp-specialised, tiles of 64 trial pairs = 128 rows; in every
 // 16-row group rows 0-7 are side 0 and rows 8-15 side 1 of the same 8 pairs:
@@ -83,7 +86,8 @@ struct Args {
     const uint8_t *w1img, *w2img;   // MODE 1: w1img is the fp16 + 2 x e4m3 image
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
     const float *hdr;       // MODE 1: hdr[0] = 2^-(9 + gw), the scale that undoes the weight pre-scaling
-    int *guard;             // MODE 1: guard[0] set when an input leaves the range the e4m3 terms cover; MODE 0 with
+    const float *hdr16;     // MODE 2: {2^gw1, 2^-gw1, 2^gw2, 2^-gw2, ...}: the fp16 images hold W1 2^gw1 and W2 2^gw2
+    int *guard;             // MODE 1 / 2: guard[0] set when an input leaves the range the mode covers; MODE 0 with
                             //         guard != nullptr: run only if guard[0] is set (fallback pass), then clear it
 
     float *scores;
@@ -206,10 +210,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t IDESC = make_idesc_bf16(128, NPAD);
     constexpr uint32_t IDESC_F16 = make_idesc_fmt(0, 0, 128, NPAD), IDESC_E4M3 = make_idesc_fmt(0, 0, 128, NPAD);
-    const float s1 = MODE == 1 ? g.hdr[0] : 1.f;
+    // MODE 2 takes x 2^4: the lo halves of inputs down to |x| ~ 2^-7 stay normal fp16 numbers, inputs up to 2048 fit
+    constexpr float XS = 16.f;
+    const float s1 = MODE == 1 ? g.hdr[0] : (MODE == 2 ? g.hdr16[1] * (1.f / XS) : 1.f);
+    const float c2 = MODE == 2 ? g.hdr16[3] : 1.f;         // undoes the layer-2 weight scale
     const bool img_ok = MODE != 1 || g.hdr[2] != 0.f;      // mixed image built by this pack (NPLDA_PACK_MIXED)?
+    constexpr uint32_t IDESC_L1 = MODE == 2 ? make_idesc_f16(128, NPAD) : make_idesc_bf16(128, NPAD);
+    constexpr uint32_t IDESC_L2 = IDESC_L1;                // MODE 1: layer 2 is bf16x3
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ptime = PROF ? clock64() : 0;
 
     if (warp < EPI_WARPS) {
@@ -245,16 +253,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             }
             uint32_t hi, lo;
             const int kc = c0 >> 3;
-            split_bf16x2(a00, a01, hi, lo);
+            auto split2 = [](float x, float y, uint32_t &h, uint32_t &l) {
+                if (MODE == 2) split_f16x2(x, y, h, l); else split_bf16x2(x, y, h, l);
+            };
+            split2(a00, a01, hi, lo);
             *reinterpret_cast<uint32_t *>(u0 + kc * KCH_U) = hi;
             *reinterpret_cast<uint32_t *>(u0 + U_HALF + kc * KCH_U) = lo;
-            split_bf16x2(a02, a03, hi, lo);
+            split2(a02, a03, hi, lo);
             *reinterpret_cast<uint32_t *>(u0 + (kc + 1) * KCH_U) = hi;
             *reinterpret_cast<uint32_t *>(u0 + U_HALF + (kc + 1) * KCH_U) = lo;
-            split_bf16x2(a10, a11, hi, lo);
+            split2(a10, a11, hi, lo);
             *reinterpret_cast<uint32_t *>(u1 + kc * KCH_U) = hi;
             *reinterpret_cast<uint32_t *>(u1 + U_HALF + kc * KCH_U) = lo;
-            split_bf16x2(a12, a13, hi, lo);
+            split2(a12, a13, hi, lo);
             *reinterpret_cast<uint32_t *>(u1 + (kc + 1) * KCH_U) = hi;
             *reinterpret_cast<uint32_t *>(u1 + U_HALF + (kc + 1) * KCH_U) = lo;
         };
@@ -316,8 +327,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             float ss0 = ss[0] + ss[1], ss1 = ss[2] + ss[3];
             ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
             ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
-            const float r0 = 1.f / fmaxf(sqrtf(ss0), 1e-12f);      // F.normalize eps (models.py:368)
-            const float r1 = 1.f / fmaxf(sqrtf(ss1), 1e-12f);
+            const float r0 = c2 / fmaxf(sqrtf(ss0), 1e-12f);       // F.normalize eps (models.py:368) (x the layer-2 scale)
+            const float r1 = c2 / fmaxf(sqrtf(ss1), 1e-12f);
+            if (MODE == 2) {
+                // fp16 range guard for U: |a|_2 < 32768 bounds every element; NaN / inf fail the comparison too
+                const int64_t pe = (blockIdx.x + i * gridDim.x) * TP + pl;
+                if (!(ss0 < 1.0e9f && ss1 < 1.0e9f) && pe < g.n) *reinterpret_cast<volatile int *>(g.guard) = 1;
+            }
             fence_proxy_async();      // U is read by tcgen05.mma (async proxy)
             tc_fence_before();        // our TMEM reads of D are done before Y overwrites it
             mbar_arrive(u_full);
@@ -379,10 +395,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             // stages and each checks the values it converted (its pair's two rows, 8 columns of every other
             // stage).  The e4m3 terms need typical |x| in about [2^-3, 2^8); outside that, the call is flagged and
             // the bf16x3 pass that follows on the stream recomputes it.
-            const bool tile_end = MODE == 1 && ++stage_in_tile == g.nst1;
+            const bool tile_end = MODE != 0 && ++stage_in_tile == g.nst1;
             auto guard_check = [&]() {
                 const int64_t pr = (blockIdx.x + tile_i * gridDim.x) * TP + pl;
-                if (pr < g.n && (amax < 0.25f || amax >= 256.f || !img_ok)) *reinterpret_cast<volatile int *>(g.guard) = 1;
+                const bool out = MODE == 1 ? (amax < 0.25f || amax >= 256.f || !img_ok) : !(amax < 2048.f);
+                if (pr < g.n && out) *reinterpret_cast<volatile int *>(g.guard) = 1;
                 amax = 0.f; stage_in_tile = 0; ++tile_i;
             };
             // mbarrier parity waits are only unambiguous for a waiter that observes EVERY phase of a
@@ -427,6 +444,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                 lo[2] = pack_e4m3x4(l[8], l[9], l[10], l[11]); lo[3] = pack_e4m3x4(l[12], l[13], l[14], l[15]);
                 lo[4] = pack_e4m3x4(v[0], v[1], v[2], v[3]); lo[5] = pack_e4m3x4(v[4], v[5], v[6], v[7]);
                 lo[6] = pack_e4m3x4(v[8], v[9], v[10], v[11]); lo[7] = pack_e4m3x4(v[12], v[13], v[14], v[15]);
+            } else if (MODE == 2) {
+                split_f16x2(a0.x * XS, a0.y * XS, hi[0], lo[0]); split_f16x2(a0.z * XS, a0.w * XS, hi[1], lo[1]);
+                split_f16x2(b0.x * XS, b0.y * XS, hi[2], lo[2]); split_f16x2(b0.z * XS, b0.w * XS, hi[3], lo[3]);
+                split_f16x2(a1.x * XS, a1.y * XS, hi[4], lo[4]); split_f16x2(a1.z * XS, a1.w * XS, hi[5], lo[5]);
+                split_f16x2(b1.x * XS, b1.y * XS, hi[6], lo[6]); split_f16x2(b1.z * XS, b1.w * XS, hi[7], lo[7]);
+                // range guard on the fp32 inputs (a NaN must not be swallowed by fmaxf: it reaches U and fails there)
+                const float m0 = fmaxf(fmaxf(fabsf(a0.x), fabsf(a0.y)), fmaxf(fabsf(a0.z), fabsf(a0.w)));
+                const float m1 = fmaxf(fmaxf(fabsf(a1.x), fabsf(a1.y)), fmaxf(fabsf(a1.z), fabsf(a1.w)));
+                const float m2 = fmaxf(fmaxf(fabsf(b0.x), fabsf(b0.y)), fmaxf(fabsf(b0.z), fabsf(b0.w)));
+                const float m3 = fmaxf(fmaxf(fabsf(b1.x), fabsf(b1.y)), fmaxf(fabsf(b1.z), fabsf(b1.w)));
+                amax = fmaxf(amax, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
             } else {
                 split_bf16x2(a0.x, a0.y, hi[0], lo[0]); split_bf16x2(a0.z, a0.w, hi[1], lo[1]);
                 split_bf16x2(b0.x, b0.y, hi[2], lo[2]); split_bf16x2(b0.z, b0.w, hi[3], lo[3]);
@@ -497,9 +525,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                             mma_ts(dcol, acol, bhi0, IDESC_F16, s != 0);
                             mma_ts(dcol, acol + 8, bhi0 + ((2 * KCH_B) >> 4), IDESC_F16, 1);
                         } else {
-                            mma_ts(dcol, acol, bhi0, IDESC, s != 0);
-                            mma_ts(dcol, acol + 16, bhi0, IDESC, 1);
-                            mma_ts(dcol, acol, bhi0 + ((2 * KCH_B) >> 4), IDESC, 1);
+                            mma_ts(dcol, acol, bhi0, IDESC_L1, s != 0);
+                            mma_ts(dcol, acol + 16, bhi0, IDESC_L1, 1);
+                            mma_ts(dcol, acol, bhi0 + ((2 * KCH_B) >> 4), IDESC_L1, 1);
                         }
                     }
                     __syncwarp();
@@ -520,9 +548,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                                 mma_f8_ts(dcol, acol + 16, bhi1, IDESC_E4M3, 1);
                                 mma_f8_ts(dcol, acol + 24, bhi1 + ((2 * KCH_B) >> 4), IDESC_E4M3, 1);
                             } else {
-                                mma_ts(dcol, acol + 8, bhi1, IDESC, 1);
-                                mma_ts(dcol, acol + 24, bhi1, IDESC, 1);
-                                mma_ts(dcol, acol + 8, bhi1 + ((2 * KCH_B) >> 4), IDESC, 1);
+                                mma_ts(dcol, acol + 8, bhi1, IDESC_L1, 1);
+                                mma_ts(dcol, acol + 24, bhi1, IDESC_L1, 1);
+                                mma_ts(dcol, acol + 8, bhi1 + ((2 * KCH_B) >> 4), IDESC_L1, 1);
                             }
                         }
                         mma_commit(&a_empty[ra.stage]);
@@ -566,9 +594,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                         const uint64_t uhi0 = make_smem_desc(u_base + ks * 2 * KCH_U, KCH_U, 128);
                         const uint64_t ulo0 = make_smem_desc(u_base + U_HALF + ks * 2 * KCH_U, KCH_U, 128);
                         if (elect_one() && !skip_mma) {
-                            mma_ss(dcol, uhi0, bhi0, IDESC, ks != 0);
-                            mma_ss(dcol, ulo0, bhi0, IDESC, 1);
-                            mma_ss(dcol, uhi0, bhi0 + ((2 * KCH_B) >> 4), IDESC, 1);
+                            mma_ss(dcol, uhi0, bhi0, IDESC_L2, ks != 0);
+                            mma_ss(dcol, ulo0, bhi0, IDESC_L2, 1);
+                            mma_ss(dcol, uhi0, bhi0 + ((2 * KCH_B) >> 4), IDESC_L2, 1);
                         }
                         __syncwarp();
                         Ring nb = rb;
@@ -580,9 +608,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                             if (nst == 2 && !skip_mma) {
                                 const uint64_t bhi1 = bhi0 + (B_STEP >> 4);
                                 const uint64_t uhi1 = uhi0 + ((2 * KCH_U) >> 4), ulo1 = ulo0 + ((2 * KCH_U) >> 4);
-                                mma_ss(dcol, uhi1, bhi1, IDESC, 1);
-                                mma_ss(dcol, ulo1, bhi1, IDESC, 1);
-                                mma_ss(dcol, uhi1, bhi1 + ((2 * KCH_B) >> 4), IDESC, 1);
+                                mma_ss(dcol, uhi1, bhi1, IDESC_L2, 1);
+                                mma_ss(dcol, ulo1, bhi1, IDESC_L2, 1);
+                                mma_ss(dcol, uhi1, bhi1 + ((2 * KCH_B) >> 4), IDESC_L2, 1);
                             }
                             mma_commit(&b_empty[rb.stage]);
                         }
@@ -686,11 +714,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
 // sym: pack W + W^T (square W) -- DPlda's Pm = Wb + Wb^T and R = Ww + Ww^T.
 // sn, sk: element strides of W along n and k (0, 0 = row-major [N][K]).
 __global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ksteps, uint8_t *__restrict__ img,
-                               float *__restrict__ hdr_invalidate, int sym = 0, int64_t sn = 0, int64_t sk = 0) {
+                               float *__restrict__ hdr_invalidate, int sym = 0, int64_t sn = 0, int64_t sk = 0,
+                               uint8_t *__restrict__ img16 = nullptr, const float *__restrict__ scale16 = nullptr) {
     if (sn == 0 && sk == 0) { sn = K; sk = 1; }
     // hdr[2] = 0 marks the MODE 1 image as not built (pack flag NPLDA_PACK_MIXED off): the mixed kernel then flags
     // every tile for the bf16x3 pass behind it
     if (hdr_invalidate && blockIdx.x == 0 && threadIdx.x == 0) { hdr_invalidate[0] = 1.f; hdr_invalidate[1] = 1.f; hdr_invalidate[2] = 0.f; }
+    const float sc = img16 ? scale16[0] : 1.f;       // fp16 image (MODE 2): W 2^gw, same layout
     const int64_t total = (int64_t)ksteps * 2 * NPAD * 8;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int kk = (int)(e & 7);
@@ -702,10 +732,49 @@ __global__ void tc_pack_kernel(const float *__restrict__ W, int N, int K, int ks
         if (sym && n < N && k < K) w += W[k * sn + n * sk];
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        uint8_t *st = img + (size_t)s * B_STEP;
-        const size_t off = (size_t)c * KCH_B + (n >> 3) * 128 + (n & 7) * 16 + kk * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(st + off) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(st + 2 * KCH_B + off) = lo;
+        const size_t off = (size_t)s * B_STEP + (size_t)c * KCH_B + (n >> 3) * 128 + (n & 7) * 16 + kk * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(img + off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(img + 2 * KCH_B + off) = lo;
+        if (img16) {
+            const float ws = w * sc;
+            const __half h16 = __float2half_rn(ws);
+            *reinterpret_cast<__half *>(img16 + off) = h16;
+            *reinterpret_cast<__half *>(img16 + 2 * KCH_B + off) = __float2half_rn(ws - __half2float(h16));
+        }
+    }
+}
+
+// Power-of-two scales of the fp16 weight images and the bound the pre-split kernel scales its layer-1 output with
+// (one launch, two blocks):  [0] 2^gw1, [1] 2^-gw1 (max|W1| 2^gw1 in [8192, 16384)), [2] 2^gw2, [3] 2^-gw2,
+// [4] max_j sum_k |W1[j][k]|, [5] max|b1|.
+__global__ void __launch_bounds__(1024) tc_scales_kernel(const float *__restrict__ W1, int n1, int k1, const float *__restrict__ b1,
+                                                         const float *__restrict__ W2, int n2, int k2, float *__restrict__ hdr,
+                                                         float headroom2 = 1.f) {
+    __shared__ float red[32], red2[32];
+    const float *W = blockIdx.x == 0 ? W1 : W2;
+    const int N = blockIdx.x == 0 ? n1 : n2, K = blockIdx.x == 0 ? k1 : k2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float m = 0.f, l1 = 0.f;
+    for (int r = warp; r < N; r += 32) {                 // one warp per weight row
+        float sum = 0.f;
+        for (int k = lane; k < K; k += 32) { const float v = fabsf(W[(int64_t)r * K + k]); m = fmaxf(m, v); sum += v; }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        l1 = fmaxf(l1, sum);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) { red[warp] = m; red2[warp] = l1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { m = fmaxf(m, red[w]); l1 = fmaxf(l1, red2[w]); }
+        const float sc = pow2_scale_to_2p13(blockIdx.x == 1 ? m * headroom2 : m);   // headroom2: images built from sums of entries
+        hdr[2 * blockIdx.x] = sc;
+        hdr[2 * blockIdx.x + 1] = 1.f / sc;
+        if (blockIdx.x == 0) {
+            float bm = 0.f;
+            for (int j = 0; j < n1; ++j) bm = fmaxf(bm, fabsf(b1[j]));
+            hdr[4] = l1 * 1.0001f;                     // the sums above are rounded: keep the bound a bound
+            hdr[5] = bm;
+        }
     }
 }
 
@@ -802,11 +871,34 @@ static bool tc_dims_ok(int d_in, int d1, int d2) {
     return d_in % tcg::KST == 0 && d_in >= tcg::KST && d1 <= tcg::NPAD && d2 <= tcg::NPAD && d1 >= 1 && d2 >= 1;
 }
 
+// tc area: [bf16 W1][bf16 W2][mixed W1 (MODE 1) | DPlda images 1, 2][hdr (MODE 1)][fp16 W1][fp16 W2][hdr16][DPlda fp16
+// images 1, 2], 256-aligned
+static int64_t al256(int64_t v) { return (v + 255) / 256 * 256; }
+struct TcArea {
+    int64_t img1, img2, img1m, hdr, img1h, img2h, hdr16, sq16, total;
+};
+static TcArea tc_area(int d_in, int d1) {
+    TcArea a;
+    const int64_t b1 = al256(tcg::image_bytes(d_in / 16)), b2 = al256(tcg::image_bytes(round_up(d1, 16) / 16));
+    a.img1 = 0;
+    a.img2 = a.img1 + b1;
+    a.img1m = a.img2 + b2;
+    a.hdr = a.img1m + al256(tcg::mixed_image_bytes(d_in));
+    a.img1h = a.hdr + tcg::HDR_BYTES;
+    a.img2h = a.img1h + b1;
+    a.hdr16 = a.img2h + b2;
+    a.sq16 = a.hdr16 + 256;          // DPlda: fp16 images 1 (Pm) and 2 (R); image 0 (Ww) sits at img2h
+    a.total = a.sq16 + 2 * b2;
+    return a;
+}
+
 int64_t tc_image_bytes(int d_in, int d1, int d2) {
     if (!tc_dims_ok(d_in, d1, d2)) return 0;
-    return tcg::image_bytes(d_in / 16) + tcg::image_bytes(round_up(d1, 16) / 16) + 512 + tcg::mixed_image_bytes(d_in) +
-           tcg::HDR_BYTES + 256;
+    return tc_area(d_in, d1).total;
 }
+
+// {2^gw1, 2^-gw1, 2^gw2, 2^-gw2, max_j ||W1_j||_1, max|b1|} of a NeuralPlda pack (score_tcx.cu reads it too)
+const float *tc_hdr16(const PackLayout &L, const char *pack) { return (const float *)(pack + L.tc + tc_area(L.d_in, L.d1).hdr16); }
 
 bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed) {
     return !dplda && !indexed && tc_dims_ok(L.d_in, L.d1, L.d2) && L.tc_bytes > 0;
@@ -814,16 +906,20 @@ bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed) {
 
 int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float *b2, const float *p_sqrt,
                   const float *q, const PackLayout &L, char *pack, int flags, cudaStream_t st) {
-    (void)b1; (void)b2; (void)p_sqrt; (void)q;   // the fp32 padded vectors of the SIMT pack are shared
+    (void)b2; (void)p_sqrt; (void)q;   // the fp32 padded vectors of the SIMT pack are shared
     if (!tc_dims_ok(L.d_in, L.d1, L.d2)) return NPLDA_OK;
-    uint8_t *img1 = (uint8_t *)pack + L.tc;
-    uint8_t *img2 = img1 + (tcg::image_bytes(L.d_in / 16) + 255) / 256 * 256;
-    uint8_t *img1m = img2 + (tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256;
-    float *hdr = (float *)(img1m + tcg::mixed_image_bytes(L.d_in));
+    const TcArea A = tc_area(L.d_in, L.d1);
+    uint8_t *base = (uint8_t *)pack + L.tc;
+    uint8_t *img1 = base + A.img1, *img2 = base + A.img2, *img1m = base + A.img1m;
+    float *hdr = (float *)(base + A.hdr), *hdr16 = (float *)(base + A.hdr16);
     const bool mixed = (flags & NPLDA_PACK_MIXED) != 0;
-    tcg::tc_pack_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / 16, img1, mixed ? nullptr : hdr);
+    tcg::tc_scales_kernel<<<2, 1024, 0, st>>>(W1, L.d1, L.d_in, b1, W2, L.d2, L.d1, hdr16);
     NPLDA_LAUNCH_CHECK();
-    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(W2, L.d2, L.d1, round_up(L.d1, 16) / 16, img2, nullptr);
+    tcg::tc_pack_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / 16, img1, mixed ? nullptr : hdr, 0, 0, 0,
+                                                        base + A.img1h, hdr16);
+    NPLDA_LAUNCH_CHECK();
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(W2, L.d2, L.d1, round_up(L.d1, 16) / 16, img2, nullptr, 0, 0, 0,
+                                                    base + A.img2h, hdr16 + 2);
     NPLDA_LAUNCH_CHECK();
     if (!mixed) return NPLDA_OK;
     tcg::tc_absmax_kernel<<<1, 1024, 0, st>>>(W1, (int64_t)L.d1 * L.d_in, hdr);
@@ -837,12 +933,18 @@ int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float
 // NeuralPlda, "layer 2" = one of three square matrices applied to the un-normalised a (the length norm commutes):
 // image 0 = Ww, image 1 = Pm = Wb + Wb^T, image 2 = R = Ww + Ww^T (images 1 and 2 live in the mixed-image area).
 static uint8_t *dplda_image(const PackLayout &L, const char *pack, int which) {
-    uint8_t *img1 = (uint8_t *)pack + L.tc;
-    uint8_t *img2 = img1 + (tcg::image_bytes(L.d_in / 16) + 255) / 256 * 256;
-    if (which == 0) return img2;
-    const int64_t sq = (tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256;
-    uint8_t *area = img2 + sq;
-    return area + (which - 1) * sq;
+    const TcArea A = tc_area(L.d_in, L.d1);
+    uint8_t *base = (uint8_t *)pack + L.tc;
+    if (which == 0) return base + A.img2;
+    const int64_t sq = al256(tcg::image_bytes(round_up(L.d1, 16) / 16));
+    return base + A.img1m + (which - 1) * sq;
+}
+
+static uint8_t *dplda_image16(const PackLayout &L, const char *pack, int which) {
+    const TcArea A = tc_area(L.d_in, L.d1);
+    uint8_t *base = (uint8_t *)pack + L.tc;
+    if (which == 0) return base + A.img2h;
+    return base + A.sq16 + (which - 1) * al256(tcg::image_bytes(round_up(L.d1, 16) / 16));
 }
 
 bool tc_dplda_ok(const PackLayout &L) {
@@ -850,18 +952,28 @@ bool tc_dplda_ok(const PackLayout &L) {
            2 * ((tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256) <= tcg::mixed_image_bytes(L.d_in);
 }
 
-int tc_pack_dplda(const float *W1, const float *, const float *w_lr, const float *, const PackLayout &L, char *pack,
+int tc_pack_dplda(const float *W1, const float *b1, const float *w_lr, const float *, const PackLayout &L, char *pack,
                   cudaStream_t st) {
     if (!tc_dplda_ok(L)) return NPLDA_OK;
     const int ks2 = round_up(L.d1, 16) / 16;
     const float *Wb = w_lr, *Ww = w_lr + (int64_t)L.d1 * L.d1;          // cat order of models.py:487
-    tcg::tc_pack_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / 16, (uint8_t *)pack + L.tc, nullptr, 0);
+    const TcArea A = tc_area(L.d_in, L.d1);
+    uint8_t *base = (uint8_t *)pack + L.tc;
+    float *hdr16 = (float *)(base + A.hdr16);
+    // one scale for the three square images: max over Wb and Ww with a factor 2 of headroom (Pm, R are sums of two entries)
+    tcg::tc_scales_kernel<<<2, 1024, 0, st>>>(W1, L.d1, L.d_in, b1, w_lr, 1, 2 * L.d1 * L.d1, hdr16, 2.f);
     NPLDA_LAUNCH_CHECK();
-    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Ww, L.d1, L.d1, ks2, dplda_image(L, pack, 0), nullptr, 0);
+    tcg::tc_pack_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / 16, base + A.img1, nullptr, 0, 0, 0,
+                                                        base + A.img1h, hdr16);
     NPLDA_LAUNCH_CHECK();
-    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Wb, L.d1, L.d1, ks2, dplda_image(L, pack, 1), nullptr, 1);
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Ww, L.d1, L.d1, ks2, dplda_image(L, pack, 0), nullptr, 0, 0, 0,
+                                                    dplda_image16(L, pack, 0), hdr16 + 2);
     NPLDA_LAUNCH_CHECK();
-    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Ww, L.d1, L.d1, ks2, dplda_image(L, pack, 2), nullptr, 1);
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Wb, L.d1, L.d1, ks2, dplda_image(L, pack, 1), nullptr, 1, 0, 0,
+                                                    dplda_image16(L, pack, 1), hdr16 + 2);
+    NPLDA_LAUNCH_CHECK();
+    tcg::tc_pack_kernel<<<sm_count(), 256, 0, st>>>(Ww, L.d1, L.d1, ks2, dplda_image(L, pack, 2), nullptr, 1, 0, 0,
+                                                    dplda_image16(L, pack, 2), hdr16 + 2);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }
@@ -897,8 +1009,38 @@ static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Ar
     return NPLDA_OK;
 }
 
-// mode 0: bf16x3 kernel.  mode 1: fp16 + 2 x e4m3 kernel for layer 1, then the bf16x3 kernel as a guarded
-// fallback pass (a no-op launch unless the range guard fired).
+// Debug switches of the tensor-core kernel (bottleneck experiments, forced modes, cycle accounting).  They exist only
+// in builds made with -DNPLDA_DEBUG_SWITCHES (make DEBUG=1) and are read ONCE per process: the production library
+// never calls getenv on the scoring path and has no profiling instantiations.
+struct TcDebug {
+    int dbg = 0;        // NPLDA_TC_DEBUG: 1 no x loads, 2 no weight copies, 4 no MMAs, 8 no TMEM stores, 16 no LDS, 32 idle epilogue
+    int mode = -1;      // NPLDA_TC_MODE: force 0 (bf16x3), 1 (fp16 + e4m3) or 2 (fp16x3)
+    bool prof = false;  // NPLDA_TC_PROF: per-role cycle accounting, synchronises and prints
+};
+static const TcDebug &tc_debug() {
+    static const TcDebug d = [] {
+        TcDebug t;
+#ifdef NPLDA_DEBUG_SWITCHES
+        if (const char *e = getenv("NPLDA_TC_DEBUG")) t.dbg = atoi(e);
+        if (const char *m = getenv("NPLDA_TC_MODE")) t.mode = atoi(m);
+        t.prof = getenv("NPLDA_TC_PROF") != nullptr;
+#endif
+        return t;
+    }();
+    return d;
+}
+
+template <int MODE>
+static int launch_tc_mode(bool prof, const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Args &a, int grid, cudaStream_t st) {
+#ifdef NPLDA_DEBUG_SWITCHES
+    if (prof) return launch_tc<true, MODE>(m1, m2, a, grid, st);
+#endif
+    (void)prof;
+    return launch_tc<false, MODE>(m1, m2, a, grid, st);
+}
+
+// mode 2 (default): fp16x3 kernel, then the bf16x3 kernel as a guarded fallback pass (a no-op launch unless the range
+// guard fired).  mode 1: fp16 + 2 x e4m3 for layer 1, same fallback.  mode 0: bf16x3 only.
 int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, const int64_t *i2, int64_t n_rows,
              int32_t *bad_flag, int64_t n, const PackLayout &L, const char *pack, float *scores, int mode, cudaStream_t st,
              float *aout, float *yout, int64_t emit_cap) {
@@ -907,56 +1049,65 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
     if (n >= (int64_t)1 << 31) return NPLDA_ERR_UNSUPPORTED_DIM;   // TMA row coordinates are int32
     CUtensorMap m1, m2;
     if (!tcg::make_x_map(&m1, x1, n, L.d_in) || !tcg::make_x_map(&m2, x2, n, L.d_in)) return NPLDA_ERR_NO_DEVICE;
+    const TcArea A = tc_area(L.d_in, L.d1);
+    const uint8_t *base = (const uint8_t *)pack + L.tc;
     tcg::Args a;
     a.x1 = x1; a.x2 = x2; a.n = n;
     a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
-    const uint8_t *img1 = (const uint8_t *)pack + L.tc;
-    const uint8_t *img2 = img1 + (tcg::image_bytes(L.d_in / 16) + 255) / 256 * 256;
-    const uint8_t *img1m = img2 + (tcg::image_bytes(round_up(L.d1, 16) / 16) + 255) / 256 * 256;
-    a.w1img = img1; a.w2img = img2;
-    a.hdr = (const float *)(img1m + tcg::mixed_image_bytes(L.d_in));
+    a.w1img = base + A.img1; a.w2img = base + A.img2;
+    a.hdr = (const float *)(base + A.hdr);
+    a.hdr16 = (const float *)(base + A.hdr16);
     a.guard = nullptr;
     a.b1 = (const float *)(pack + L.b1); a.b2 = (const float *)(pack + L.b2);
     a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.q);
     a.scores = scores;
     a.aout = aout; a.yout = yout; a.emit_cap = emit_cap;
-    if (aout != nullptr) {      // backward: a and y rows for the SIMT tile kernel, bf16x3 kernel, no scores
+    a.dbg = 0; a.trace = nullptr;
+    const TcDebug &D = tc_debug();
+    if (D.mode >= 0) mode = D.mode;
+    const int64_t ntiles = (n + tcg::TP - 1) / tcg::TP;
+    const int grid = (int)std::min<int64_t>(ntiles, sm_count());
+    tcg::Args a16 = a;                                  // the fp16x3 pass
+    a16.w1img = base + A.img1h; a16.w2img = base + A.img2h;
+    if (aout != nullptr) {      // training forward / backward: scores (if asked) plus the a and y rows
         if (!yout || emit_cap < n) return NPLDA_ERR_BAD_ARG;
-        a.guard = nullptr; a.dbg = 0; a.trace = nullptr;
-        const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
-        return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
+        if (mode == 0) return launch_tc<false, 0, true>(m1, m2, a, grid, st);
+        int *slot = guard_slot();
+        if (!slot) return NPLDA_ERR_NO_DEVICE;
+        a16.guard = slot; a.guard = slot;
+        const int rc = launch_tc<false, 2, true>(m1, m2, a16, grid, st);
+        if (rc != NPLDA_OK) return rc;
+        return launch_tc<false, 0, true>(m1, m2, a, grid, st);
     }
     if (yout != nullptr) return NPLDA_ERR_BAD_ARG;
-    {
-        const char *e = getenv("NPLDA_TC_DEBUG");
-        a.dbg = e ? atoi(e) : 0;
-        const char *m = getenv("NPLDA_TC_MODE");       // experiments: force 0 (bf16x3) or 1 (mixed)
-        if (m) mode = atoi(m) != 0;
-    }
-    a.trace = nullptr;
-    const bool prof = getenv("NPLDA_TC_PROF") != nullptr;
+    a.dbg = a16.dbg = D.dbg;
+    const bool prof = D.prof;
     if (prof) {
         NPLDA_CUDA_TRY(cudaMalloc(&a.trace, 6 * 16 * sizeof(long long)));
         NPLDA_CUDA_TRY(cudaMemsetAsync(a.trace, 0, 6 * 16 * sizeof(long long), st));
+        a16.trace = a.trace;
     }
-    const int64_t ntiles = (n + tcg::TP - 1) / tcg::TP;
-    const int grid = (int)std::min<int64_t>(ntiles, sm_count());
     int rc;
-    if (mode == 1) {
+    if (mode == 0) {
+        rc = launch_tc_mode<0>(prof, m1, m2, a, grid, st);
+    } else {
         int *slot = guard_slot();
         if (!slot) return NPLDA_ERR_NO_DEVICE;
-        tcg::Args am = a;
-        am.w1img = img1m; am.guard = slot;
-        rc = prof ? launch_tc<true, 1>(m1, m2, am, grid, st) : launch_tc<false, 1>(m1, m2, am, grid, st);
+        if (mode == 1) {
+            tcg::Args am = a;
+            am.w1img = base + A.img1m; am.guard = slot;
+            rc = launch_tc_mode<1>(prof, m1, m2, am, grid, st);
+        } else {
+            a16.guard = slot;
+            rc = launch_tc_mode<2>(prof, m1, m2, a16, grid, st);
+        }
         if (rc != NPLDA_OK) return rc;
-        a.guard = slot;
         tcg::Args af = a;
-        af.trace = nullptr;
+        af.guard = slot; af.trace = nullptr;
         rc = launch_tc<false, 0>(m1, m2, af, grid, st);
-    } else {
-        rc = prof ? launch_tc<true, 0>(m1, m2, a, grid, st) : launch_tc<false, 0>(m1, m2, a, grid, st);
     }
     if (rc != NPLDA_OK) return rc;
+#ifdef NPLDA_DEBUG_SWITCHES
     if (prof) {   // debug only: synchronises
         long long h[6 * 16];
         NPLDA_CUDA_TRY(cudaStreamSynchronize(st));
@@ -980,6 +1131,7 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
         }
         fflush(stdout);
     }
+#endif
     return NPLDA_OK;
 }
 
@@ -991,12 +1143,14 @@ int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackL
     if (n >= (int64_t)1 << 31 || emit_cap < n) return NPLDA_ERR_BAD_ARG;
     CUtensorMap m1, m2;
     if (!tcg::make_x_map(&m1, x1, n, L.d_in) || !tcg::make_x_map(&m2, x2, n, L.d_in)) return NPLDA_ERR_NO_DEVICE;
+    const TcArea A = tc_area(L.d_in, L.d1);
     tcg::Args a;
     a.x1 = x1; a.x2 = x2; a.n = n;
     a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
     a.w1img = (const uint8_t *)pack + L.tc;
     a.w2img = dplda_image(L, pack, which);
-    a.hdr = (const float *)(pack + L.p);               // unused by MODE 0
+    a.hdr = (const float *)(pack + L.p);               // unused by MODE 0 / 2
+    a.hdr16 = (const float *)(pack + L.tc + A.hdr16);
     a.guard = nullptr;
     a.b1 = (const float *)(pack + L.b1);
     a.b2 = (const float *)(pack + L.p);                // zeros
@@ -1004,7 +1158,17 @@ int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackL
     a.scores = nullptr; a.aout = aout; a.yout = yout; a.emit_cap = emit_cap;
     a.trace = nullptr; a.dbg = 0;
     const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
-    return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
+    const int grid = (int)std::min<int64_t>(nt, sm_count());
+    // fp16x3 pass, then the bf16x3 pass behind its range guard (a no-op launch unless an input left fp16's range)
+    int *slot = guard_slot();
+    if (!slot) return NPLDA_ERR_NO_DEVICE;
+    tcg::Args a16 = a;
+    a16.w1img = (const uint8_t *)pack + L.tc + A.img1h;
+    a16.w2img = dplda_image16(L, pack, which);
+    a16.guard = slot; a.guard = slot;
+    const int rc = launch_tc<false, 2, true>(m1, m2, a16, grid, st);
+    if (rc != NPLDA_OK) return rc;
+    return launch_tc<false, 0, true>(m1, m2, a, grid, st);
 }
 
 // Rows-in / rows-out product on the tensor cores, used by the backward for dL/du = dL/dy . W2: an EMIT pass whose
@@ -1031,7 +1195,7 @@ int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int row_widt
     a.x1 = xa; a.x2 = xb; a.n = n;
     a.nst1 = d_in / tcg::KST; a.ksteps2 = ksteps2;
     a.w1img = w1img; a.w2img = w2img_any;
-    a.hdr = zeros; a.guard = nullptr;
+    a.hdr = zeros; a.hdr16 = zeros; a.guard = nullptr;
     a.b1 = zeros; a.b2 = zeros; a.p = zeros; a.q = zeros;
     a.scores = nullptr; a.aout = aout; a.yout = nullptr; a.emit_cap = emit_cap;
     a.trace = nullptr; a.dbg = 0;

@@ -2,9 +2,19 @@
 //
 // The reference's callers never hold materialised [N,512] pairs: they hold a static table of x-vectors (the pickled
 // dict of xvector_NeuralPlda_pytorch.py:117) and index batches (sv_trials_loaders.py:418-426).  The table is split
-// ONCE into the tensor cores' operand format (nplda_table_split: bf16 hi/lo, x = hi + lo + O(2^-17 |x|), the same
-// split the converter warps of score_tc.cu apply per call), and this kernel scores trials (table[i1[k]], table[i2[k]])
-// with no conversion work at all:
+// ONCE into the tensor cores' operand format and this kernel scores trials (table[i1[k]], table[i2[k]]) with no
+// conversion work at all.
+//
+// Numerics ("fp16x3"): every fp32 operand v is scaled by a power of two into fp16's normal range and split
+// v 2^k = hi + lo with hi = fp16(v 2^k), lo = fp16(v 2^k - hi): two 11-bit significands, residual O(2^-22 |v|) -- against
+// O(2^-17) for the bf16 split of score_tc.cu's MODE 0.  Products are evaluated as hi*hi + lo*hi + hi*lo with fp32
+// accumulation in TMEM (the dropped lo*lo term is O(2^-22)), the same three MMAs per K step at the same tensor rate.
+// Measured / emulated on the golden parameters: scores within 1e-6 of the fp64 value (bf16x3: 8e-6), and the training
+// activations accurate enough for gradients at fp32-autograd level (2e-6 against 1e-4, tools/grad_diag.py).  The
+// scales: the table by 2^kx from its absolute maximum (nplda_table_split, two passes, once per table), W1 / W2 by
+// 2^gw from theirs (pack time), the layer-1 output a by 2^-ka from the bound max_j ||W1_j||_1 max|x| + max|b1| -- all
+// exact powers of two undone in the epilogue, so nothing can overflow and there is no fallback path.
+//
 //
 //   * two CTAs of a cluster (the two SMs of a TPC) execute M = 256 MMAs (tcgen05.mma.cta_group::2): each CTA holds
 //     the 128 rows (64 pairs, both sides) of its own tile in shared memory and HALF of the 176 weight rows, so the
@@ -20,8 +30,10 @@
 //     the leader's barriers through the cluster's shared-memory window.
 //   * epilogue (8 warps per CTA, its own 128 rows): identical arithmetic to score_tc.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -37,11 +49,17 @@ constexpr int NPAD = 176;                       // MMA N: 170 padded to a multip
 constexpr int NH = NPAD / 2;                    // weight rows held by one CTA of the pair
 constexpr int KST = 32;                         // K per stage
 constexpr int A_STAGE = 128 * 128;              // 16384 B: [128 rows][hi 32 bf16 | lo 32 bf16], 128-byte swizzle
-constexpr int NA = 5;                           // A ring stages
+#ifndef TCX_NA
+#define TCX_NA 5
+#endif
+#ifndef TCX_NB
+#define TCX_NB 4
+#endif
+constexpr int NA = TCX_NA;                      // A ring stages
 constexpr int KCH_BH = (NH / 8) * 128;          // 1408 B: one 8-wide k-chunk of 88 weight rows (11 core matrices)
 constexpr int B_HALF = 8 * KCH_BH;              // 11264 B: hi chunks 0-3, lo chunks 0-3 of one stage (K = 32)
 constexpr int B_LINES = B_HALF / 128;           // 88 rows of the [lines x 128 B] view the weight TMA uses
-constexpr int NB = 4;                           // B ring stages
+constexpr int NB = TCX_NB;                      // B ring stages
 constexpr int KCH_U = (128 / 8) * 128;          // 2048 B: one k-chunk of U (16 core matrices)
 constexpr int U_HALF = (NPAD / 8) * KCH_U;      // 45056 B (hi or lo), K = 176
 
@@ -66,8 +84,11 @@ struct Args {
     int nst1;               // layer-1 stages  = d_in / 32
     int ksteps2;            // layer-2 K steps = round_up(d1, 16) / 16
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
+    const float *thdr;      // table header: [0] max|x|, [1] 2^kx (the table is stored as x 2^kx), [2] 2^-kx
+    const float *whdr;      // pair-image header: [0] 2^gw1, [1] 2^-gw1, [2] 2^gw2, [3] 2^-gw2, [4] max_j ||W1_j||_1, [5] max|b1|
     float *scores;
     int32_t *bad_flag;
+    int variant;            // experiments (DEBUG builds, NPLDA_TCX_VARIANT): 1 = barrier waits not interleaved with the MMAs
 };
 
 struct Ring {
@@ -128,8 +149,14 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / TMA completion
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t IDESC = make_idesc_bf16(256, NPAD);
+    constexpr uint32_t IDESC = make_idesc_f16(256, NPAD);
     const int nst2 = (g.ksteps2 + 1) / 2;
+    // scales (exact powers of two): layer-1 accumulator = a 2^(kx + gw1); U holds a 2^-ka with |a 2^-ka| < 16384 for
+    // every input the bound covers; layer-2 accumulator = (W2 a) 2^(gw2 - ka)
+    const float s1 = g.thdr[2] * g.whdr[1];
+    const float a_bound = g.whdr[4] * g.thdr[0] + g.whdr[5];
+    const float sa = a_bound < 16384.f ? 1.f : pow2_scale_to_2p13(a_bound);
+    const float c2 = g.whdr[3] / sa;
 
     if (warp < EPI_WARPS) {
         // =============================== EPILOGUE (this CTA's 128 rows) ===============================
@@ -147,26 +174,26 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
         auto pass1 = [&](const uint32_t (&v)[8], int c0, float (&ss)[4]) {
             const float2 ba = b1s[(c0 >> 1) + cq], bb = b1s[(c0 >> 1) + 4 + cq];
-            const float a00 = __uint_as_float(v[0]) + ba.x, a01 = __uint_as_float(v[1]) + ba.y;
-            const float a10 = __uint_as_float(v[2]) + ba.x, a11 = __uint_as_float(v[3]) + ba.y;
-            const float a02 = __uint_as_float(v[4]) + bb.x, a03 = __uint_as_float(v[5]) + bb.y;
-            const float a12 = __uint_as_float(v[6]) + bb.x, a13 = __uint_as_float(v[7]) + bb.y;
+            const float a00 = fmaf(__uint_as_float(v[0]), s1, ba.x), a01 = fmaf(__uint_as_float(v[1]), s1, ba.y);
+            const float a10 = fmaf(__uint_as_float(v[2]), s1, ba.x), a11 = fmaf(__uint_as_float(v[3]), s1, ba.y);
+            const float a02 = fmaf(__uint_as_float(v[4]), s1, bb.x), a03 = fmaf(__uint_as_float(v[5]), s1, bb.y);
+            const float a12 = fmaf(__uint_as_float(v[6]), s1, bb.x), a13 = fmaf(__uint_as_float(v[7]), s1, bb.y);
             ss[0] = fmaf(a00, a00, ss[0]); ss[1] = fmaf(a01, a01, ss[1]);
             ss[0] = fmaf(a02, a02, ss[0]); ss[1] = fmaf(a03, a03, ss[1]);
             ss[2] = fmaf(a10, a10, ss[2]); ss[3] = fmaf(a11, a11, ss[3]);
             ss[2] = fmaf(a12, a12, ss[2]); ss[3] = fmaf(a13, a13, ss[3]);
             uint32_t hi, lo;
             const int kc = c0 >> 3;
-            split_bf16x2(a00, a01, hi, lo);
+            split_f16x2(a00 * sa, a01 * sa, hi, lo);
             *reinterpret_cast<uint32_t *>(u0 + kc * KCH_U) = hi;
             *reinterpret_cast<uint32_t *>(u0 + U_HALF + kc * KCH_U) = lo;
-            split_bf16x2(a02, a03, hi, lo);
+            split_f16x2(a02 * sa, a03 * sa, hi, lo);
             *reinterpret_cast<uint32_t *>(u0 + (kc + 1) * KCH_U) = hi;
             *reinterpret_cast<uint32_t *>(u0 + U_HALF + (kc + 1) * KCH_U) = lo;
-            split_bf16x2(a10, a11, hi, lo);
+            split_f16x2(a10 * sa, a11 * sa, hi, lo);
             *reinterpret_cast<uint32_t *>(u1 + kc * KCH_U) = hi;
             *reinterpret_cast<uint32_t *>(u1 + U_HALF + kc * KCH_U) = lo;
-            split_bf16x2(a12, a13, hi, lo);
+            split_f16x2(a12 * sa, a13 * sa, hi, lo);
             *reinterpret_cast<uint32_t *>(u1 + (kc + 1) * KCH_U) = hi;
             *reinterpret_cast<uint32_t *>(u1 + U_HALF + (kc + 1) * KCH_U) = lo;
         };
@@ -210,8 +237,8 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             float ss0 = ss[0] + ss[1], ss1 = ss[2] + ss[3];
             ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
             ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
-            const float r0 = 1.f / fmaxf(sqrtf(ss0), 1e-12f);      // F.normalize eps (models.py:368)
-            const float r1 = 1.f / fmaxf(sqrtf(ss1), 1e-12f);
+            const float r0 = c2 / fmaxf(sqrtf(ss0), 1e-12f);       // F.normalize eps (models.py:368), times the layer-2 scale
+            const float r1 = c2 / fmaxf(sqrtf(ss1), 1e-12f);
             fence_proxy_async();      // U is read by tcgen05.mma (async proxy)
             tc_fence_before();        // our TMEM reads of D are done before Y overwrites it
             __syncwarp();
@@ -252,10 +279,14 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int half = g.nst1 / 2;
             // One stage: K = 32 as two K = 16 steps, each hi*Whi + lo*Whi + hi*Wlo.  A descriptors: tile base + 0 / 32 B
             // (hi, steps 0 / 1) and + 64 / 96 B (lo); B: chunks 0-3 hi, 4-7 lo of this CTA's half, two chunks per step.
+            // The MMA queue is shallow: an issue stalls until the pipe accepts it, so whatever the warp executes
+            // between two issues runs under the previous MMA.  The barrier waits of stage s + 1 (~100 cycles each even
+            // when already satisfied) therefore sit between the two K steps of stage s.
             auto layer1 = [&](uint32_t dcol, int s_begin, int s_end) {
+                if (s_begin >= s_end) return;
+                mbar_wait(&a_full[ra.stage], ra.phase);
+                mbar_wait(&b_full[rb.stage], rb.phase);
                 for (int s = s_begin; s < s_end; ++s) {
-                    mbar_wait(&a_full[ra.stage], ra.phase);
-                    mbar_wait(&b_full[rb.stage], rb.phase);
                     tc_fence_after();
                     const uint64_t ad = make_smem_desc_sw128(a_base + ra.stage * A_STAGE);
                     const uint64_t bd = make_smem_desc(b_base + rb.stage * B_HALF, KCH_BH, 128);
@@ -263,6 +294,16 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         mma2_ss(dcol, ad, bd, IDESC, s != 0);
                         mma2_ss(dcol, ad + 4, bd, IDESC, 1);
                         mma2_ss(dcol, ad, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
+                    }
+                    __syncwarp();
+                    Ring na = ra, nb = rb;
+                    na.advance();
+                    nb.advance();
+                    if (s + 1 < s_end && !(g.variant & 1)) {
+                        mbar_wait(&a_full[na.stage], na.phase);
+                        mbar_wait(&b_full[nb.stage], nb.phase);
+                    }
+                    if (elect_one()) {
                         mma2_ss(dcol, ad + 2, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
                         mma2_ss(dcol, ad + 6, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
                         mma2_ss(dcol, ad + 2, bd + ((6 * KCH_BH) >> 4), IDESC, 1);
@@ -270,8 +311,12 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         mma2_commit_mc(&b_empty[rb.stage], 3);
                     }
                     __syncwarp();
-                    ra.advance();
-                    rb.advance();
+                    if (s + 1 < s_end && (g.variant & 1)) {
+                        mbar_wait(&a_full[na.stage], na.phase);
+                        mbar_wait(&b_full[nb.stage], nb.phase);
+                    }
+                    ra = na;
+                    rb = nb;
                 }
             };
             for (int64_t i = 0; i <= T; ++i) {
@@ -287,8 +332,8 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     const uint32_t dcol = tmem + d * NPAD;
                     mbar_wait(u_full, (uint32_t)(j & 1));
                     tc_fence_after();
+                    mbar_wait(&b_full[rb.stage], rb.phase);
                     for (int ks = 0; ks < g.ksteps2; ks += 2) {
-                        mbar_wait(&b_full[rb.stage], rb.phase);
                         tc_fence_after();
                         const uint64_t bd = make_smem_desc(b_base + rb.stage * B_HALF, KCH_BH, 128);
                         const uint64_t uhi = make_smem_desc(u_base + ks * 2 * KCH_U, KCH_U, 128);
@@ -297,6 +342,12 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             mma2_ss(dcol, uhi, bd, IDESC, ks != 0);
                             mma2_ss(dcol, ulo, bd, IDESC, 1);
                             mma2_ss(dcol, uhi, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
+                        }
+                        __syncwarp();
+                        Ring nb = rb;
+                        nb.advance();
+                        if (ks + 2 < g.ksteps2) mbar_wait(&b_full[nb.stage], nb.phase);
+                        if (elect_one()) {
                             if (ks + 1 < g.ksteps2) {
                                 const uint64_t uhi1 = uhi + ((2 * KCH_U) >> 4), ulo1 = ulo + ((2 * KCH_U) >> 4);
                                 mma2_ss(dcol, uhi1, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
@@ -306,7 +357,7 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             mma2_commit_mc(&b_empty[rb.stage], 3);
                         }
                         __syncwarp();
-                        rb.advance();
+                        rb = nb;
                     }
                     if (elect_one()) {
                         mma2_commit_mc(&y_full[d], 3);
@@ -389,9 +440,22 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 }
 
 // ---- table split ------------------------------------------------------------------------------
-// split[row][stage s][hi k = 32 s .. 32 s + 31 (bf16) | lo (bf16)]: d_in * 4 bytes per row, as many as the fp32 row.
+// split[row][stage s][hi k = 32 s .. 32 s + 31 (fp16) | lo (fp16)] of x 2^kx: d_in * 4 bytes per row, as many as the fp32
+// row; then a 128-byte header {max|x|, 2^kx, 2^-kx}.  Two passes, once per table: absolute maximum, then the split.
+__global__ void __launch_bounds__(256) table_absmax_kernel(const float *__restrict__ table, int64_t count, uint32_t *__restrict__ hdr) {
+    float m = 0.f;
+    for (int64_t e = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; e < count; e += (int64_t)gridDim.x * blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(table + e);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(hdr, __float_as_uint(m));     // non-negative floats order like their bit patterns
+}
+
 __global__ void __launch_bounds__(256) table_split_kernel(const float *__restrict__ table, int64_t n_rows, int d_in,
-                                                          uint8_t *__restrict__ out) {
+                                                          uint8_t *__restrict__ out, float *__restrict__ hdr) {
+    const float scale = pow2_scale_to_2p13(hdr[0]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { hdr[1] = scale; hdr[2] = 1.f / scale; }
     const int per_row = d_in / 8;                                   // 8 consecutive elements per thread
     const int64_t total = n_rows * per_row;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -400,8 +464,8 @@ __global__ void __launch_bounds__(256) table_split_kernel(const float *__restric
         const float4 a = *reinterpret_cast<const float4 *>(table + row * d_in + k0);
         const float4 b = *reinterpret_cast<const float4 *>(table + row * d_in + k0 + 4);
         uint4 hi, lo;
-        split_bf16x2(a.x, a.y, hi.x, lo.x); split_bf16x2(a.z, a.w, hi.y, lo.y);
-        split_bf16x2(b.x, b.y, hi.z, lo.z); split_bf16x2(b.z, b.w, hi.w, lo.w);
+        split_f16x2(a.x * scale, a.y * scale, hi.x, lo.x); split_f16x2(a.z * scale, a.w * scale, hi.y, lo.y);
+        split_f16x2(b.x * scale, b.y * scale, hi.z, lo.z); split_f16x2(b.z * scale, b.w * scale, hi.w, lo.w);
         uint8_t *st = out + row * (int64_t)d_in * 4 + (k0 / KST) * 128 + (k0 % KST) * 2;
         *reinterpret_cast<uint4 *>(st) = hi;
         *reinterpret_cast<uint4 *>(st + 64) = lo;
@@ -410,22 +474,25 @@ __global__ void __launch_bounds__(256) table_split_kernel(const float *__restric
 
 // ---- pair weight images -----------------------------------------------------------------------
 // Stage s (K = [32 s, 32 s + 32)) = [half 0][half 1], a half = weight rows [88 h, 88 h + 88) as 8 chunks
-// [hi k 0-7][hi 8-15][hi 16-23][hi 24-31][lo x 4], a chunk = 11 core matrices of 8 rows x 8 k (128 B each).
-__global__ void pair_pack_kernel(const float *__restrict__ W, int N, int K, int nstages, uint8_t *__restrict__ img) {
+// [hi k 0-7][hi 8-15][hi 16-23][hi 24-31][lo x 4], a chunk = 11 core matrices of 8 rows x 8 k (128 B each);
+// fp16 hi / lo of W 2^gw (*scale).
+__global__ void pair_pack_kernel(const float *__restrict__ W, int N, int K, int nstages, const float *__restrict__ scale,
+                                 uint8_t *__restrict__ img) {
+    const float sc = scale[0];
     const int64_t total = (int64_t)nstages * NPAD * KST;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int kk = (int)(e % KST);
         const int n = (int)((e / KST) % NPAD);
         const int s = (int)(e / ((int64_t)KST * NPAD));
         const int k = s * KST + kk;
-        const float w = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        const float w = (n < N && k < K) ? W[(int64_t)n * K + k] * sc : 0.f;
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
         const int hsel = n / NH, nn = n % NH;
         uint8_t *st = img + ((size_t)s * 2 + hsel) * B_HALF;
         const size_t off = (size_t)(kk >> 3) * KCH_BH + (nn >> 3) * 128 + (nn & 7) * 16 + (kk & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(st + off) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(st + 4 * KCH_BH + off) = lo;
+        *reinterpret_cast<__half *>(st + off) = hi;
+        *reinterpret_cast<__half *>(st + 4 * KCH_BH + off) = lo;
     }
 }
 
@@ -475,17 +542,21 @@ static int tcx_nst2(int d1) { return (round_up(d1, 16) / 16 + 1) / 2; }
 
 int64_t tcx_image_bytes(int d_in, int d1, int d2) {
     if (!tcx_dims_ok(d_in, d1, d2)) return 0;
-    return pair_image_bytes(d_in / tcx::KST) + pair_image_bytes(tcx_nst2(d1)) + 512;
+    return (pair_image_bytes(d_in / tcx::KST) + 255) / 256 * 256 + (pair_image_bytes(tcx_nst2(d1)) + 255) / 256 * 256 + 512;
 }
 
 // pair images of a NeuralPlda pack (flag NPLDA_PACK_PAIR): [W1: d_in / 32 stages][W2: ceil(ksteps2 / 2) stages]
-int tcx_pack_nplda(const float *W1, const float *W2, const PackLayout &L, char *pack, cudaStream_t st) {
+const float *tc_hdr16(const PackLayout &L, const char *pack);   // score_tc.cu: weight scales + layer-1 bound (tc_scales_kernel)
+
+int tcx_pack_nplda(const float *W1, const float *b1, const float *W2, const PackLayout &L, char *pack, cudaStream_t st) {
     if (!tcx_dims_ok(L.d_in, L.d1, L.d2) || L.tcx_bytes <= 0) return NPLDA_OK;
     uint8_t *img1 = (uint8_t *)pack + L.tcx;
     uint8_t *img2 = img1 + (pair_image_bytes(L.d_in / tcx::KST) + 255) / 256 * 256;
-    tcx::pair_pack_kernel<<<sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / tcx::KST, img1);
+    (void)b1;
+    const float *hdr = tc_hdr16(L, pack);            // filled by the tensor-core pack that ran just before on this stream
+    tcx::pair_pack_kernel<<<sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / tcx::KST, hdr, img1);
     NPLDA_LAUNCH_CHECK();
-    tcx::pair_pack_kernel<<<sm_count() / 2, 256, 0, st>>>(W2, L.d2, L.d1, tcx_nst2(L.d1), img2);
+    tcx::pair_pack_kernel<<<sm_count() / 2, 256, 0, st>>>(W2, L.d2, L.d1, tcx_nst2(L.d1), hdr + 2, img2);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }
@@ -494,7 +565,11 @@ int table_split(const float *table, int64_t n_rows, int d_in, void *split, cudaS
     if (d_in % tcx::KST != 0 || d_in < tcx::KST) return NPLDA_ERR_UNSUPPORTED_DIM;
     const int64_t total = n_rows * (d_in / 8);
     const int grid = (int)std::min<int64_t>((total + 255) / 256, 16 * (int64_t)sm_count());
-    tcx::table_split_kernel<<<grid, 256, 0, st>>>(table, n_rows, d_in, (uint8_t *)split);
+    float *hdr = (float *)((uint8_t *)split + n_rows * (int64_t)d_in * 4);
+    NPLDA_CUDA_TRY(cudaMemsetAsync(hdr, 0, 128, st));
+    tcx::table_absmax_kernel<<<grid, 256, 0, st>>>(table, n_rows * (int64_t)d_in, (uint32_t *)hdr);
+    NPLDA_LAUNCH_CHECK();
+    tcx::table_split_kernel<<<grid, 256, 0, st>>>(table, n_rows, d_in, (uint8_t *)split, hdr);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }
@@ -514,7 +589,13 @@ int score_tcx(const void *split, int64_t n_rows, const int64_t *i1, const int64_
     a.nst1 = L.d_in / tcx::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
     a.b1 = (const float *)(pack + L.b1); a.b2 = (const float *)(pack + L.b2);
     a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.q);
+    a.thdr = (const float *)((const uint8_t *)split + n_rows * (int64_t)L.d_in * 4);
+    a.whdr = tc_hdr16(L, pack);
     a.scores = scores; a.bad_flag = bad_flag;
+    a.variant = 0;
+#ifdef NPLDA_DEBUG_SWITCHES
+    { static const int v = getenv("NPLDA_TCX_VARIANT") ? atoi(getenv("NPLDA_TCX_VARIANT")) : 0; a.variant = v; }
+#endif
     const int64_t nsuper = (n + 2 * tcx::TP - 1) / (2 * tcx::TP);
     const int grid = 2 * (int)std::min<int64_t>(nsuper, sm_count() / 2);
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(tcx::score_tcx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::SMEM_BYTES));

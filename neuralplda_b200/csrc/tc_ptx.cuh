@@ -180,5 +180,27 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uin
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
 }
 
+// ---- fp16 hi/lo split ("fp16x3" operands) -----------------------------------------------------------
+// v = hi + lo + O(2^-22 |v|) for |v| inside fp16's normal range [2^-14, 65504): hi = fp16(v), lo = fp16(v - hi).
+// Callers scale their operands by a power of two first (weights at pack time, tables at split time).
+// Returns hi and lo of two consecutive elements packed as f16x2 (element 0 in the low half).
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));   // first source -> upper half
+    float ha, hb;
+    asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}\n" : "=f"(ha), "=f"(hb) : "r"(hi));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
+// Instruction descriptor for kind::f16 with fp16 A/B (both K-major), fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// 2^k with v 2^k in [8192, 16384) for a finite v > 0 (k clamped to +-100), else 1
+__device__ __forceinline__ float pow2_scale_to_2p13(float v) {
+    if (!(v > 0.f) || !(v < 3.0e38f)) return 1.f;
+    int e;
+    frexpf(v, &e);                       // v = f 2^e, f in [0.5, 1)
+    return exp2f((float)max(-100, min(100, 14 - e)));
+}
+
 }  // namespace tc
 }  // namespace nplda

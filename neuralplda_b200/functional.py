@@ -144,18 +144,18 @@ def split_supported(kind, d_in, d1, d2):
     return kind == "nplda" and d_in % 32 == 0 and d_in >= 64 and max(d1, d2) <= 176
 
 
-def score_split(table, split, i1, i2, params, dims, packed):
+def score_split(table, split, i1, i2, params, dims, packed, flag_ptr=None):
     """NeuralPlda scores of trials (table[i1[k]], table[i2[k]]) from the pre-split image of the table
     (nplda_score_fwd_split: TMA row gather + tcgen05 CTA-pair MMAs)."""
     d_in, d1, d2 = dims
     n = i1.numel()
     dev = split.device
     scores = torch.empty(n, dtype=torch.float32, device=dev)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    fp, flag = _flag(dev, flag_ptr)
     pack = packed.get("nplda", params, d_in, d1, d2, pair=True)
     with on_device(dev):
         check(lib().nplda_score_fwd_split(ptr(split), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1, d2, ptr(pack),
-                                          ptr(scores), ptr(flag), stream_ptr()), "nplda_score_fwd_split")
+                                          ptr(scores), fp, stream_ptr()), "nplda_score_fwd_split")
     return scores, flag
 
 
@@ -174,12 +174,14 @@ def _zero_grads(params, need):
 SAVE_ACTIVATIONS_MIN_PAIRS = 64       # one tile of the tensor-core kernel; below, the all-fp32 tile kernel does everything
 
 
-def _wants_activations(ctx, packed, impl, n, dev):
+def _wants_activations(ctx, packed, impl, n, dev, grad_mode):
     """A forward whose backward will run keeps the activations the backward needs (3 KB per pair for NeuralPlda,
     4.6 KB for DPlda -- about the size of the inputs; PyTorch's autograd in the reference keeps far more) instead of
-    recomputing them in the backward.  `module.packed.save_activations = False` restores recomputation."""
-    if not (n >= SAVE_ACTIVATIONS_MIN_PAIRS and impl in (_lib.IMPL_AUTO, _lib.IMPL_TC) and any(ctx.needs_input_grad)
-            and getattr(packed, "save_activations", True)):
+    recomputing them in the backward.  `module.packed.save_activations = False` restores recomputation.
+    `grad_mode` is torch.is_grad_enabled() at the CALL (inside Function.forward it is always off, and
+    ctx.needs_input_grad ignores torch.no_grad()): evaluation forwards take the plain score kernel."""
+    if not (grad_mode and n >= SAVE_ACTIVATIONS_MIN_PAIRS and impl in (_lib.IMPL_AUTO, _lib.IMPL_TC)
+            and any(ctx.needs_input_grad) and getattr(packed, "save_activations", True)):
         return False
     nbytes = 6 * n * 176 * 4                          # upper bound (DPlda); only worth a driver query when it is large
     if nbytes > (1 << 30):
@@ -204,7 +206,7 @@ class NpldaScoreFn(torch.autograd.Function):
     """S = NeuralPlda.forward(x1, x2)  (reference utils/models.py:378-382)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, W1, b1, W2, b2, P_sqrt, Q, packed, impl):
+    def forward(ctx, x1, x2, W1, b1, W2, b2, P_sqrt, Q, packed, impl, grad_mode=True):
         d1, d_in = W1.shape
         d2 = W2.shape[0]
         _check_pair_inputs(x1, x2, d_in)
@@ -215,7 +217,7 @@ class NpldaScoreFn(torch.autograd.Function):
         ctx.act = None
         with on_device(x1c.device):
             rc = _lib.ERR_UNSUPPORTED_DIM
-            if _wants_activations(ctx, packed, impl, n, x1c.device):
+            if _wants_activations(ctx, packed, impl, n, x1c.device, grad_mode):
                 act = torch.empty(int(lib().nplda_act_floats(n, 0)), dtype=torch.float32, device=x1c.device)
                 rc = lib().nplda_score_fwd_train(ptr(x1c), ptr(x2c), n, d_in, d1, d2, ptr(pack), ptr(scores), ptr(act),
                                                  stream_ptr())
@@ -251,14 +253,14 @@ class NpldaScoreFn(torch.autograd.Function):
                 check(lib().nplda_score_bwd_act(ptr(x1), ptr(x2), n, d_in, d1, d2, *[ptr(p) for p in params],
                                                 ptr(ds), *[ptr(g) for g in grads], ptr(dx1), ptr(dx2), ptr(ctx.act),
                                                 ptr(ws), ws.numel(), stream_ptr()), "nplda_score_bwd")
-        return (dx1, dx2, *grads, None, None)
+        return (dx1, dx2, *grads, None, None, None)
 
 
 class DpldaScoreFn(torch.autograd.Function):
     """S = DPlda.forward(x1, x2)  (reference utils/models.py:491-495)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, W1, b1, w_lr, c_lr, packed, impl):
+    def forward(ctx, x1, x2, W1, b1, w_lr, c_lr, packed, impl, grad_mode=True):
         d1, d_in = W1.shape
         _check_pair_inputs(x1, x2, d_in)
         if w_lr.numel() != 2 * d1 * d1 + d1:
@@ -268,7 +270,7 @@ class DpldaScoreFn(torch.autograd.Function):
         pack = packed.get("dplda", (W1, b1, w_lr, c_lr), d_in, d1, d1)
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
         ctx.act = None
-        if _wants_activations(ctx, packed, impl, n, x1c.device):
+        if _wants_activations(ctx, packed, impl, n, x1c.device, grad_mode):
             with on_device(x1c.device):
                 act = torch.empty(int(lib().nplda_act_floats(n, 1)), dtype=torch.float32, device=x1c.device)
                 rc = lib().dplda_score_fwd_train(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), ptr(act),
@@ -310,11 +312,13 @@ class DpldaScoreFn(torch.autograd.Function):
                 check(lib().dplda_score_bwd_act(ptr(x1), ptr(x2), n, d_in, d1, ptr(W1c), ptr(b1c), ptr(wc), ptr(ds),
                                                 ptr(dW1), ptr(db1), ptr(dw), ptr(dc), ptr(dx1), ptr(dx2), ptr(ctx.act),
                                                 ptr(ws), ws.numel(), stream_ptr()), "dplda_score_bwd")
-        return (dx1, dx2, dW1, db1, dw, dc, None, None)
+        return (dx1, dx2, dW1, db1, dw, dc, None, None, None)
 
 
 def embed(kind, x, params, dims, packed):
     """extract_plda_embeddings of the reference (models.py:366-370 / 478-481), no autograd."""
+    from .lazy import dense
+    x = dense(x)
     require_cuda(x)
     d_in, d1, d2 = dims
     if x.dim() != 2 or x.shape[1] != d_in:
@@ -360,7 +364,16 @@ def score_from_embeddings(kind, e1, e2, params, dims, packed):
 SPLIT_MIN_TRIALS = 128       # one CTA-pair tile; below, the fp32 kernels are launch-bound either way
 
 
-def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO, embed_once=None, use_split=None):
+def _flag(dev, flag_ptr):
+    """(ctypes pointer for the kernels, tensor to return): a fresh device int32, or the caller's (pinned host) flag."""
+    if flag_ptr is not None:
+        return flag_ptr, None
+    t = torch.zeros(1, dtype=torch.int32, device=dev)
+    return ptr(t), t
+
+
+def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO, embed_once=None, use_split=None,
+                  flag_ptr=None):
     """Scores of trials (table[i1[k]], table[i2[k]]) (replaces sv_trials_loaders.load_xvec_trials_from_numbatch
     + forward).  Three device paths:
       * embed once: every table row is transformed ONCE (nplda_table_prepare, cached per table object / parameter
@@ -385,10 +398,10 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
             packed.rowtab_valid(kind, table, d_in, d1, d2) or table.shape[0] <= 2 * n)
     if embed_once:
         scores = torch.empty(n, dtype=torch.float32, device=dev)
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        fp, flag = _flag(dev, flag_ptr)
         rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
         with on_device(dev):
-            check(lib().nplda_score_pairs(ptr(rowtab), table.shape[0], ptr(i1), ptr(i2), n, ptr(scores), ptr(flag),
+            check(lib().nplda_score_pairs(ptr(rowtab), table.shape[0], ptr(i1), ptr(i2), n, ptr(scores), fp,
                                           stream_ptr()), "nplda_score_pairs")
         return scores, flag
     if use_split is None:
@@ -397,20 +410,20 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
     if use_split:
         if not split_supported(kind, d_in, d1, d2):
             raise RuntimeError("the pre-split tensor-core path takes NeuralPlda shapes with d_in % 32 == 0, widths <= 176")
-        return score_split(table, split_table(table), i1, i2, params, dims, packed)
+        return score_split(table, split_table(table), i1, i2, params, dims, packed, flag_ptr)
     table = _f32c(table)
     scores = torch.empty(n, dtype=torch.float32, device=dev)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    fp, flag = _flag(dev, flag_ptr)
     pack = packed.get(kind, params, d_in, d1, d2, mixed=(impl == _lib.IMPL_TC_F8))
     if impl in (_lib.IMPL_TC, _lib.IMPL_TC_F8):
         impl = _lib.IMPL_AUTO                     # the materialised-pair tcgen05 kernel has no gather; fp32 kernel
     with on_device(dev):
         if kind == "nplda":
             rc = lib().nplda_score_fwd_indexed(ptr(table), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1, d2,
-                                               ptr(pack), ptr(scores), ptr(flag), impl, stream_ptr())
+                                               ptr(pack), ptr(scores), fp, impl, stream_ptr())
         else:
             rc = lib().dplda_score_fwd_indexed(ptr(table), table.shape[0], ptr(i1), ptr(i2), n, d_in, d1,
-                                               ptr(pack), ptr(scores), ptr(flag), impl, stream_ptr())
+                                               ptr(pack), ptr(scores), fp, impl, stream_ptr())
     check(rc, "score_fwd_indexed")
     return scores, flag
 
@@ -509,8 +522,13 @@ class LossFn(torch.autograd.Function):
         # Threshold gradients are sums over this rank's trials; under a process
         # group the caller all-reduces parameter gradients (DDP-style), as for
         # the other parameters.
-        dthr = dth[:K].float() if (thresholds is not None and ctx.needs_input_grad[2]) else None
-        dthx = dth[K:].float() if (th_xent is not None and ctx.needs_input_grad[3]) else None
+        # A parameter the loss does not read gets NO gradient (None), as under the reference's autograd: softCdet never
+        # touches threshold_Xent and BCE never touches the Th{beta} thresholds (models.py:384-393).  A zero tensor would
+        # not be equivalent: Adam(weight_decay=1e-5) -- the reference's optimiser, xvector_NeuralPlda_pytorch.py:139 --
+        # skips parameters whose grad is None but decays (and, normalised, moves by lr per step) those with a zero grad.
+        soft = ctx.loss_id == _lib.LOSS_SOFTCDET
+        dthr = dth[:K].float() if (thresholds is not None and ctx.needs_input_grad[2] and soft) else None
+        dthx = dth[K:].float() if (th_xent is not None and ctx.needs_input_grad[3] and not soft) else None
         return ds, None, dthr, dthx, None, None, None, None
 
 

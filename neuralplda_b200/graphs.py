@@ -57,7 +57,7 @@ class GraphedTrainStep:
 
     def _body(self, i1, i2, t):
         self.optimizer.zero_grad(set_to_none=False)                 # static .grad buffers: the graph accumulates into them
-        x1, x2 = _gather(self.tab, i1, i2)
+        x1, x2 = _gather(self.tab, i1, i2, lazy=False)
         loss = self.model.loss(self.model(x1, x2), t)
         loss.backward()
         self.optimizer.step()

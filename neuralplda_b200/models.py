@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from . import _lib, functional as F_
 from . import kaldi_io_lite
+from .lazy import dense, lazy_pair
 
 _TRANSIENT = ("_packed", "_impl", "_group", "_alpha_cache")
 
@@ -166,6 +167,19 @@ class _PldaBase(nn.Module):
             minc_avg = out_min.sum() / len(self.beta)
         return minc_avg, minc_threshold
 
+    def _forward_lazy(self, kind, x1, x2):
+        """Scores for a pair of lazily gathered loader outputs (lazy.py) straight from (table, row indices): the
+        materialised [B, D] pair the reference's loop passes between its loader and forward is never written.  Returns
+        None when that shortcut does not apply (gradients wanted, or the rows were already materialised)."""
+        lp = lazy_pair(x1, x2)
+        if lp is None or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            return None
+        tab, r1, r2 = lp
+        from .sv_trials_loaders import bad_flag_of
+        scores, _ = F_.score_indexed(kind, tab.table, r1, r2, self._params(), self._dims(), self.packed, self.impl,
+                                     flag_ptr=bad_flag_of(tab).ptr)
+        return scores
+
     def SaveModel(self, filename):
         with open(filename, 'wb') as f:
             pickle.dump(self, f)
@@ -194,7 +208,10 @@ class NeuralPlda(_PldaBase):
                 self.centering_and_wccn_plda.weight, self.centering_and_wccn_plda.bias, self.P_sqrt, self.Q)
 
     def forward(self, x1, x2):
-        return F_.NpldaScoreFn.apply(x1, x2, *self._params(), self.packed, self.impl)
+        s = self._forward_lazy("nplda", x1, x2)
+        if s is not None:
+            return s
+        return F_.NpldaScoreFn.apply(dense(x1), dense(x2), *self._params(), self.packed, self.impl, torch.is_grad_enabled())
 
     def forward_indexed(self, table, idx1, idx2, embed_once=None, use_split=None):
         """Scores for trials given as row indices into a device-resident x-vector table (no gradient).
@@ -219,7 +236,7 @@ class NeuralPlda(_PldaBase):
         return F_.embed("nplda", x, self._params(), self._dims(), self.packed)
 
     def forward_from_plda_embeddings(self, x1, x2):
-        return F_.score_from_embeddings("nplda", x1, x2, self._params(), self._dims(), self.packed)
+        return F_.score_from_embeddings("nplda", dense(x1), dense(x2), self._params(), self._dims(), self.packed)
 
     def LoadPldaParamsFromKaldi(self, mean_vec_file, transform_mat_file, PldaFile):
         """models.py:441-457 without the Kaldi binaries (files parsed directly)."""
@@ -254,7 +271,10 @@ class DPlda(_PldaBase):
                 self.logistic_regres.weight, self.logistic_regres.bias)
 
     def forward(self, x1, x2):
-        return F_.DpldaScoreFn.apply(x1, x2, *self._params(), self.packed, self.impl)
+        s = self._forward_lazy("dplda", x1, x2)
+        if s is not None:
+            return s
+        return F_.DpldaScoreFn.apply(dense(x1), dense(x2), *self._params(), self.packed, self.impl, torch.is_grad_enabled())
 
     def forward_indexed(self, table, idx1, idx2, embed_once=None):
         with torch.no_grad():
@@ -272,7 +292,7 @@ class DPlda(_PldaBase):
         return F_.embed("dplda", x, self._params(), self._dims(), self.packed)
 
     def forward_from_plda_embeddings(self, x1, x2):
-        return F_.score_from_embeddings("dplda", x1, x2, self._params(), self._dims(), self.packed)
+        return F_.score_from_embeddings("dplda", dense(x1), dense(x2), self._params(), self._dims(), self.packed)
 
     def LoadParamsFromKaldi(self, mean_vec_file, transform_mat_file):
         """models.py:551-563 without the Kaldi binaries."""

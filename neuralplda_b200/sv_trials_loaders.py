@@ -20,6 +20,10 @@ import torch
 from torch.utils.data import TensorDataset, DataLoader, ConcatDataset, Subset
 
 from ._lib import check, lib, on_device, ptr, stream_ptr
+from .lazy import GatheredRows, PairGather
+
+# Under torch.no_grad() the loaders return lazily gathered rows (lazy.py): forward() scores them straight from the table.
+LAZY_GATHER = True
 
 
 class XvectorTable:
@@ -134,12 +138,16 @@ class _BadIndexFlag:
                            "(the reference raises KeyError from its dict lookup)")
 
 
-def _gather(tab, r1, r2):
-    """(X1, X2) = (table[r1], table[r2]) on the device, one launch (nplda_gather_pairs)."""
+def bad_flag_of(tab):
     flag = tab.__dict__.get("_bad_flag")
     if flag is None:
         flag = tab._bad_flag = _BadIndexFlag()
-    flag.check()
+    return flag
+
+
+def _gather_now(tab, r1, r2):
+    """(X1, X2) = (table[r1], table[r2]) on the device, one launch (nplda_gather_pairs)."""
+    flag = bad_flag_of(tab)
     n, d = r1.numel(), tab.table.shape[1]
     x1 = torch.empty(n, d, dtype=torch.float32, device=tab.device)
     x2 = torch.empty(n, d, dtype=torch.float32, device=tab.device)
@@ -147,6 +155,17 @@ def _gather(tab, r1, r2):
         check(lib().nplda_gather_pairs(ptr(tab.table), tab.table.shape[0], d, ptr(r1), ptr(r2), n, ptr(x1), ptr(x2),
                                        flag.ptr, stream_ptr()), "nplda_gather_pairs")
     return x1, x2
+
+
+def _gather(tab, r1, r2, lazy=None):
+    """The loaders' return value: the materialised pair, or -- under no_grad -- its lazily gathered stand-in."""
+    bad_flag_of(tab).check()
+    if lazy is None:
+        lazy = LAZY_GATHER and not torch.is_grad_enabled()
+    if lazy and r1.numel() > 0:
+        state = PairGather(tab, r1, r2, _gather_now)
+        return GatheredRows(state, 0), GatheredRows(state, 1)
+    return _gather_now(tab, r1, r2)
 
 
 def _device_rows(tab, num_to_id_dict, data, device):

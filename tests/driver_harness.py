@@ -203,10 +203,20 @@ def main():
         return out
 
     def minc_spy(self, output, target, update_thresholds=False, showplots=False):
+        # what validate() itself computed just before calling minc (xvector_NeuralPlda_pytorch.py:67-69), with the
+        # thresholds the model holds at that point; hard decisions also as raw counts (a score that EQUALS a threshold
+        # -- minc picks thresholds among the scores -- may fall on either side when two implementations differ in the
+        # last bits, so the test compares counts with a tolerance of a few trials instead of the normalised cost)
+        th_now = [float(self.threshold[b].detach()) for b in self.beta]
+        s, tg = output.detach().float().cpu(), target.detach().float().cpu()
+        rec = {"n": int(output.numel()), "n_target": int(tg.sum()), "softcdet": float(self.softcdet(output, target)),
+               "cdet": float(self.cdet(output, target)), "thresholds_before": th_now,
+               "miss_counts": [int(((s < th) & (tg > 0.5)).sum()) for th in th_now],
+               "fa_counts": [int(((s > th) & (tg < 0.5)).sum()) for th in th_now],
+               "score_mean": float(s.double().mean()), "score_std": float(s.double().std())}
         mc, th = orig_minc(self, output, target, update_thresholds, showplots)
-        record["validate"].append({"n": int(output.numel()), "minc": float(mc), "softcdet": float(self.softcdet(output, target)),
-                                   "cdet": float(self.cdet(output, target)),
-                                   "thresholds": {str(b): float(v) for b, v in th.items()}})
+        rec.update({"minc": float(mc), "thresholds": {str(b): float(v) for b, v in th.items()}})
+        record["validate"].append(rec)
         return mc, th
 
     cls.loss, cls.minc = loss_spy, minc_spy

@@ -47,6 +47,23 @@ def make_dplda(kp, ref_out, impl=None):
     return m
 
 
+_BWD = {"gemm": 0, "emit": 0, "du": 0}
+_CODE = {None: 0, "simt": 1, "tc": 2, "0": 1, "1": 2}
+
+
+def bwd_paths(**kw):
+    """Force pieces of the backward (nplda_debug_backward_paths): gemm="simt"|"tc", emit="0"|"1", du="0"|"1"; None = auto."""
+    for k, v in kw.items():
+        _BWD[k] = _CODE[v]
+    _lib.lib().nplda_debug_backward_paths(_BWD["gemm"], _BWD["emit"], _BWD["du"])
+
+
+@pytest.fixture(autouse=True)
+def _reset_bwd_paths():
+    yield
+    bwd_paths(gemm=None, emit=None, du=None)
+
+
 IMPLS = [npl.IMPL_SIMT, npl.IMPL_AUTO]       # AUTO = tcgen05 kernel for the reference dims (512-170-170)
 
 
@@ -71,9 +88,12 @@ def test_nplda_forward_ragged_sizes(kaldi_params, cfg1, impl, n):
     with torch.no_grad():
         s = m(x1[:n].to(DEV), x2[:n].to(DEV))
     assert s.shape == (n,)
-    ok, worst = parity_ok(s, ref, rel=1e-4)
-    assert ok or n < 8, worst          # rms of a handful of scores is not a meaningful scale
-    np.testing.assert_allclose(s.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-4)
+    # the SURVEY 8d criterion with the scale of the WHOLE 10k workload (the rms of one or two scores is not a scale):
+    # |S - S_ref| <= 1e-4 * max(|S_ref|, rms(S_ref over configs[0]))
+    full = O.nplda_score(x1, x2, kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"]).double()
+    bound = 1e-4 * torch.maximum(ref.double().abs(), full.pow(2).mean().sqrt())
+    err = (s.cpu().double() - ref.double()).abs()
+    assert bool((err <= bound).all()), float((err / bound).max())
 
 
 def test_tc_kernel_is_selected_and_deterministic(kaldi_params, cfg1):
@@ -106,12 +126,12 @@ def test_tc_kernel_is_selected_and_deterministic(kaldi_params, cfg1):
 def test_tc_f8_mode_parity_and_range_guard(ref_out, kaldi_params, cfg1):
     """IMPL_TC_F8 (layer 1 as fp16*fp16 + two e4m3*e4m3 products on one accumulator): 1e-4 parity on the golden
     10k config and on ragged sizes; inputs outside the range the e4m3 terms cover must be recomputed on the
-    device by the bf16x3 kernel (bit-identical to IMPL_TC), and a later in-range call must again take the fp8 path
+    device by the bf16x3 kernel (bit-identical to IMPL_TC_BF16), and a later in-range call must again take the fp8 path
     (the guard slot is cleared)."""
     x1, x2, _ = cfg1
     a, b = x1.to(DEV), x2.to(DEV)
     m = make_nplda(kaldi_params, npl.IMPL_TC_F8)
-    mt = make_nplda(kaldi_params, npl.IMPL_TC)
+    mt = make_nplda(kaldi_params, npl.IMPL_TC_BF16)
     with torch.no_grad():
         s = m(a, b)
         ok, worst = parity_ok(s, torch.from_numpy(ref_out["c1_scores"]), rel=1e-4)
@@ -131,6 +151,43 @@ def test_tc_f8_mode_parity_and_range_guard(ref_out, kaldi_params, cfg1):
         assert torch.equal(m(one_bad, b), mt(one_bad, b))
         again = m(a, b)                                            # guard cleared: fp8 path again, same bits as before
         assert torch.equal(again, s)
+
+
+def test_tc_fp16x3_mode_parity_and_range_guard(ref_out, kaldi_params, cfg1):
+    """IMPL_TC = "fp16x3" (both layers as split fp16, weights scaled into range at pack time): closer to the reference
+    than bf16x3 on the golden 10k config (bound 1e-4; measured ~0.04 of it against 0.13), different bits from bf16x3;
+    inputs outside fp16's range (|x| >= 2048 after the kernel's 2^4 scaling, inf) are recomputed on the device by the
+    bf16x3 kernel -- bit-identical to IMPL_TC_BF16 -- and NaN inputs give NaN scores as in the reference; the guard slot
+    is cleared afterwards.  IMPL_AUTO scores with the bf16x3 arithmetic (the fastest)."""
+    x1, x2, _ = cfg1
+    a, b = x1.to(DEV), x2.to(DEV)
+    m16 = make_nplda(kaldi_params, npl.IMPL_TC)
+    mb = make_nplda(kaldi_params, npl.IMPL_TC_BF16)
+    ma = make_nplda(kaldi_params, npl.IMPL_AUTO)
+    ref = torch.from_numpy(ref_out["c1_scores"])
+    kp = kaldi_params
+    with torch.no_grad():
+        s16, sb = m16(a, b), mb(a, b)
+        ok16, w16 = parity_ok(s16, ref, rel=1e-4)
+        okb, wb = parity_ok(sb, ref, rel=1e-4)
+        assert ok16 and okb and w16 < 0.6 * wb, (w16, wb)
+        assert not torch.equal(s16, sb) and torch.equal(ma(a, b), sb)
+        for n in (1, 63, 65, 1000, 4097):
+            r = O.nplda_score(x1[:n], x2[:n], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+            np.testing.assert_allclose(m16(a[:n], b[:n]).cpu().numpy(), r.numpy(), rtol=1e-4, atol=1e-4)
+        for scale in (1.0e3, 1.0e5):                               # |x| 2^4 beyond fp16 -> guarded bf16x3 pass
+            got, want = m16(a * scale, b * scale), mb(a * scale, b * scale)
+            assert torch.equal(got, want), scale
+        small = m16(a * 1e-3, b * 1e-3)                            # small inputs stay on the fp16x3 path and stay accurate
+        r = O.nplda_score(x1 * 1e-3, x2 * 1e-3, kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+        ok, worst = parity_ok(small, r, rel=1e-4)
+        assert ok, worst
+        one_bad = a.clone(); one_bad[777, 5] = float("inf")
+        assert torch.equal(m16(one_bad, b).nan_to_num(7.0), mb(one_bad, b).nan_to_num(7.0))
+        nan_in = a.clone(); nan_in[12, 3] = float("nan")
+        out = m16(nan_in, b)
+        assert bool(torch.isnan(out[12])) and bool(torch.isfinite(out[:12]).all()) and bool(torch.isfinite(out[13:]).all())
+        assert torch.equal(m16(a, b), s16)                         # guard cleared: the fp16x3 path again, same bits
 
 
 def test_empty_input(kaldi_params):
@@ -349,13 +406,13 @@ def test_minc_quirks_gpu(ref_out, kaldi_params):
     assert [float(th[b]) for b in NC.beta] == [float(oth[b]) for b in NC.beta]
 
 
-def _check_grads(model, ref_out, prefix, names, rtol=2e-3):
+def _check_grads(model, ref_out, prefix, names, rtol=1e-4):
     got = dict(model.named_parameters())
     for n in names:
         sample = ref_out[f"{prefix}_grad_{n}_sample"]
         p = got[n]
-        if sample.size == 0:
-            assert p.grad is None or float(p.grad.abs().sum()) == 0.0, n
+        if sample.size == 0:      # the reference's autograd leaves .grad None (Adam with weight decay then skips the parameter)
+            assert p.grad is None, n
             continue
         assert p.grad is not None, n
         g = p.grad.reshape(-1).cpu()
@@ -481,8 +538,8 @@ def test_scorefile_generation_matches_reference_files(tmp_path, kaldi_params):
 
 
 def test_large_properties_1m(kaldi_params):
-    """BASELINE.json configs[1] size: 1M pairs.  Oracle on a strided subsample, plus
-    size-independent properties: pair symmetry S(x1,x2)=S(x2,x1) and chunking invariance."""
+    """BASELINE.json configs[1] size: 1M pairs.  EVERY pair against the CPU oracle ("the CPU oracle checks
+    all pairs for <= 1 M"), plus size-independent properties: pair symmetry S(x1,x2)=S(x2,x1) and chunking invariance."""
     mean = kaldi_params["mean"].to(DEV)
     g = torch.Generator(device=DEV).manual_seed(1002)
     n = 1_000_000
@@ -492,6 +549,8 @@ def test_large_properties_1m(kaldi_params):
     x1 = mean + spk[s1] + 0.7 * torch.randn(n, 512, generator=g, device=DEV)
     x2 = mean + spk[s2] + 0.7 * torch.randn(n, 512, generator=g, device=DEV)
     kp = kaldi_params
+    ref = torch.cat([O.nplda_score(x1[c:c + 100_000].cpu(), x2[c:c + 100_000].cpu(), kp["W1"], kp["b1"], kp["W2"], kp["b2"],
+                                   kp["P_sqrt"], kp["Q"]) for c in range(0, n, 100_000)])
     for impl in IMPLS:
         m = make_nplda(kp, impl)
         with torch.no_grad():
@@ -502,9 +561,7 @@ def test_large_properties_1m(kaldi_params):
         np.testing.assert_allclose(s.cpu().numpy(), s_sw.cpu().numpy(), rtol=1e-4, atol=1e-4)
         ok, worst = parity_ok(s_part, s.cpu(), rel=1e-4)
         assert ok, worst
-        idx = torch.arange(0, n, 97, device=DEV)
-        ref = O.nplda_score(x1[idx].cpu(), x2[idx].cpu(), kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
-        ok, worst = parity_ok(s[idx], ref, rel=1e-4)
+        ok, worst = parity_ok(s, ref, rel=1e-4)                     # all 1,000,000 pairs
         assert ok, worst
 
 
@@ -813,7 +870,7 @@ def test_mixed_impl_without_and_with_mixed_image(kaldi_params, cfg1):
     out = torch.empty(4096, device=DEV)
     _lib.check(_lib.lib().nplda_score_fwd(_lib.ptr(a), _lib.ptr(b), 4096, 512, 170, 170, _lib.ptr(pack), _lib.ptr(out),
                                           npl.IMPL_TC_F8, _lib.stream_ptr()), "nplda_score_fwd")
-    m.impl = npl.IMPL_TC
+    m.impl = npl.IMPL_TC_BF16
     with torch.no_grad():
         s_tc = m(a, b)
     assert torch.equal(out, s_tc)                                # the fallback pass is the bf16x3 kernel
@@ -867,14 +924,14 @@ def test_tensor_core_weight_gradients(ref_out, kaldi_params, cfg1, kind):
     a, b, y = x1[:n].to(DEV), x2[:n].to(DEV), t[:n].to(DEV)
     grads = {}
     for mode in ("simt", "tc"):
-        os.environ["NPLDA_BWD_GEMM"] = mode
+        bwd_paths(gemm=mode)
         try:
             m = make_nplda(kaldi_params, loss="crossentropy") if kind == "nplda" else make_dplda(kaldi_params, ref_out)
             m.loss(m(a, b), y).backward()
             torch.cuda.synchronize()
             grads[mode] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
         finally:
-            os.environ.pop("NPLDA_BWD_GEMM", None)
+            bwd_paths(gemm=None)
     assert set(grads["tc"]) == set(grads["simt"]) and len(grads["tc"]) >= 4
     for k, gs in grads["simt"].items():
         scale = float(gs.abs().max()) + 1e-30
@@ -885,7 +942,7 @@ def test_tensor_core_weight_gradients(ref_out, kaldi_params, cfg1, kind):
 def test_tensor_core_weight_gradients_vs_reference_autograd(ref_out, kaldi_params, cfg1, lossname, monkeypatch):
     """Same golden check as test_nplda_training_step_gradients (the unmodified reference's .grad on 2048 pairs), with
     the tensor-core contraction forced for this small batch."""
-    monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
+    bwd_paths(gemm="tc")
     test_nplda_training_step_gradients(ref_out, kaldi_params, cfg1, lossname)
 
 
@@ -946,8 +1003,8 @@ def test_backward_with_emitted_activations(ref_out, kaldi_params, cfg1, kind):
     grads = {}
     for variant, save, emit in (("fp32", False, "0"), ("emit_in_backward", False, "1"), ("saved_by_forward", True, None)):
         if emit is not None:
-            os.environ["NPLDA_BWD_EMIT"] = emit
-        os.environ["NPLDA_BWD_GEMM"] = "simt"
+            bwd_paths(emit=emit)
+        bwd_paths(gemm="simt")
         try:
             m = make_nplda(kaldi_params, loss="SoftCdet") if kind == "nplda" else make_dplda(kaldi_params, ref_out)
             m.packed.save_activations = save
@@ -958,8 +1015,8 @@ def test_backward_with_emitted_activations(ref_out, kaldi_params, cfg1, kind):
             grads[variant] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
             grads[variant]["x1"], grads[variant]["x2"], grads[variant]["scores"] = a.grad.clone(), b.grad.clone(), out.detach().clone()
         finally:
-            os.environ.pop("NPLDA_BWD_EMIT", None)
-            os.environ.pop("NPLDA_BWD_GEMM", None)
+            bwd_paths(emit=None)
+            bwd_paths(gemm=None)
     for variant in ("emit_in_backward", "saved_by_forward"):
         for k, g0 in grads["fp32"].items():
             scale = float(g0.abs().max()) + 1e-30
@@ -986,8 +1043,8 @@ def test_saved_activations_survive_retain_graph(kaldi_params, cfg1):
 @pytest.mark.parametrize("lossname", ["SoftCdet", "crossentropy"])
 def test_emitted_activations_vs_reference_autograd(ref_out, kaldi_params, cfg1, lossname, monkeypatch):
     """The golden .grad of the unmodified reference (2048 pairs) with both tensor-core pieces of the backward forced."""
-    monkeypatch.setenv("NPLDA_BWD_EMIT", "1")
-    monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
+    bwd_paths(emit="1")
+    bwd_paths(gemm="tc")
     test_nplda_training_step_gradients(ref_out, kaldi_params, cfg1, lossname)
 
 
@@ -1016,7 +1073,7 @@ def test_saved_activations_vs_reference_autograd(ref_out, kaldi_params, cfg1, lo
     """The golden .grad of the unmodified reference (2048 pairs) through the default large-batch training path:
     activations saved by the tensor-core forward, tensor-core dL/du pass and weight gradients."""
     monkeypatch.setattr(F_, "SAVE_ACTIVATIONS_MIN_PAIRS", 1)
-    monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
+    bwd_paths(gemm="tc")
     launches0 = _lib.launch_count()
     test_nplda_training_step_gradients(ref_out, kaldi_params, cfg1, lossname)
     assert _lib.launch_count() > launches0
@@ -1024,7 +1081,7 @@ def test_saved_activations_vs_reference_autograd(ref_out, kaldi_params, cfg1, lo
 
 def test_dplda_saved_activations_vs_reference_autograd(ref_out, kaldi_params, cfg1, monkeypatch):
     monkeypatch.setattr(F_, "SAVE_ACTIVATIONS_MIN_PAIRS", 1)
-    monkeypatch.setenv("NPLDA_BWD_GEMM", "tc")
+    bwd_paths(gemm="tc")
     test_dplda_training_step_gradients(ref_out, kaldi_params, cfg1)
 
 
@@ -1080,7 +1137,7 @@ def test_backward_ragged_small_batches(ref_out, kaldi_params, cfg1, kind, n):
     res = {}
     for variant in ("default", "fp32"):
         if variant == "fp32":
-            os.environ["NPLDA_BWD_EMIT"] = "0"; os.environ["NPLDA_BWD_GEMM"] = "simt"
+            bwd_paths(emit="0"); bwd_paths(gemm="simt")
         try:
             m = make_nplda(kaldi_params, loss="crossentropy") if kind == "nplda" else make_dplda(kaldi_params, ref_out)
             m.packed.save_activations = variant == "default"
@@ -1089,7 +1146,7 @@ def test_backward_ragged_small_batches(ref_out, kaldi_params, cfg1, kind, n):
             torch.cuda.synchronize()
             res[variant] = (loss.item(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
         finally:
-            os.environ.pop("NPLDA_BWD_EMIT", None); os.environ.pop("NPLDA_BWD_GEMM", None)
+            bwd_paths(emit=None); bwd_paths(gemm=None)
     assert res["default"][0] == pytest.approx(res["fp32"][0], rel=1e-5, abs=1e-7)
     for k, g0 in res["fp32"][1].items():
         scale = float(g0.abs().max()) + 1e-30

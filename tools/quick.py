@@ -21,7 +21,7 @@ def run(impl, cnt):
     _lib.check(lib.nplda_score_fwd(_lib.ptr(x1), _lib.ptr(x2), cnt, 512, 170, 170, _lib.ptr(pack), _lib.ptr(out), impl, _lib.stream_ptr()), "k1")
     return out
 worst_all = 0.0
-IMPLS = {"tc": npl.IMPL_TC, "f8": npl.IMPL_TC_F8}
+IMPLS = {"tc": npl.IMPL_TC, "f8": npl.IMPL_TC_F8, "bf16": npl.IMPL_TC_BF16}
 which = os.environ.get("IMPLS", "tc,f8").split(",")
 for cnt in (1, 63, 64, 65, 9471, 9472, 100_003, 1_000_000):
     ref = run(npl.IMPL_SIMT, cnt).double()
@@ -34,7 +34,7 @@ if "f8" in which:       # range guard: scaled inputs must be recomputed by the b
     keep = (x1, x2)
     for sc in (1e-3, 0.05, 300.0):
         x1, x2 = keep[0][:200_000] * sc, keep[1][:200_000] * sc
-        ref = run(npl.IMPL_SIMT, 200_000).double(); got = run(npl.IMPL_TC_F8, 200_000).double(); tc = run(npl.IMPL_TC, 200_000).double()
+        ref = run(npl.IMPL_SIMT, 200_000).double(); got = run(npl.IMPL_TC_F8, 200_000).double(); tc = run(npl.IMPL_TC_BF16, 200_000).double()
         bound = 1e-4 * torch.maximum(ref.abs(), ref.pow(2).mean().sqrt())
         w = float(((got - ref).abs() / bound).max()); worst_all = max(worst_all, w)
         print(f"guard x*{sc}: worst/bound {w:.3f}, identical to IMPL_TC: {bool((got == tc).all())}", flush=True)

@@ -22,7 +22,7 @@ for impl in (npl.IMPL_TC, npl.IMPL_TC_F8, npl.IMPL_SIMT):
 m.impl = npl.IMPL_AUTO
 loss = m.loss(m(a[:4096], b[:4096]), y[:4096]); loss.backward()
 # tensor-core backward pieces (EMIT pass + tcgen05 weight gradients) and the DPlda tensor-core forward / backward
-os.environ["NPLDA_BWD_EMIT"] = "1"; os.environ["NPLDA_BWD_GEMM"] = "tc"
+_lib.lib().nplda_debug_backward_paths(2, 2, 0)
 n_tc = 8192 + 37
 loss = m.loss(m(a[:n_tc], b[:n_tc]), y[:n_tc]); loss.backward()
 class NCD(bench.NC):
@@ -31,7 +31,7 @@ d = npl.DPlda(NCD).to(dev)
 d.state_dict()["centering_and_LDA.weight"].copy_(kp["W1"]); d.state_dict()["centering_and_LDA.bias"].copy_(kp["b1"])
 ld = d.loss(d(a[:n_tc], b[:n_tc]), y[:n_tc]); ld.backward()
 print("tc backward", float(loss), float(ld), float(d.logistic_regres.weight.grad.abs().sum()))
-os.environ.pop("NPLDA_BWD_EMIT"); os.environ.pop("NPLDA_BWD_GEMM")
+_lib.lib().nplda_debug_backward_paths(0, 0, 0)
 table, i1, i2, _ = O.synth_grid(40, 50, 7, seed=2, mean=kp["mean"])
 s, f = m.forward_indexed(table.to(dev), i1.to(dev), i2.to(dev))
 s, f = m.forward_indexed(table.to(dev), i1.to(dev), i2.to(dev), embed_once=False)
