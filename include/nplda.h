@@ -206,6 +206,12 @@ int nplda_score_pairs(const float *rowtab, int64_t n_rows, const int64_t *idx1, 
 int nplda_score_grid(const float *rowtab, int64_t n_rows, const int64_t *enrol_rows, int64_t n_enrol,
                      const int64_t *test_rows, int64_t n_test, float *scores, int64_t ld_scores,
                      int32_t *bad_index_flag, void *stream);
+/* The same with the kernel chosen: NPLDA_IMPL_AUTO / NPLDA_IMPL_TC = the tcgen05 kernel (csrc/grid_tc.cu: rows gathered by
+ * TMA from the fp16 hi/lo grid operands nplda_table_prepare leaves behind the rows, r[i] + r[j] folded into the
+ * contraction), NPLDA_IMPL_SIMT = the fp32 FFMA2 kernel. */
+int nplda_score_grid_impl(const float *rowtab, int64_t n_rows, const int64_t *enrol_rows, int64_t n_enrol,
+                          const int64_t *test_rows, int64_t n_test, float *scores, int64_t ld_scores,
+                          int32_t *bad_index_flag, int impl, void *stream);
 
 /* ---------------------------------------------------------------------------
  * K2: loss / detection-cost accumulators.

@@ -76,6 +76,7 @@ SIGNATURES = {
     "nplda_minc_sweep": (c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
                                  ctypes.POINTER(ctypes.c_double), c_int, c_vp, c_vp, c_vp]),
     "nplda_score_grid": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "nplda_score_grid_impl": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_vp]),
     "nplda_cohort_stats": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "nplda_score_norm": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nplda_trials_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),

@@ -64,6 +64,14 @@ inline bool dims_supported(int d_in, int d1, int d2) {
     return d_in >= 1 && d1 >= 1 && d2 >= 1 && d1 <= NP && d2 <= NP;
 }
 
+// ---- row table of the trial-list / grid paths (pairs.cu, grid.cu, grid_tc.cu) ----------------
+// [n_rows][2 * 176] fp32 rows {A | B}  |  256-byte trailer {u64 fingerprint the rows were built from, at +64: grid
+// operand header floats}  |  (1024-aligned) grid operands [n_rows][1536 B] fp16 hi/lo (grid_tc.cu)
+constexpr int ROWTAB_LD = 176, ROWTAB_FLOATS = 2 * ROWTAB_LD;
+inline int64_t rowtab_trailer_offset(int64_t n_rows) { return n_rows * ROWTAB_FLOATS * (int64_t)sizeof(float); }
+inline int64_t rowtab_gtab_offset(int64_t n_rows) { return (rowtab_trailer_offset(n_rows) + 256 + 1023) / 1024 * 1024; }
+int64_t gtab_bytes(int64_t n_rows);      // grid_tc.cu
+
 // ---- bookkeeping --------------------------------------------------------------
 void count_launch(int n = 1);            // api.cu
 int sm_count();                          // api.cu (cached per process)

@@ -18,6 +18,10 @@
 #include "common.cuh"
 
 namespace nplda {
+
+int score_grid_tc(const uint8_t *gtab, const float *hdr, int64_t n_rows, const int64_t *er, int64_t E, const int64_t *tr, int64_t T,
+                  float *scores, int64_t ld, int32_t *bad_flag, cudaStream_t st);   // grid_tc.cu
+
 namespace grid {
 
 constexpr int ROW_LD = 176, ROW_FLOATS = 2 * ROW_LD;     // row table geometry (pairs.cu)
@@ -174,12 +178,16 @@ __global__ void __launch_bounds__(NT, 2) score_grid_kernel(Args g) {
 
 using namespace nplda;
 
-extern "C" int nplda_score_grid(const float *rowtab, int64_t n_rows, const int64_t *enrol_rows, int64_t n_enrol,
-                                const int64_t *test_rows, int64_t n_test, float *scores, int64_t ld_scores,
-                                int32_t *bad_index_flag, void *stream) {
+extern "C" int nplda_score_grid_impl(const float *rowtab, int64_t n_rows, const int64_t *enrol_rows, int64_t n_enrol,
+                                     const int64_t *test_rows, int64_t n_test, float *scores, int64_t ld_scores,
+                                     int32_t *bad_index_flag, int impl, void *stream) {
     if (n_enrol < 0 || n_test < 0 || n_rows < 0 || ld_scores < n_test) return NPLDA_ERR_BAD_ARG;
     if (n_enrol == 0 || n_test == 0) return NPLDA_OK;
     if (!rowtab || !enrol_rows || !test_rows || !scores || !bad_index_flag || n_rows == 0) return NPLDA_ERR_BAD_ARG;
+    if (impl != NPLDA_IMPL_SIMT)      // the tensor-core kernel over the fp16 hi/lo operands nplda_table_prepare left behind the rows
+        return score_grid_tc((const uint8_t *)rowtab + rowtab_gtab_offset(n_rows),
+                             (const float *)((const char *)rowtab + rowtab_trailer_offset(n_rows) + 64), n_rows, enrol_rows, n_enrol,
+                             test_rows, n_test, scores, ld_scores, bad_index_flag, (cudaStream_t)stream);
     const int64_t tiles = ((n_enrol + grid::TM - 1) / grid::TM) * ((n_test + grid::TN - 1) / grid::TN);
     if (tiles > 0x7fffffff) return NPLDA_ERR_BAD_ARG;
     grid::Args a{rowtab, n_rows, enrol_rows, test_rows, n_enrol, n_test, scores, ld_scores, bad_index_flag,
@@ -187,4 +195,11 @@ extern "C" int nplda_score_grid(const float *rowtab, int64_t n_rows, const int64
     grid::score_grid_kernel<<<(unsigned)tiles, grid::NT, 0, (cudaStream_t)stream>>>(a);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
+}
+
+extern "C" int nplda_score_grid(const float *rowtab, int64_t n_rows, const int64_t *enrol_rows, int64_t n_enrol,
+                                const int64_t *test_rows, int64_t n_test, float *scores, int64_t ld_scores,
+                                int32_t *bad_index_flag, void *stream) {
+    return nplda_score_grid_impl(rowtab, n_rows, enrol_rows, n_enrol, test_rows, n_test, scores, ld_scores, bad_index_flag,
+                                 NPLDA_IMPL_AUTO, stream);
 }

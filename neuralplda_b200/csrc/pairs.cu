@@ -26,6 +26,8 @@ namespace nplda {
 int simt_aux(int mode, const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack,
              float *out, int64_t ld_out, cudaStream_t st, const unsigned long long *fp_cur = nullptr,
              const unsigned long long *fp_built = nullptr);   // score_simt.cu
+int gtab_prepare(const float *rowtab, int64_t n_rows, int row_floats, int row_ld, int d, float *hdr, uint8_t *gtab,
+                 const unsigned long long *fp_cur, const unsigned long long *fp_built, cudaStream_t st);   // grid_tc.cu
 
 constexpr int ROW_LD = 176;              // floats per half row (width <= 175; the last float of A holds r)
 constexpr int ROW_FLOATS = 2 * ROW_LD;
@@ -143,7 +145,7 @@ using namespace nplda;
 
 extern "C" int64_t nplda_rowtab_bytes(int64_t n_rows) {
     if (n_rows < 0) return NPLDA_ERR_BAD_ARG;
-    return n_rows * ROW_FLOATS * (int64_t)sizeof(float) + 256;     // + the fingerprint the rows were built from
+    return rowtab_gtab_offset(n_rows) + gtab_bytes(n_rows);        // rows + trailer (fingerprint, grid header) + grid operands
 }
 
 extern "C" int nplda_table_prepare(const float *table, int64_t n_rows, int d_in, int d1, int d2, const void *pack,
@@ -170,6 +172,10 @@ extern "C" int nplda_table_prepare(const float *table, int64_t n_rows, int d_in,
                                                  g_cur, fp_built);
     }
     NPLDA_LAUNCH_CHECK();
+    // fp16 hi/lo operands of the tensor-core grid kernel (grid_tc.cu), rebuilt together with the rows
+    rc = gtab_prepare(rowtab, n_rows, ROW_FLOATS, ROW_LD, is_dplda ? d1 : d2, (float *)((char *)rowtab + rowtab_trailer_offset(n_rows) + 64),
+                      (uint8_t *)rowtab + rowtab_gtab_offset(n_rows), g_cur, fp_built, st);
+    if (rc != NPLDA_OK) return rc;
     rowtab_commit_kernel<<<1, 1, 0, st>>>(fp_cur, fp_built);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;

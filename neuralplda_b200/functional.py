@@ -428,7 +428,7 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
     return scores, flag
 
 
-def score_grid(kind, table, enrol_rows, test_rows, params, dims, packed):
+def score_grid(kind, table, enrol_rows, test_rows, params, dims, packed, impl=_lib.IMPL_AUTO):
     """[E, T] scores of every enrol row against every test row of `table` (enrol-major trial order): the row
     table of nplda_table_prepare (cached like in score_indexed) and one fp32 grid product (nplda_score_grid)."""
     require_cuda(table, enrol_rows, test_rows)
@@ -449,8 +449,10 @@ def score_grid(kind, table, enrol_rows, test_rows, params, dims, packed):
             raise RuntimeError("empty x-vector table")
         rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
         with on_device(dev):
-            check(lib().nplda_score_grid(ptr(rowtab), table.shape[0], ptr(er), er.numel(), ptr(tr), tr.numel(),
-                                         ptr(scores), tr.numel(), ptr(flag), stream_ptr()), "nplda_score_grid")
+            check(lib().nplda_score_grid_impl(ptr(rowtab), table.shape[0], ptr(er), er.numel(), ptr(tr), tr.numel(),
+                                              ptr(scores), tr.numel(), ptr(flag),
+                                              _lib.IMPL_SIMT if impl == _lib.IMPL_SIMT else _lib.IMPL_AUTO, stream_ptr()),
+                  "nplda_score_grid")
     return scores, flag
 
 

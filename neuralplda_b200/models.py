@@ -227,7 +227,7 @@ class NeuralPlda(_PldaBase):
         """[E, T] scores of every enrol row against every test row of a device-resident x-vector table
         (enrol-major, the order of an enrol x test trial list); no gradient.  Returns (scores, bad_index_flag)."""
         with torch.no_grad():
-            return F_.score_grid("nplda", table, enrol_rows, test_rows, self._params(), self._dims(), self.packed)
+            return F_.score_grid("nplda", table, enrol_rows, test_rows, self._params(), self._dims(), self.packed, self.impl)
 
     # The two half-steps of forward are part of the reference's public surface (models.py:366-376).
     # No reference call site uses them separately (forward is the hot path and never materialises
@@ -286,7 +286,7 @@ class DPlda(_PldaBase):
         """[E, T] scores of every enrol row against every test row of a device-resident x-vector table
         (enrol-major, the order of an enrol x test trial list); no gradient.  Returns (scores, bad_index_flag)."""
         with torch.no_grad():
-            return F_.score_grid("dplda", table, enrol_rows, test_rows, self._params(), self._dims(), self.packed)
+            return F_.score_grid("dplda", table, enrol_rows, test_rows, self._params(), self._dims(), self.packed, self.impl)
 
     def extract_plda_embeddings(self, x):
         return F_.embed("dplda", x, self._params(), self._dims(), self.packed)

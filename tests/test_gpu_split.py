@@ -175,3 +175,51 @@ def test_split_kernel_1m_trials_full_oracle_check(kaldi_params):
     for _ in range(3):                                          # deterministic across launches (no races in the pipelines)
         s2, _ = m.forward_indexed(table.to(DEV), i1.to(DEV), i2.to(DEV), embed_once=False, use_split=True)
         assert torch.equal(s, s2)
+
+
+@pytest.mark.parametrize("kind", ["nplda", "dplda"])
+@pytest.mark.parametrize("shape", [(1, 1), (37, 53), (128, 128), (129, 257), (300, 1001), (1000, 131)])
+def test_grid_tensor_core_kernel_vs_fp32_and_oracle(ref_out, kaldi_params, kind, shape):
+    """K5-TC (csrc/grid_tc.cu): enrol x test grids on tcgen05 with r[i] + r[j] folded into the contraction, against the
+    fp32 FFMA2 grid kernel and the CPU oracle on the gathered pairs; ragged tiles, repeated and permuted rows, a
+    strided output is not needed (ld = T), bad indices flagged."""
+    from test_gpu_parity import make_dplda
+    kp = kaldi_params
+    E, T = shape
+    table = _table(kp, 700, 31 + E)
+    g = torch.Generator().manual_seed(E * 7 + T)
+    er, tr = torch.randint(0, 700, (E,), generator=g), torch.randint(0, 700, (T,), generator=g)
+    if kind == "nplda":
+        m = make_nplda(kp)
+        oracle = lambda a, b: O.nplda_score(a, b, kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    else:
+        m = make_dplda(kp, ref_out)
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        oracle = lambda a, b: O.dplda_score(a, b, sd["centering_and_LDA.weight"], sd["centering_and_LDA.bias"],
+                                            sd["logistic_regres.weight"], sd["logistic_regres.bias"])
+    t = table.to(DEV)
+    s_tc, flag = m.forward_grid(t, er.to(DEV), tr.to(DEV))
+    assert s_tc.shape == (E, T) and int(flag) == 0
+    m.impl = npl.IMPL_SIMT
+    s_f32, _ = m.forward_grid(t, er.to(DEV), tr.to(DEV))
+    m.impl = npl.IMPL_AUTO
+    i1, i2 = er.repeat_interleave(T), tr.repeat(E)
+    ref = oracle(table[i1], table[i2]).reshape(E, T)
+    scale = torch.maximum(ref.abs(), ref.pow(2).mean().sqrt() if E * T >= 64 else torch.tensor(0.5)).double()
+    for name, s in (("tc", s_tc), ("fp32", s_f32)):
+        worst = float(((s.cpu().double() - ref.double()).abs() / (1e-4 * scale)).max())
+        assert worst <= 1.0, (name, worst)
+    assert float(((s_tc - s_f32).abs().cpu().double() / scale).max()) <= 2e-5
+    bad = er.clone(); bad[0] = 700
+    _, flag = m.forward_grid(t, bad.to(DEV), tr.to(DEV))
+    assert int(flag) != 0
+    s_again, flag = m.forward_grid(t, er.to(DEV), tr.to(DEV))      # cached rows + cached grid operands: same bits
+    assert int(flag) == 0 and torch.equal(s_again, s_tc)
+    with torch.no_grad():                                          # a parameter update rebuilds rows AND grid operands
+        p = m.Q if kind == "nplda" else m.logistic_regres.bias
+        p.add_(0.01)
+    s_new, _ = m.forward_grid(t, er.to(DEV), tr.to(DEV))
+    assert not torch.equal(s_new, s_tc)
+    m.impl = npl.IMPL_SIMT
+    s_new32, _ = m.forward_grid(t, er.to(DEV), tr.to(DEV))
+    assert float(((s_new - s_new32).abs().cpu().double() / scale).max()) <= 2e-5

@@ -29,6 +29,18 @@ for ne, nt, spk, seed in ((2500, 4000, 500, 1003), (5000, 10000, 700, 1004)):
     got = s.flatten()[sub.to(dev)].cpu().double()
     bound = 1e-4 * torch.maximum(ref.abs(), ref.pow(2).mean().sqrt())
     print(f"{ne} x {nt}: parity on {sub.numel()} strided trials: worst/bound {float(((got - ref).abs() / bound).max()):.3f}")
+    from neuralplda_b200 import _lib
+    rowtab = m.packed.get_rowtab("nplda", t, m._params(), 512, 170, 170)
+    sc, flag = torch.empty(ne, nt, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+    for impl, nm in ((_lib.IMPL_AUTO, "tcgen05"), (_lib.IMPL_SIMT, "fp32 FFMA2")):
+        k = lambda: _lib.check(_lib.lib().nplda_score_grid_impl(_lib.ptr(rowtab), t.shape[0], _lib.ptr(er), ne, _lib.ptr(tr), nt, _lib.ptr(sc), nt,
+                                                                _lib.ptr(flag), impl, _lib.stream_ptr()), "grid")
+        k(); torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()                    # 20 launches per graph replay: no host time between the kernels
+        with torch.cuda.graph(gr):
+            for _ in range(20): k()
+        msk = timeit(gr.replay, 5) / 20
+        print(f"  kernel alone ({nm}): {msk * 1e3:.1f} us -> {n / msk / 1e6:.1f} G trials/s, {4 * n / msk / 1e6:.0f} GB/s of scores")
     ms = timeit(lambda: m.forward_grid(t, er, tr))
     print(f"  grid, rows cached: {ms:.3f} ms -> {n / ms / 1e6:.1f} G trials/s, {2 * 176 * n / ms / 1e9:.1f} TFLOP/s fp32, "
           f"{4 * n / ms / 1e6:.0f} GB/s of scores")
