@@ -113,10 +113,11 @@ int nplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d
  *   S = u1^T(Wb+Wb^T)u2 + u1^T Ww u1 + u2^T Ww u2 + ws.(u1+u2) + c          */
 int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int d_in, int d1,
                     const void *pack, float *scores, int impl, void *stream);
-/* The same with a caller-owned workspace of dplda_fwd_workspace_bytes(n, d_in, d1) bytes (256-byte aligned):
- * for 512-170-like shapes NPLDA_IMPL_AUTO then evaluates layer 1 and the two 170 x 170 forms on the tensor cores
- * (two EMIT passes of the tcgen05 kernel + one finishing kernel, ~3x the fp32 SIMT kernel); without a
- * workspace, or for other shapes, it is dplda_score_fwd. */
+/* The entry the module uses: for 512-170-like shapes NPLDA_IMPL_AUTO evaluates layer 1 and both 170 x 170 forms on the
+ * tensor cores in ONE pass over x (the DPL form of the tcgen05 score kernel: Y_P = a Pm^T, then Y_R = a R^T into the same
+ * accumulator, a re-read from shared memory); for other shapes it is dplda_score_fwd.  The kernel needs no workspace:
+ * dplda_fwd_workspace_bytes returns 0 and `workspace` may be NULL (both kept so that callers written against the
+ * two-pass version keep working). */
 int64_t dplda_fwd_workspace_bytes(int64_t n, int d_in, int d1);
 int dplda_score_fwd_ws(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
                        float *scores, int impl, void *workspace, int64_t workspace_bytes, void *stream);
@@ -272,11 +273,22 @@ int dplda_score_bwd(const float *x1, const float *x2, int64_t n, int d_in, int d
  * Passing that buffer to nplda_score_bwd_act / dplda_score_bwd_act (otherwise identical to the functions above;
  * act == NULL makes them the same) saves the backward its passes of the tensor-core forward kernel.  `act` is
  * only read.  NPLDA_ERR_UNSUPPORTED_DIM for shapes the tcgen05 kernel does not take: use the plain entries. */
-int64_t nplda_act_floats(int64_t n, int is_dplda);
+int64_t nplda_act_floats(int64_t n, int kind);   /* kind: 0 NeuralPlda, 1 DPlda (trainable LDA), 2 DPlda rows u only */
 int nplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2, const void *pack,
                           float *scores, float *act, void *stream);
 int dplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
                           float *scores, float *act, void *stream);
+/* DPlda with the LDA frozen -- what the reference's driver trains (xvector_DPlda_pytorch.py:140-147 sets
+ * requires_grad = False on centering_and_LDA): the forward keeps only the normalised rows u = a / |a|
+ * (urows: nplda_act_floats(n, 2) floats, [2 n][176], side 1 of pair p n rows after side 0) and the gradient of
+ * logistic_regres (autograd through models.py:483-489) is two contractions over the batch on the tensor cores,
+ *   dWw = (Ps + Pd) / 2, dWb = (Ps - Pd) / 2,  Ps = sum_p g_p s_p s_p^T, Pd = sum_p g_p d_p d_p^T,  s = u1 + u2, d = u1 - u2,
+ *   dws = sum_p g_p s_p, dc = sum_p g_p   (g = dscores), ADDED into dw_lr [2 d1^2 + d1] and dc_lr [1] (either may be NULL). */
+int dplda_score_fwd_train_u(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
+                            float *scores, float *urows, void *stream);
+int64_t dplda_lr_bwd_workspace_bytes(int64_t n, int d1);     /* caller-owned, 256-byte aligned */
+int dplda_lr_bwd(const float *urows, int64_t n, int d1, const float *dscores, float *dw_lr, float *dc_lr,
+                 void *workspace, int64_t workspace_bytes, void *stream);
 int nplda_score_bwd_act(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2,
                         const float *W1, const float *b1, const float *W2, const float *b2,
                         const float *p_sqrt, const float *q, const float *dscores, float *dW1,

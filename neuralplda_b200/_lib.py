@@ -73,6 +73,9 @@ SIGNATURES = {
     "nplda_act_floats": (c_i64, [c_i64, c_int]),
     "nplda_score_fwd_train": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "dplda_score_fwd_train": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "dplda_score_fwd_train_u": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "dplda_lr_bwd_workspace_bytes": (c_i64, [c_i64, c_int]),
+    "dplda_lr_bwd": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "nplda_minc_sweep": (c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
                                  ctypes.POINTER(ctypes.c_double), c_int, c_vp, c_vp, c_vp]),
     "nplda_score_grid": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),

@@ -37,7 +37,12 @@ int score_tcx(const void *split, int64_t n_rows, const int64_t *i1, const int64_
 
 bool tc_dplda_ok(const PackLayout &L);   // score_tc.cu
 int dplda_score_tc(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
-                   void *workspace, int64_t workspace_bytes, cudaStream_t st);   // dplda_tc.cu
+                   cudaStream_t st);   // dplda_tc.cu
+int dplda_score_tc_train_u(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+                           float *urows, cudaStream_t st);   // dplda_tc.cu
+int64_t dplda_lr_workspace_bytes(int64_t n, int d1);   // dplda_lr.cu
+int dplda_lr_grad(const float *urows, int64_t n, int64_t cap, int d1, const float *dscores, float *dw_lr, float *dc_lr,
+                  void *workspace, int64_t workspace_bytes, cudaStream_t st);   // dplda_lr.cu
 
 int dplda_score_tc_train(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
                          float *act, cudaStream_t st);   // dplda_tc.cu
@@ -123,7 +128,10 @@ extern "C" int dplda_score_fwd(const float *x1, const float *x2, int64_t n, int 
 // Training forwards: scores plus the activations the backward needs, kept by the caller (act), so that the backward
 // does not run the tensor-core kernel again.  NPLDA_ERR_UNSUPPORTED_DIM for shapes the tcgen05 kernel does not take.
 constexpr int ACT_LD = 176;   // floats per saved activation row (EMIT_LD of score_tc.cu, the backward's row pitch)
-extern "C" int64_t nplda_act_floats(int64_t n, int is_dplda) { return n < 0 ? NPLDA_ERR_BAD_ARG : (is_dplda ? 6 : 4) * n * ACT_LD; }
+// kind: 0 NeuralPlda (a, y), 1 DPlda with a trainable LDA (a, R u, Pm u), 2 DPlda with the LDA frozen (u)
+extern "C" int64_t nplda_act_floats(int64_t n, int kind) {
+    return n < 0 ? NPLDA_ERR_BAD_ARG : (kind == 1 ? 6 : (kind == 2 ? 2 : 4)) * n * ACT_LD;
+}
 
 extern "C" int nplda_score_fwd_train(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2, const void *pack,
                                      float *scores, float *act, void *stream) {
@@ -146,6 +154,31 @@ extern "C" int dplda_score_fwd_train(const float *x1, const float *x2, int64_t n
     return dplda_score_tc_train(x1, x2, n, L, (const char *)pack, scores, act, (cudaStream_t)stream);
 }
 
+// Training forward of DPlda with the LDA frozen: scores + normalised rows u ([2 n][176] fp32, nplda_act_floats(n, 2)).
+extern "C" int dplda_score_fwd_train_u(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
+                                       float *scores, float *urows, void *stream) {
+    if (n < 0 || !pack || (n > 0 && (!x1 || !x2 || !scores || !urows))) return NPLDA_ERR_BAD_ARG;
+    if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n == 0) return NPLDA_OK;
+    const PackLayout L = make_pack_layout(d_in, d1, d1);
+    if (!tc_dplda_ok(L) || (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)urows) & 15) != 0) return NPLDA_ERR_UNSUPPORTED_DIM;
+    return dplda_score_tc_train_u(x1, x2, n, L, (const char *)pack, scores, urows, (cudaStream_t)stream);
+}
+
+// Gradient of logistic_regres (weight [2 d1^2 + d1] = Wb | Ww | ws, bias) from the rows kept by dplda_score_fwd_train_u and
+// dL/dS; ADDED into dw_lr / dc_lr (either may be null).
+extern "C" int64_t dplda_lr_bwd_workspace_bytes(int64_t n, int d1) {
+    if (n < 0 || d1 < 1 || d1 > 176) return NPLDA_ERR_BAD_ARG;
+    return dplda_lr_workspace_bytes(n, d1);
+}
+
+extern "C" int dplda_lr_bwd(const float *urows, int64_t n, int d1, const float *dscores, float *dw_lr, float *dc_lr,
+                            void *workspace, int64_t workspace_bytes, void *stream) {
+    if (n < 0 || d1 < 1 || d1 > 176 || (n > 0 && (!urows || !dscores))) return NPLDA_ERR_BAD_ARG;
+    if (n == 0 || (!dw_lr && !dc_lr)) return NPLDA_OK;
+    return dplda_lr_grad(urows, n, n, d1, dscores, dw_lr, dc_lr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int dplda_score_fwd_ws(const float *x1, const float *x2, int64_t n, int d_in, int d1, const void *pack,
                                   float *scores, int impl, void *workspace, int64_t workspace_bytes, void *stream) {
     if (n < 0 || !pack || (n > 0 && (!x1 || !x2 || !scores))) return NPLDA_ERR_BAD_ARG;
@@ -153,10 +186,11 @@ extern "C" int dplda_score_fwd_ws(const float *x1, const float *x2, int64_t n, i
     if (n == 0) return NPLDA_OK;
     const PackLayout L = make_pack_layout(d_in, d1, d1);
     const bool aligned = ((((uintptr_t)x1) | ((uintptr_t)x2)) & 15) == 0;
-    const bool tc_ok = tc_dplda_ok(L) && aligned && workspace != nullptr;
+    (void)workspace; (void)workspace_bytes;               // the fused tensor-core kernel needs no workspace
+    const bool tc_ok = tc_dplda_ok(L) && aligned;
     if (impl == NPLDA_IMPL_TC && !tc_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (impl == NPLDA_IMPL_TC || (impl == NPLDA_IMPL_AUTO && tc_ok && n >= 1024))
-        return dplda_score_tc(x1, x2, n, L, (const char *)pack, scores, workspace, workspace_bytes, (cudaStream_t)stream);
+        return dplda_score_tc(x1, x2, n, L, (const char *)pack, scores, (cudaStream_t)stream);
     return score_dispatch(true, x1, x2, nullptr, nullptr, 0, nullptr, n, d_in, d1, d1, pack, scores,
                           impl == NPLDA_IMPL_SIMT ? NPLDA_IMPL_SIMT : NPLDA_IMPL_AUTO, stream);
 }

@@ -1,11 +1,11 @@
 // DPlda forward on the tensor cores (models.py:478-495 in the closed form of SURVEY.md 8 a-6):
 //     u = normalize(W1 x + b1)
 //     S = u1^T Pm u2 + u1^T Ww u1 + u2^T Ww u2 + ws.(u1 + u2) + c ,   Pm = Wb + Wb^T
-// The reference materialises a 57 970-wide feature vector per trial (models.py:483-489).  Here two passes of the
-// tcgen05 score kernel in EMIT mode (score_tc.cu) leave, per row, a = W1 x + b1, V = Ww u and Z = Pm u in a
-// workspace (layer 1 is evaluated in both passes: the kernel is bound by its x stream either way), and one
-// warp per pair finishes  S = (a1.Z2 + a1.V1 + ws.a1) / |a1| + (a2.V2 + ws.a2) / |a2| + c.
-// Pairs are processed in chunks so that the workspace stays at 3 x [2 * chunk][176] fp32.
+// The reference materialises a 57 970-wide feature vector per trial (models.py:483-489).  Scoring (and training with the
+// LDA frozen, the reference driver's case) is ONE pass of the tcgen05 score kernel in its DPL form (score_tc.cu): x read
+// once, both square products per tile, no workspace.  Training with a trainable LDA keeps the two-pass form below: two
+// EMIT passes leave, per row, a = W1 x + b1, R u and Z = Pm u for the backward, and one warp per pair finishes
+// S = (a1.Z2 + a1.V1 / 2 + ws.a1) / |a1| + (a2.V2 / 2 + ws.a2) / |a2| + c.
 #include <algorithm>
 
 #include "common.cuh"
@@ -15,6 +15,8 @@ namespace nplda {
 bool tc_dplda_ok(const PackLayout &L);   // score_tc.cu
 int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, int which,
                         float *aout, float *yout, int64_t emit_cap, cudaStream_t st);   // score_tc.cu
+int score_tc_dplda_fused(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+                         float *uout, int64_t emit_cap, cudaStream_t st);                // score_tc.cu
 
 namespace dtc {
 
@@ -52,25 +54,15 @@ static int64_t cap_for(int64_t n) { return (std::min(n, CHUNK_PAIRS) + TILE_PAIR
 }  // namespace dtc
 
 int dplda_score_tc(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
-                   void *workspace, int64_t workspace_bytes, cudaStream_t st) {
-    if (!tc_dplda_ok(L)) return NPLDA_ERR_UNSUPPORTED_DIM;
-    const int64_t cap = dtc::cap_for(n);
-    if (!workspace || ((uintptr_t)workspace & 255) != 0) return NPLDA_ERR_BAD_ARG;
-    if (workspace_bytes < 3 * 2 * cap * dtc::LD * 4) return NPLDA_ERR_WORKSPACE;
-    float *A = (float *)workspace, *V = A + 2 * cap * dtc::LD, *Z = V + 2 * cap * dtc::LD;
-    for (int64_t c0 = 0; c0 < n; c0 += dtc::CHUNK_PAIRS) {
-        const int64_t nc = std::min(dtc::CHUNK_PAIRS, n - c0);
-        const float *a = x1 + c0 * L.d_in, *b = x2 + c0 * L.d_in;
-        int rc = score_tc_dplda_emit(a, b, nc, L, pack, 0, A, V, cap, st);            // a, V = Ww u
-        if (rc != NPLDA_OK) return rc;
-        rc = score_tc_dplda_emit(a, b, nc, L, pack, 1, nullptr, Z, cap, st);          // Z = Pm u
-        if (rc != NPLDA_OK) return rc;
-        const int grid = (int)std::min<int64_t>((nc + 7) / 8, 16 * (int64_t)sm_count());
-        dtc::dplda_finish_kernel<<<grid, 256, 0, st>>>(A, V, Z, cap, nc, (const float *)(pack + L.b2),
-                                                        (const float *)(pack + L.c), scores + c0, 1.f);
-        NPLDA_LAUNCH_CHECK();
-    }
-    return NPLDA_OK;
+                   cudaStream_t st) {
+    return score_tc_dplda_fused(x1, x2, n, L, pack, scores, nullptr, 0, st);
+}
+
+// Training forward with the LDA frozen (xvector_DPlda_pytorch.py:140-147): scores and the normalised rows u, [2 n][176],
+// side 1 n rows after side 0 -- the gradient of logistic_regres (dplda_lr_bwd, gemm_tc.cu) needs nothing else.
+int dplda_score_tc_train_u(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+                           float *urows, cudaStream_t st) {
+    return score_tc_dplda_fused(x1, x2, n, L, pack, scores, urows, n, st);
 }
 
 // Training forward: the rows the backward needs -- a, R u (R = Ww + Ww^T) and Pm u, each [2 n][176], side 1 n rows
@@ -97,6 +89,5 @@ using namespace nplda;
 extern "C" int64_t dplda_fwd_workspace_bytes(int64_t n, int d_in, int d1) {
     if (n < 0) return NPLDA_ERR_BAD_ARG;
     if (!dims_supported(d_in, d1, d1)) return NPLDA_ERR_UNSUPPORTED_DIM;
-    if (!tc_dplda_ok(make_pack_layout(d_in, d1, d1))) return 0;           // SIMT kernel: no workspace
-    return 3 * 2 * dtc::cap_for(n) * dtc::LD * 4;
+    return 0;            // the fused kernel needs none (kept in the ABI: callers size their workspace with it)
 }

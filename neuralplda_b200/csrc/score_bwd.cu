@@ -610,13 +610,20 @@ static int64_t workspace_bytes(int64_t n, int d_in, int d1, int d2) {
 static std::atomic<int> g_force_gemm{0}, g_force_emit{0}, g_force_du{0};
 
 // C[M,N] += A^T B: the tcgen05 bf16x3 kernel for batches worth its launch
-static int gemm_tn_auto(const float *A, int lda, int M, const float *B, int ldb, int N, int64_t R, float *C,
-                        int ldc, cudaStream_t st) {
+}  // namespace bwd
+int gemm_tn_auto(const float *A, int lda, int M, const float *B, int ldb, int N, int64_t R, float *C, int ldc, cudaStream_t st);
+namespace bwd {
+using nplda::gemm_tn_auto;
+}  // namespace bwd
+int gemm_tn_auto(const float *A, int lda, int M, const float *B, int ldb, int N, int64_t R, float *C,
+                 int ldc, cudaStream_t st) {
+    using namespace bwd;
     const int forced = g_force_gemm.load(std::memory_order_relaxed);
     const bool tc_ok = M <= 176;
     if (tc_ok && (forced == 2 || (forced == 0 && R >= 8192))) return gemm_tn_tc(B, ldb, N, A, lda, M, R, C, ldc, st);
     return gemm_tn(A, lda, M, B, ldb, N, R, C, ldc, st);
 }
+namespace bwd {
 
 template <bool DPLDA>
 static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, int d2, const float *W1,

@@ -73,7 +73,7 @@ constexpr int SM_B = SM_X + NX * X_STAGE;
 constexpr int SM_U = SM_B + NBS * B_STAGE;
 constexpr int SM_PAR = SM_U + 2 * U_HALF;                 // b1, b2, P, Q (NPAD floats each)
 constexpr int SM_BAR = SM_PAR + 4 * NPAD * 4;
-constexpr int N_BARS = 2 * NX + 2 * NA + 2 * NBS + 8;
+constexpr int N_BARS = 2 * NX + 2 * NA + 2 * NBS + 12;
 constexpr int SM_TMEM = SM_BAR + N_BARS * 8;
 constexpr int SMEM_BYTES = SM_TMEM + 16 + 1024;       // + slack for the 1 KB alignment
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -84,6 +84,8 @@ struct Args {
     int nst1;               // layer-1 stages  = d_in / 32
     int ksteps2;            // layer-2 K steps = round_up(d1, 16) / 16
     const uint8_t *w1img, *w2img;   // MODE 1: w1img is the fp16 + 2 x e4m3 image
+    const uint8_t *w3img;           // DPL: image of R = Ww + Ww^T (w2img: Pm = Wb + Wb^T); b2 = ws, cbias = logistic_regres.bias
+    const float *cbias;
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
     const float *hdr;       // MODE 1: hdr[0] = 2^-(9 + gw), the scale that undoes the weight pre-scaling
     const float *hdr16;     // MODE 2: {2^gw1, 2^-gw1, 2^gw2, 2^-gw2, ...}: the fp16 images hold W1 2^gw1 and W2 2^gw2
@@ -171,7 +173,13 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
 
 constexpr int EMIT_LD = NPAD;  // 176: row stride of the emitted a / y rows (= the backward's row pitch for these shapes)
 
-template <bool PROF, int MODE, bool EMIT>
+// DPL (DPlda, models.py:478-495 in the closed form of SURVEY.md 8 a-6): the same pipeline with TWO square products per
+// tile on the un-normalised a = W1 x + b1 (the length norm commutes): Y_P = a Pm^T, then Y_R = a R^T into the same
+// accumulator once the epilogue has consumed Y_P;  S = a1.Y_P(a2) / (|a1||a2|) + (a1.Y_R(a1) / |a1|^2 + a2.Y_R(a2) / |a2|^2) / 2
+// + ws.(a1 / |a1| + a2 / |a2|) + c.  The epilogue re-reads a from its own hi/lo entries of U (shared memory) in both
+// passes, so x is streamed once and nothing goes through a workspace.  EMIT: the normalised u rows (what the gradient of
+// logistic_regres needs) go to aout.
+template <bool PROF, int MODE, bool EMIT, bool DPL = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -185,6 +193,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
     uint64_t *b_full = a_empty + NA, *b_empty = b_full + NBS;
     uint64_t *d_full = b_empty + NBS, *d_empty = d_full + 2, *y_full = d_full + 4;
     uint64_t *u_full = d_full + 6, *u_empty = d_full + 7;
+    uint64_t *y2_full = d_full + 8, *p2a_done = d_full + 10;      // DPL: second product published / first one consumed
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -203,6 +212,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         for (int d = 0; d < 2; ++d) { mbar_init(&d_full[d], 1); mbar_init(&d_empty[d], EPI_WARPS * 32); mbar_init(&y_full[d], 1); }
         mbar_init(u_full, EPI_WARPS * 32);
         mbar_init(u_empty, 1);
+        for (int d = 0; d < 2; ++d) { mbar_init(&y2_full[d], 1); mbar_init(&p2a_done[d], EPI_WARPS * 32); }
         mbar_fence_init();
     }
     if (warp == WARP_MMA) tmem_alloc(tmem_slot, 512);
@@ -235,6 +245,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         const float2 *qs = reinterpret_cast<const float2 *>(par + 3 * NPAD);
 
         float *ea0 = nullptr, *ea1 = nullptr, *ey0 = nullptr, *ey1 = nullptr;   // EMIT: this thread's two rows of the tile
+        float ln[4] = {0.f, 0.f, 0.f, 0.f};                      // DPL: partial sums of ws . a (sides 0, 0, 1, 1)
         auto pass1 = [&](const uint32_t (&v)[8], int c0, float (&ss)[4]) {
             const float2 ba = b1s[(c0 >> 1) + cq], bb = b1s[(c0 >> 1) + 4 + cq];
             const float a00 = fmaf(__uint_as_float(v[0]), s1, ba.x), a01 = fmaf(__uint_as_float(v[1]), s1, ba.y);
@@ -245,7 +256,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             ss[0] = fmaf(a02, a02, ss[0]); ss[1] = fmaf(a03, a03, ss[1]);
             ss[2] = fmaf(a10, a10, ss[2]); ss[3] = fmaf(a11, a11, ss[3]);
             ss[2] = fmaf(a12, a12, ss[2]); ss[3] = fmaf(a13, a13, ss[3]);
-            if (EMIT && ea0 != nullptr) {
+            if (DPL) {
+                const float2 wa = b2s[(c0 >> 1) + cq], wb = b2s[(c0 >> 1) + 4 + cq];      // ws (the b2 slot of a DPlda pack)
+                ln[0] = fmaf(wa.x, a00, ln[0]); ln[1] = fmaf(wa.y, a01, ln[1]);
+                ln[0] = fmaf(wb.x, a02, ln[0]); ln[1] = fmaf(wb.y, a03, ln[1]);
+                ln[2] = fmaf(wa.x, a10, ln[2]); ln[3] = fmaf(wa.y, a11, ln[3]);
+                ln[2] = fmaf(wb.x, a12, ln[2]); ln[3] = fmaf(wb.y, a13, ln[3]);
+            }
+            if (EMIT && !DPL && ea0 != nullptr) {
                 *reinterpret_cast<float2 *>(ea0 + c0 + 2 * cq) = make_float2(a00, a01);
                 *reinterpret_cast<float2 *>(ea0 + c0 + 8 + 2 * cq) = make_float2(a02, a03);
                 *reinterpret_cast<float2 *>(ea1 + c0 + 2 * cq) = make_float2(a10, a11);
@@ -288,6 +306,122 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             sc[1] = fmaf(qb.y, fmaf(y03, y03, y13 * y13), sc[1]); sc[1] = fmaf(2.f * pb.y, y03 * y13, sc[1]);
         };
 
+        // ---- DPL: a of this thread's (row, column pair) entries, back from the hi/lo halves it wrote to U ----
+        auto ld_a = [&](const uint8_t *up, int kc, float &x, float &y) {
+            const uint32_t h = *reinterpret_cast<const uint32_t *>(up + kc * KCH_U);
+            const uint32_t l = *reinterpret_cast<const uint32_t *>(up + U_HALF + kc * KCH_U);
+            if (MODE == 2) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&h));
+                const float2 lf = __half22float2(*reinterpret_cast<const __half2 *>(&l));
+                x = hf.x + lf.x; y = hf.y + lf.y;
+            } else {
+                x = __uint_as_float(h << 16) + __uint_as_float(l << 16);
+                y = __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
+            }
+        };
+        // pass 2a: Y_P rows (Pm a) -> cross term a1 . (Pm a2); EMIT: normalised u rows
+        auto pass2a = [&](const uint32_t (&v)[8], int c0, float r0, float r1, float (&cr)[2]) {
+            const int kc = c0 >> 3;
+            float a00, a01, a02, a03, a10, a11, a12, a13;
+            ld_a(u0, kc, a00, a01); ld_a(u0, kc + 1, a02, a03);
+            ld_a(u1, kc, a10, a11); ld_a(u1, kc + 1, a12, a13);
+            cr[0] = fmaf(a00, __uint_as_float(v[2]), cr[0]); cr[1] = fmaf(a01, __uint_as_float(v[3]), cr[1]);
+            cr[0] = fmaf(a02, __uint_as_float(v[6]), cr[0]); cr[1] = fmaf(a03, __uint_as_float(v[7]), cr[1]);
+            if (EMIT && ea0 != nullptr) {
+                *reinterpret_cast<float2 *>(ea0 + c0 + 2 * cq) = make_float2(a00 * r0, a01 * r0);
+                *reinterpret_cast<float2 *>(ea0 + c0 + 8 + 2 * cq) = make_float2(a02 * r0, a03 * r0);
+                *reinterpret_cast<float2 *>(ea1 + c0 + 2 * cq) = make_float2(a10 * r1, a11 * r1);
+                *reinterpret_cast<float2 *>(ea1 + c0 + 8 + 2 * cq) = make_float2(a12 * r1, a13 * r1);
+            }
+        };
+        // pass 2b: Y_R rows (R a) -> the two quadratic forms a1 . (R a1), a2 . (R a2)
+        auto pass2b = [&](const uint32_t (&v)[8], int c0, float (&qa)[4]) {
+            const int kc = c0 >> 3;
+            float a00, a01, a02, a03, a10, a11, a12, a13;
+            ld_a(u0, kc, a00, a01); ld_a(u0, kc + 1, a02, a03);
+            ld_a(u1, kc, a10, a11); ld_a(u1, kc + 1, a12, a13);
+            qa[0] = fmaf(a00, __uint_as_float(v[0]), qa[0]); qa[1] = fmaf(a01, __uint_as_float(v[1]), qa[1]);
+            qa[0] = fmaf(a02, __uint_as_float(v[4]), qa[0]); qa[1] = fmaf(a03, __uint_as_float(v[5]), qa[1]);
+            qa[2] = fmaf(a10, __uint_as_float(v[2]), qa[2]); qa[3] = fmaf(a11, __uint_as_float(v[3]), qa[3]);
+            qa[2] = fmaf(a12, __uint_as_float(v[6]), qa[2]); qa[3] = fmaf(a13, __uint_as_float(v[7]), qa[3]);
+        };
+        auto quad4 = [](float v) {                                  // sum over the four lanes sharing a pair
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            return v + __shfl_xor_sync(0xffffffffu, v, 2);
+        };
+
+        if (DPL) for (int64_t i = 0; i < T; ++i) {
+            const int d = (int)(i & 1);
+            const uint32_t par_d = (uint32_t)((i >> 1) & 1);
+            const uint32_t taddr = tbase + d * NPAD;
+            const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + pl;
+            if (EMIT) {                                              // normalised u rows: side 0 row pr, side 1 row emit_cap + pr
+                const bool ok = pr < g.emit_cap && g.aout != nullptr;
+                ea0 = ok ? g.aout + pr * EMIT_LD : nullptr;
+                ea1 = ok ? g.aout + (g.emit_cap + pr) * EMIT_LD : nullptr;
+            }
+            // ---- layer-1 accumulator: a = D + b1, |a|, ws . a, hi/lo of a -> U ----
+            WAIT_OFFPATH(&d_full[d], par_d);
+            tc_fence_after();
+            float ss[4] = {0.f, 0.f, 0.f, 0.f};
+            ln[0] = ln[1] = ln[2] = ln[3] = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NPAD - 16; c0 += 32) {
+                uint32_t va[8], vb[8];
+                tmem_ld_16x256b_x2(taddr + c0, va);
+                tmem_ld_16x256b_x2(taddr + c0 + 16, vb);
+                tmem_ld_wait();
+                pass1(va, c0, ss);
+                pass1(vb, c0 + 16, ss);
+            }
+            {
+                uint32_t va[8];
+                tmem_ld_16x256b_x2(taddr + NPAD - 16, va);
+                tmem_ld_wait();
+                pass1(va, NPAD - 16, ss);
+            }
+            const float ss0 = quad4(ss[0] + ss[1]), ss1 = quad4(ss[2] + ss[3]);
+            const float r0 = 1.f / fmaxf(sqrtf(ss0), 1e-12f);      // F.normalize eps (models.py:480)
+            const float r1 = 1.f / fmaxf(sqrtf(ss1), 1e-12f);
+            if (MODE == 2) {                                        // fp16 range guard for U, as in the NeuralPlda path
+                if (!(ss0 < 1.0e9f && ss1 < 1.0e9f) && pr < g.n) *reinterpret_cast<volatile int *>(g.guard) = 1;
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(u_full);
+            // ---- Y_P = a Pm^T ----
+            WAIT_OFFPATH(&y_full[d], par_d);
+            tc_fence_after();
+            float cr[2] = {0.f, 0.f};
+#pragma unroll 1
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                uint32_t va[8];
+                tmem_ld_16x256b_x2(taddr + c0, va);
+                tmem_ld_wait();
+                pass2a(va, c0, r0, r1, cr);
+            }
+            tc_fence_before();
+            mbar_arrive(&p2a_done[d]);                              // the accumulator may be overwritten by Y_R
+            // ---- Y_R = a R^T ----
+            WAIT_OFFPATH(&y2_full[d], par_d);
+            tc_fence_after();
+            float qa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                uint32_t va[8];
+                tmem_ld_16x256b_x2(taddr + c0, va);
+                tmem_ld_wait();
+                pass2b(va, c0, qa);
+            }
+            tc_fence_before();
+            mbar_arrive(&d_empty[d]);
+            const float cross = quad4(cr[0] + cr[1]), q0 = quad4(qa[0] + qa[1]), q1 = quad4(qa[2] + qa[3]);
+            const float l0 = quad4(ln[0] + ln[1]), l1 = quad4(ln[2] + ln[3]);
+            // c2 undoes the power-of-two scale of the square images (MODE 2)
+            const float s = c2 * (cross * r0 * r1 + 0.5f * (q0 * r0 * r0 + q1 * r1 * r1)) + l0 * r0 + l1 * r1 + g.cbias[0];
+            if ((!EMIT || g.scores != nullptr) && cq == 0 && pr < g.n) g.scores[pr] = s;
+        }
+        else
         for (int64_t i = 0; i < T; ++i) {
             const int d = (int)(i & 1);
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
@@ -566,22 +700,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             // Layer 2 lands mid-way so that the final epilogue of tile i-1 runs under the second half and
             // the D buffer it frees is ready when layer 1 of tile i+1 starts.  The B loader follows the
             // same order.
-            for (int64_t i = 0; i <= T; ++i) {
-                const uint32_t dcol_i = tmem + (uint32_t)(i & 1) * NPAD;
-                cur_tile = i;
-                if (i < T) {
-                    PMARK(6);
-                    mbar_wait(&d_empty[i & 1], (uint32_t)(((i >> 1) & 1) ^ 1));
-                    tc_fence_after();
-                    PMARK(0);
-                    layer1(dcol_i, 0, half);
-                }
-                if (i >= 1) {      // layer 2 of tile i - 1
-                    const int64_t j = i - 1;
+            // One square product of tile j on U (shared memory): Y = U M^T into accumulator d; the B loader streams the
+            // image of M in the same order.  `ready` / `ready_par`: the barrier that makes U (first product) or the
+            // accumulator (DPL, second product) available; `published`: committed when the product has completed.
+            auto layer2 = [&](int64_t j, uint64_t *ready, uint32_t ready_par, uint64_t *published, bool release_u) {
                     const int d = (int)(j & 1);
                     const uint32_t dcol = tmem + d * NPAD;
                     PMARK(6);
-                    mbar_wait(u_full, (uint32_t)(j & 1));
+                    mbar_wait(ready, ready_par);
                     tc_fence_after();
                     PMARK(4);
                     mbar_wait(&b_full[rb.stage], rb.phase);
@@ -618,12 +744,44 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                         rb = nb;
                     }
                     if (elect_one()) {
-                        mma_commit(&y_full[d]);
-                        mma_commit(u_empty);
+                        mma_commit(published);
+                        if (release_u) mma_commit(u_empty);
                     }
                     __syncwarp();
                     PMARK(5);
+            };
+            for (int64_t i = 0; i <= T; ++i) {
+                const uint32_t dcol_i = tmem + (uint32_t)(i & 1) * NPAD;
+                cur_tile = i;
+                const int64_t j = i - 1;                           // the tile whose square products are issued in this round
+                const int dj = (int)(j & 1);
+                const uint32_t par_j = (uint32_t)((j >> 1) & 1);
+                if (DPL) {
+                    // thirds of layer 1 around the two products: Y_P (needs U), Y_R (needs the epilogue's pass over Y_P)
+                    const int c1 = g.nst1 / 3, c2s = 2 * g.nst1 / 3;
+                    if (i < T) {
+                        mbar_wait(&d_empty[i & 1], (uint32_t)(((i >> 1) & 1) ^ 1));
+                        tc_fence_after();
+                        layer1(dcol_i, 0, c1);
+                    }
+                    if (i >= 1) layer2(j, u_full, (uint32_t)(j & 1), &y_full[dj], false);
+                    if (i < T) layer1(dcol_i, c1, c2s);
+                    if (i >= 1) layer2(j, &p2a_done[dj], par_j, &y2_full[dj], false);
+                    if (i < T) {
+                        layer1(dcol_i, c2s, g.nst1);
+                        if (elect_one()) mma_commit(&d_full[i & 1]);
+                        __syncwarp();
+                    }
+                    continue;
                 }
+                if (i < T) {
+                    PMARK(6);
+                    mbar_wait(&d_empty[i & 1], (uint32_t)(((i >> 1) & 1) ^ 1));
+                    tc_fence_after();
+                    PMARK(0);
+                    layer1(dcol_i, 0, half);
+                }
+                if (i >= 1) layer2(j, u_full, (uint32_t)(j & 1), &y_full[dj], true);      // layer 2 of tile i - 1
                 if (i < T) {
                     layer1(dcol_i, half, g.nst1);
                     if (elect_one()) mma_commit(&d_full[i & 1]);
@@ -637,7 +795,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             if (T > 0) {
                 for (int k = 0; k < NA; ++k) { mbar_wait(&a_empty[ra.stage], ra.phase ^ 1); ra.advance(); }
                 for (int k = 0; k < NBS; ++k) { mbar_wait(&b_empty[rb.stage], rb.phase ^ 1); rb.advance(); }
-                mbar_wait(u_empty, (uint32_t)((T & 1) ^ 1));
+                if (!DPL) mbar_wait(u_empty, (uint32_t)((T & 1) ^ 1));
             }
             PMARK(7);
             if (lane == 0) PFLUSH(3);
@@ -662,14 +820,25 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                 rb.advance();
                 ++nput;
             };
+            auto put_l1 = [&](int s0, int s1) {
+                for (int s = s0; s < s1; ++s) put(g.w1img + (size_t)s * B_STAGE, B_STAGE);
+            };
+            auto put_sq = [&](const uint8_t *img) {
+                for (int ks = 0; ks < g.ksteps2; ks += 2) put(img + (size_t)ks * B_STEP, min(2, g.ksteps2 - ks) * B_STEP);
+            };
+            const int c1 = g.nst1 / 3, c2s = 2 * g.nst1 / 3;           // DPL: the MMA warp's order (thirds of layer 1)
             for (int64_t i = 0; i <= T; ++i) {
-                if (i < T)
-                    for (int s = 0; s < half; ++s) put(g.w1img + (size_t)s * B_STAGE, B_STAGE);
-                if (i >= 1)
-                    for (int ks = 0; ks < g.ksteps2; ks += 2)
-                        put(g.w2img + (size_t)ks * B_STEP, min(2, g.ksteps2 - ks) * B_STEP);
-                if (i < T)
-                    for (int s = half; s < g.nst1; ++s) put(g.w1img + (size_t)s * B_STAGE, B_STAGE);
+                if (DPL) {
+                    if (i < T) put_l1(0, c1);
+                    if (i >= 1) put_sq(g.w2img);
+                    if (i < T) put_l1(c1, c2s);
+                    if (i >= 1) put_sq(g.w3img);
+                    if (i < T) put_l1(c2s, g.nst1);
+                    continue;
+                }
+                if (i < T) put_l1(0, half);
+                if (i >= 1) put_sq(g.w2img);
+                if (i < T) put_l1(half, g.nst1);
             }
             PMARK(1);
             PFLUSH(4);
@@ -961,7 +1130,7 @@ int tc_pack_dplda(const float *W1, const float *b1, const float *w_lr, const flo
     uint8_t *base = (uint8_t *)pack + L.tc;
     float *hdr16 = (float *)(base + A.hdr16);
     // one scale for the three square images: max over Wb and Ww with a factor 2 of headroom (Pm, R are sums of two entries)
-    tcg::tc_scales_kernel<<<2, 1024, 0, st>>>(W1, L.d1, L.d_in, b1, w_lr, 1, 2 * L.d1 * L.d1, hdr16, 2.f);
+    tcg::tc_scales_kernel<<<2, 1024, 0, st>>>(W1, L.d1, L.d_in, b1, w_lr, 2 * L.d1, L.d1, hdr16, 2.f);   // Wb | Ww as 2 d1 rows
     NPLDA_LAUNCH_CHECK();
     tcg::tc_pack_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / 16, base + A.img1, nullptr, 0, 0, 0,
                                                         base + A.img1h, hdr16);
@@ -1000,9 +1169,9 @@ static int *guard_slot() {
     return ring[dev] + 2 * (ticket.fetch_add(1, std::memory_order_relaxed) & 1023u);
 }
 
-template <bool PROF, int MODE, bool EMIT = false>
+template <bool PROF, int MODE, bool EMIT = false, bool DPL = false>
 static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Args &a, int grid, cudaStream_t st) {
-    auto kern = tcg::score_tc_kernel<PROF, MODE, EMIT>;
+    auto kern = tcg::score_tc_kernel<PROF, MODE, EMIT, DPL>;
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
     kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
     NPLDA_LAUNCH_CHECK();
@@ -1054,7 +1223,7 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
     tcg::Args a;
     a.x1 = x1; a.x2 = x2; a.n = n;
     a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
-    a.w1img = base + A.img1; a.w2img = base + A.img2;
+    a.w1img = base + A.img1; a.w2img = base + A.img2; a.w3img = nullptr; a.cbias = nullptr;
     a.hdr = (const float *)(base + A.hdr);
     a.hdr16 = (const float *)(base + A.hdr16);
     a.guard = nullptr;
@@ -1148,7 +1317,7 @@ int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackL
     a.x1 = x1; a.x2 = x2; a.n = n;
     a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
     a.w1img = (const uint8_t *)pack + L.tc;
-    a.w2img = dplda_image(L, pack, which);
+    a.w2img = dplda_image(L, pack, which); a.w3img = nullptr; a.cbias = nullptr;
     a.hdr = (const float *)(pack + L.p);               // unused by MODE 0 / 2
     a.hdr16 = (const float *)(pack + L.tc + A.hdr16);
     a.guard = nullptr;
@@ -1169,6 +1338,42 @@ int score_tc_dplda_emit(const float *x1, const float *x2, int64_t n, const PackL
     const int rc = launch_tc<false, 2, true>(m1, m2, a16, grid, st);
     if (rc != NPLDA_OK) return rc;
     return launch_tc<false, 0, true>(m1, m2, a, grid, st);
+}
+
+// DPlda scores in ONE pass over x (DPL instantiation): both square products per tile, nothing through a workspace.
+// uout != nullptr (training with the LDA frozen): also the normalised rows u = a / |a|, [2 * emit_cap][176] fp32, side 1
+// of pair p emit_cap rows after side 0 -- all the gradient of logistic_regres needs.
+int score_tc_dplda_fused(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+                         float *uout, int64_t emit_cap, cudaStream_t st) {
+    if (!tc_dplda_ok(L) || !scores) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n >= (int64_t)1 << 31 || (uout && emit_cap < n)) return NPLDA_ERR_BAD_ARG;
+    CUtensorMap m1, m2;
+    if (!tcg::make_x_map(&m1, x1, n, L.d_in) || !tcg::make_x_map(&m2, x2, n, L.d_in)) return NPLDA_ERR_NO_DEVICE;
+    const TcArea A = tc_area(L.d_in, L.d1);
+    tcg::Args a;
+    a.x1 = x1; a.x2 = x2; a.n = n;
+    a.nst1 = L.d_in / tcg::KST; a.ksteps2 = round_up(L.d1, 16) / 16;
+    a.w1img = (const uint8_t *)pack + L.tc;
+    a.w2img = dplda_image(L, pack, 1); a.w3img = dplda_image(L, pack, 2);
+    a.hdr = (const float *)(pack + L.p);
+    a.hdr16 = (const float *)(pack + L.tc + A.hdr16);
+    a.b1 = (const float *)(pack + L.b1);
+    a.b2 = (const float *)(pack + L.b2);               // ws
+    a.cbias = (const float *)(pack + L.c);
+    a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.p);
+    a.scores = scores; a.aout = uout; a.yout = nullptr; a.emit_cap = emit_cap;
+    a.trace = nullptr; a.dbg = 0;
+    const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
+    const int grid = (int)std::min<int64_t>(nt, sm_count());
+    int *slot = guard_slot();
+    if (!slot) return NPLDA_ERR_NO_DEVICE;
+    tcg::Args a16 = a;                                 // fp16x3 pass, then the bf16x3 pass behind its range guard
+    a16.w1img = (const uint8_t *)pack + L.tc + A.img1h;
+    a16.w2img = dplda_image16(L, pack, 1); a16.w3img = dplda_image16(L, pack, 2);
+    a16.guard = slot; a.guard = slot;
+    int rc = uout ? launch_tc<false, 2, true, true>(m1, m2, a16, grid, st) : launch_tc<false, 2, false, true>(m1, m2, a16, grid, st);
+    if (rc != NPLDA_OK) return rc;
+    return uout ? launch_tc<false, 0, true, true>(m1, m2, a, grid, st) : launch_tc<false, 0, false, true>(m1, m2, a, grid, st);
 }
 
 // Rows-in / rows-out product on the tensor cores, used by the backward for dL/du = dL/dy . W2: an EMIT pass whose
@@ -1194,7 +1399,7 @@ int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int row_widt
     tcg::Args a;
     a.x1 = xa; a.x2 = xb; a.n = n;
     a.nst1 = d_in / tcg::KST; a.ksteps2 = ksteps2;
-    a.w1img = w1img; a.w2img = w2img_any;
+    a.w1img = w1img; a.w2img = w2img_any; a.w3img = nullptr; a.cbias = nullptr;
     a.hdr = zeros; a.hdr16 = zeros; a.guard = nullptr;
     a.b1 = zeros; a.b2 = zeros; a.p = zeros; a.q = zeros;
     a.scores = nullptr; a.aout = aout; a.yout = nullptr; a.emit_cap = emit_cap;

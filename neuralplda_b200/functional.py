@@ -270,13 +270,18 @@ class DpldaScoreFn(torch.autograd.Function):
         pack = packed.get("dplda", (W1, b1, w_lr, c_lr), d_in, d1, d1)
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
         ctx.act = None
+        ctx.lda_frozen = False
         if _wants_activations(ctx, packed, impl, n, x1c.device, grad_mode):
+            # LDA frozen (the reference driver's case, xvector_DPlda_pytorch.py:140-147) and no input gradients: the
+            # backward is the gradient of logistic_regres alone and needs only the normalised rows u
+            frozen = not any(ctx.needs_input_grad[:4])
             with on_device(x1c.device):
-                act = torch.empty(int(lib().nplda_act_floats(n, 1)), dtype=torch.float32, device=x1c.device)
-                rc = lib().dplda_score_fwd_train(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), ptr(act),
-                                                 stream_ptr())
+                act = torch.empty(int(lib().nplda_act_floats(n, 2 if frozen else 1)), dtype=torch.float32, device=x1c.device)
+                fn = lib().dplda_score_fwd_train_u if frozen else lib().dplda_score_fwd_train
+                rc = fn(ptr(x1c), ptr(x2c), n, d_in, d1, ptr(pack), ptr(scores), ptr(act), stream_ptr())
             if rc == 0:
                 ctx.act = act
+                ctx.lda_frozen = frozen
                 ctx.save_for_backward(x1c, x2c, W1, b1, w_lr)
                 return scores
             if rc != _lib.ERR_UNSUPPORTED_DIM:
@@ -303,6 +308,15 @@ class DpldaScoreFn(torch.autograd.Function):
         dW1, db1, dw, dc = _zero_grads([W1c, b1c, wc, b1c[:1]], need[2:6])       # dc: [1] like logistic_regres.bias
         dx1 = torch.zeros_like(x1) if need[0] else None
         dx2 = torch.zeros_like(x2) if need[1] else None
+        if n > 0 and ctx.lda_frozen:
+            with on_device(dev):
+                wsb = lib().dplda_lr_bwd_workspace_bytes(n, d1)
+                if wsb < 0:
+                    check(wsb, "dplda_lr_bwd_workspace_bytes")
+                ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=dev)
+                check(lib().dplda_lr_bwd(ptr(ctx.act), n, d1, ptr(ds), ptr(dw), ptr(dc), ptr(ws), ws.numel(), stream_ptr()),
+                      "dplda_lr_bwd")
+            return (None, None, None, None, dw, dc, None, None, None)
         if n > 0:
             with on_device(dev):
                 wsb = lib().nplda_bwd_workspace_bytes(n, d_in, d1, d1)

@@ -246,7 +246,7 @@ def test_unsupported_dims_error():
         m(torch.zeros(4, 512, device=DEV), torch.zeros(4, 512, device=DEV))
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", IMPLS + [npl.IMPL_TC])       # 768 pairs: AUTO stays on the fp32 kernel, TC = the fused kernel
 def test_dplda_forward_golden(ref_out, kaldi_params, cfg1, impl):
     x1, x2, _ = cfg1
     m = make_dplda(kaldi_params, ref_out, impl)
@@ -256,6 +256,51 @@ def test_dplda_forward_golden(ref_out, kaldi_params, cfg1, impl):
         s = m(x1[:n].to(DEV), x2[:n].to(DEV))
     ok, worst = parity_ok(s, ref, rel=1e-4)
     assert ok, worst
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 127, 129, 1000, 4097])
+def test_dplda_fused_forward_ragged_sizes(ref_out, kaldi_params, cfg1, n):
+    """The one-pass tensor-core DPlda kernel (both square products per tile) on ragged sizes, forced with IMPL_TC, against
+    the oracle's closed form; the criterion uses the score scale of the whole 10k workload."""
+    x1, x2, _ = cfg1
+    kp = kaldi_params
+    m = make_dplda(kp, ref_out, npl.IMPL_TC)
+    w, c = dplda_weights(ref_out)
+    ref = O.dplda_score(x1[:n], x2[:n], kp["W1"], kp["b1"], w, c)
+    full = O.dplda_score(x1[:2000], x2[:2000], kp["W1"], kp["b1"], w, c).double()
+    with torch.no_grad():
+        s = m(x1[:n].to(DEV), x2[:n].to(DEV))
+    assert s.shape == (n,)
+    bound = 1e-4 * torch.maximum(ref.double().abs(), full.pow(2).mean().sqrt())
+    err = (s.cpu().double() - ref.double()).abs()
+    assert bool((err <= bound).all()), float((err / bound).max())
+
+
+@pytest.mark.parametrize("n", [64, 65, 256, 1000])
+def test_dplda_frozen_lda_training_step(ref_out, kaldi_params, cfg1, n):
+    """LDA frozen (xvector_DPlda_pytorch.py:140-147): the forward keeps only the normalised rows u and the backward is
+    the gradient of logistic_regres alone (dplda_lr_bwd: Ps / Pd contractions).  Same loss and logistic_regres gradients
+    as with a trainable LDA (golden .grad of the unmodified reference at n = 256), no gradient on the frozen parameters."""
+    x1, x2, t = cfg1
+    a, b, tt = x1[:n].to(DEV), x2[:n].to(DEV), t[:n].to(DEV)
+    full = make_dplda(kaldi_params, ref_out)
+    lf = full.loss(full(a, b), tt)
+    lf.backward()
+    m = make_dplda(kaldi_params, ref_out)
+    for p in (m.centering_and_LDA.weight, m.centering_and_LDA.bias):
+        p.requires_grad_(False)
+    out = m(a, b)
+    loss = m.loss(out, tt)
+    loss.backward()
+    assert m.centering_and_LDA.weight.grad is None and m.centering_and_LDA.bias.grad is None
+    assert loss.item() == pytest.approx(lf.item(), rel=1e-5)
+    for name in ("weight", "bias"):
+        got, want = getattr(m.logistic_regres, name).grad, getattr(full.logistic_regres, name).grad
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 1e-4 * scale, name
+    if n == 256:
+        assert loss.item() == pytest.approx(float(ref_out["c4_train_loss"]), rel=1e-4)
+        _check_grads(m, ref_out, "c4", ["logistic_regres.weight", "logistic_regres.bias"])
 
 
 @pytest.mark.parametrize("impl", IMPLS)
