@@ -35,6 +35,10 @@ int64_t tc_rows_image_bytes(int d_in);   // score_tc.cu
 int tc_rows_image_pack(const float *Wkn, int64_t ldk, int N, int K, int d_in, uint8_t *img, cudaStream_t st);
 int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int row_width, int d_in, const uint8_t *w1img,
                        const uint8_t *w2img_any, int ksteps2, const float *zeros, float *aout, int64_t emit_cap, cudaStream_t st);
+int score_tc_bwd_mid(const float *yrows, const float *arows, int64_t pre_cap, int64_t n, int rw, int d_k, int d1, int d2,
+                     const uint8_t *w2t_img, const float *p, const float *q, const float *psq2, const float *dscores,
+                     float *U, float *G, float *DA, int64_t out_cap, float *db1, float *db2, float *dq, float *dpsqrt,
+                     cudaStream_t st);   // score_tc.cu (BWD instantiation)
 
 namespace bwd {
 
@@ -718,7 +722,12 @@ static int run(const float *x1, const float *x2, int64_t n, int d_in, int d1, in
             rc = score_tc_dplda_emit(a.x1, a.x2, nc, FL, fpack, 1, nullptr, PMU, cap, st);
             if (rc != NPLDA_OK) return rc;
         }
-        if (du_tc) {
+        // default: the two elementwise phases folded into the rows pass (one launch); forcing du = 2 keeps the three-launch form
+        if (du_tc && rw == 176 && g_force_du.load(std::memory_order_relaxed) == 0) {
+            int rc = score_tc_bwd_mid(a.Ypre, a.Apre, a.pre_cap, nc, rw, NP, d1, d2, duimg, pk + P.p, pk + P.q, pk + P.psq2, a.ds,
+                                      U, G, DA, cap, db1, db2, dq, dps, st);
+            if (rc != NPLDA_OK) return rc;
+        } else if (du_tc) {
             const int grid = (int)std::min<int64_t>(ntiles, sm_count());
             kern1<<<grid, NTHREADS, BWD_SMEM_BYTES, st>>>(a);
             NPLDA_LAUNCH_CHECK();

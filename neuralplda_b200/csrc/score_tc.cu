@@ -86,6 +86,15 @@ struct Args {
     const uint8_t *w1img, *w2img;   // MODE 1: w1img is the fp16 + 2 x e4m3 image
     const uint8_t *w3img;           // DPL: image of R = Ww + Ww^T (w2img: Pm = Wb + Wb^T); b2 = ws, cbias = logistic_regres.bias
     const float *cbias;
+    // BWD (middle of NeuralPlda's backward, see the kernel comment): x1 / x2 are the y rows of sides 0 / 1
+    const float *ds;                // dL/dS [n]
+    const float *apre;              // a = W1 x + b1 rows, side 1 `pre_cap` rows after side 0, `rw` floats per row
+    int64_t pre_cap, out_cap;
+    int rw;
+    float *uout, *gout, *daout;     // U (normalised), dL/dy and dL/da rows, side 1 `out_cap` rows after side 0
+    float *db1, *db2, *dq, *dpsqrt; // column sums, ADDED into (any may be null)
+    const float *psq2;              // 2 P_sqrt (dL/dP_sqrt = dL/dP 2 P_sqrt)
+    int nb1, nb2;                   // layer widths d1, d2 (lengths of db1 and of db2 / dq / dpsqrt)
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
     const float *hdr;       // MODE 1: hdr[0] = 2^-(9 + gw), the scale that undoes the weight pre-scaling
     const float *hdr16;     // MODE 2: {2^gw1, 2^-gw1, 2^gw2, 2^-gw2, ...}: the fp16 images hold W1 2^gw1 and W2 2^gw2
@@ -179,7 +188,15 @@ constexpr int EMIT_LD = NPAD;  // 176: row stride of the emitted a / y rows (= t
 // + ws.(a1 / |a1| + a2 / |a2|) + c.  The epilogue re-reads a from its own hi/lo entries of U (shared memory) in both
 // passes, so x is streamed once and nothing goes through a workspace.  EMIT: the normalised u rows (what the gradient of
 // logistic_regres needs) go to aout.
-template <bool PROF, int MODE, bool EMIT, bool DPL = false>
+//
+// BWD (NeuralPlda, autograd through models.py:366-376 between the two affine layers): the rows pipeline with the
+// elementwise halves of the backward folded into its two ends.  The "x" tiles are the y rows of both sides; the
+// converters turn them into dL/dy = 2 g (Q y_self + P y_other) (a thread holds both sides of its pair), store those rows
+// for dW2, reduce the b2 / Q / P gradients, and feed the bf16 hi/lo halves to the tensor cores; the single product is
+// dL/du = dL/dy W2; the epilogue reads its a rows, applies the length-norm backward dL/da = (du - u (u.du)) / |a| and
+// stores the U and dL/da rows for dW2 / dW1 (+ the b1 gradient).  One launch instead of two elementwise kernels around
+// a rows pass: every row is read once and written once.
+template <bool PROF, int MODE, bool EMIT, bool DPL = false, bool BWD = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, Args g) {
     extern __shared__ uint8_t smem_raw[];
@@ -215,6 +232,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         for (int d = 0; d < 2; ++d) { mbar_init(&y2_full[d], 1); mbar_init(&p2a_done[d], EPI_WARPS * 32); }
         mbar_fence_init();
     }
+    float *colacc = reinterpret_cast<float *>(Us);            // BWD: [4][NPAD] column sums db1, db2, dq, dp (U is not used)
+    if (BWD)
+        for (int i = tid; i < 4 * NPAD; i += NTHREADS) colacc[i] = 0.f;
     if (warp == WARP_MMA) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -350,7 +370,78 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             return v + __shfl_xor_sync(0xffffffffu, v, 2);
         };
 
-        if (DPL) for (int64_t i = 0; i < T; ++i) {
+        // sum over the eight lanes that hold the same columns (rsub = lane >> 2)
+        auto oct8 = [](float v) {
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            return v + __shfl_xor_sync(0xffffffffu, v, 16);
+        };
+        if (BWD) for (int64_t i = 0; i < T; ++i) {
+            const int d = (int)(i & 1);
+            const uint32_t par_d = (uint32_t)((i >> 1) & 1);
+            const uint32_t taddr = tbase + d * NPAD;
+            const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + pl;
+            const bool live = pr < g.n;
+            const int64_t prc = live ? pr : g.n - 1;
+            const float *ar0 = g.apre + prc * g.rw + 2 * cq, *ar1 = g.apre + (g.pre_cap + prc) * g.rw + 2 * cq;
+            WAIT_OFFPATH(&d_full[d], par_d);                         // dL/du of this tile
+            tc_fence_after();
+            float ss0 = 0.f, ss1 = 0.f, ad0 = 0.f, ad1 = 0.f;
+#pragma unroll 2
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                uint32_t v[8];
+                tmem_ld_16x256b_x2(taddr + c0, v);
+                const float2 p0 = *reinterpret_cast<const float2 *>(ar0 + c0), p1 = *reinterpret_cast<const float2 *>(ar0 + c0 + 8);
+                const float2 q0 = *reinterpret_cast<const float2 *>(ar1 + c0), q1 = *reinterpret_cast<const float2 *>(ar1 + c0 + 8);
+                tmem_ld_wait();
+                ss0 = fmaf(p0.x, p0.x, ss0); ss0 = fmaf(p0.y, p0.y, ss0); ss0 = fmaf(p1.x, p1.x, ss0); ss0 = fmaf(p1.y, p1.y, ss0);
+                ss1 = fmaf(q0.x, q0.x, ss1); ss1 = fmaf(q0.y, q0.y, ss1); ss1 = fmaf(q1.x, q1.x, ss1); ss1 = fmaf(q1.y, q1.y, ss1);
+                ad0 = fmaf(p0.x, __uint_as_float(v[0]), ad0); ad0 = fmaf(p0.y, __uint_as_float(v[1]), ad0);
+                ad0 = fmaf(p1.x, __uint_as_float(v[4]), ad0); ad0 = fmaf(p1.y, __uint_as_float(v[5]), ad0);
+                ad1 = fmaf(q0.x, __uint_as_float(v[2]), ad1); ad1 = fmaf(q0.y, __uint_as_float(v[3]), ad1);
+                ad1 = fmaf(q1.x, __uint_as_float(v[6]), ad1); ad1 = fmaf(q1.y, __uint_as_float(v[7]), ad1);
+            }
+            ss0 = quad4(ss0); ss1 = quad4(ss1); ad0 = quad4(ad0); ad1 = quad4(ad1);
+            // F.normalize (models.py:368): u = a / max(|a|, eps); below the clamp it is the linear map a / eps
+            const float n0 = sqrtf(ss0), n1 = sqrtf(ss1);
+            const float den0 = fmaxf(n0, 1e-12f), den1 = fmaxf(n1, 1e-12f);
+            const bool cl0 = !(n0 > 1e-12f), cl1 = !(n1 > 1e-12f);
+            const float rr0 = cl0 ? 1e12f : 1.f / den0, rr1 = cl1 ? 1e12f : 1.f / den1;
+            const float dot0 = cl0 ? 0.f : ad0 / den0, dot1 = cl1 ? 0.f : ad1 / den1;      // u . du
+            float *ur0 = g.uout + pr * g.rw + 2 * cq, *ur1 = g.uout + (g.out_cap + pr) * g.rw + 2 * cq;
+            float *dr0 = g.daout + pr * g.rw + 2 * cq, *dr1 = g.daout + (g.out_cap + pr) * g.rw + 2 * cq;
+#pragma unroll 2
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                uint32_t v[8];
+                tmem_ld_16x256b_x2(taddr + c0, v);
+                const float2 p0 = *reinterpret_cast<const float2 *>(ar0 + c0), p1 = *reinterpret_cast<const float2 *>(ar0 + c0 + 8);
+                const float2 q0 = *reinterpret_cast<const float2 *>(ar1 + c0), q1 = *reinterpret_cast<const float2 *>(ar1 + c0 + 8);
+                tmem_ld_wait();
+                const float2 u00 = make_float2(p0.x / den0, p0.y / den0), u01 = make_float2(p1.x / den0, p1.y / den0);
+                const float2 u10 = make_float2(q0.x / den1, q0.y / den1), u11 = make_float2(q1.x / den1, q1.y / den1);
+                float2 e00, e01, e10, e11;
+                e00.x = (__uint_as_float(v[0]) - u00.x * dot0) * rr0; e00.y = (__uint_as_float(v[1]) - u00.y * dot0) * rr0;
+                e01.x = (__uint_as_float(v[4]) - u01.x * dot0) * rr0; e01.y = (__uint_as_float(v[5]) - u01.y * dot0) * rr0;
+                e10.x = (__uint_as_float(v[2]) - u10.x * dot1) * rr1; e10.y = (__uint_as_float(v[3]) - u10.y * dot1) * rr1;
+                e11.x = (__uint_as_float(v[6]) - u11.x * dot1) * rr1; e11.y = (__uint_as_float(v[7]) - u11.y * dot1) * rr1;
+                if (!live) e00 = e01 = e10 = e11 = make_float2(0.f, 0.f);
+                if (live) {
+                    *reinterpret_cast<float2 *>(ur0 + c0) = u00; *reinterpret_cast<float2 *>(ur0 + c0 + 8) = u01;
+                    *reinterpret_cast<float2 *>(ur1 + c0) = u10; *reinterpret_cast<float2 *>(ur1 + c0 + 8) = u11;
+                    *reinterpret_cast<float2 *>(dr0 + c0) = e00; *reinterpret_cast<float2 *>(dr0 + c0 + 8) = e01;
+                    *reinterpret_cast<float2 *>(dr1 + c0) = e10; *reinterpret_cast<float2 *>(dr1 + c0 + 8) = e11;
+                }
+                // b1 gradient: column sums of dL/da over the tile's rows
+                const float t0 = oct8(e00.x + e10.x), t1 = oct8(e00.y + e10.y), t2 = oct8(e01.x + e11.x), t3 = oct8(e01.y + e11.y);
+                if (rsub == 0) {
+                    atomicAdd(colacc + c0 + 2 * cq, t0); atomicAdd(colacc + c0 + 2 * cq + 1, t1);
+                    atomicAdd(colacc + c0 + 8 + 2 * cq, t2); atomicAdd(colacc + c0 + 8 + 2 * cq + 1, t3);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&d_empty[d]);
+        }
+        else if (DPL) for (int64_t i = 0; i < T; ++i) {
             const int d = (int)(i & 1);
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
             const uint32_t taddr = tbase + d * NPAD;
@@ -524,7 +615,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         float amax = 0.f;       // MODE 1 range guard: largest |x| this thread saw in the current tile
         int stage_in_tile = 0;
         int64_t tile_i = 0;
+        int bs_next = 0;        // BWD: stage within the tile / tile of iteration `it`
+        int64_t bt_next = 0;
         for (int64_t it = 0; it < total; ++it, rx.advance(), ra.advance()) {
+            const int bs = bs_next;
+            const int64_t bt = bt_next;
+            if (BWD && ++bs_next == g.nst1) { bs_next = 0; ++bt_next; }
             // MODE 1 range guard, evaluated after the last stage of every tile: both converter sets count
             // stages and each checks the values it converted (its pair's two rows, 8 columns of every other
             // stage).  The e4m3 terms need typical |x| in about [2^-3, 2^8); outside that, the call is flagged and
@@ -561,6 +657,45 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             // registers of tcgen05.st.16x256b.x2: r0,r1 -> (row, cols 2j,2j+1)  r2,r3 -> (row+8, same cols);
             // r4..r7 the same for the next 8 columns (k + 16)
             if (odd) { float4 t = a0; a0 = a1; a1 = t; t = b0; b0 = b1; b1 = t; }
+            if (BWD) {
+                // a0 / a1: y of side 0 at columns col0 .. col0 + 3 / col0 + 16 .. col0 + 19, b0 / b1: side 1.  They become
+                // dL/dy = 2 g (Q y_self + P y_other); columns >= NPAD are padding (y reads as 0 there: TMA zero fill).
+                const int64_t pr = (blockIdx.x + bt * gridDim.x) * TP + pl;
+                const bool live = pr < g.n;
+                const float g2 = live ? 2.f * g.ds[pr] : 0.f;
+                const int col0 = bs * KST + 4 * cq, col1 = col0 + 16;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 P0 = *reinterpret_cast<const float4 *>(par + 2 * NPAD + col0), Q0 = *reinterpret_cast<const float4 *>(par + 3 * NPAD + col0);
+                const bool in1 = col1 < NPAD;
+                const float4 P1 = in1 ? *reinterpret_cast<const float4 *>(par + 2 * NPAD + col1) : z4;
+                const float4 Q1 = in1 ? *reinterpret_cast<const float4 *>(par + 3 * NPAD + col1) : z4;
+                float sb[8], sq[8], sp[8];
+                auto one = [&](float &ya, float &yb, float P, float Q, int j) {
+                    const float da = g2 * fmaf(Q, ya, P * yb), db = g2 * fmaf(Q, yb, P * ya);
+                    sb[j] = da + db;
+                    sq[j] = 0.5f * g2 * fmaf(ya, ya, yb * yb);
+                    sp[j] = g2 * ya * yb;
+                    ya = da; yb = db;
+                };
+                one(a0.x, b0.x, P0.x, Q0.x, 0); one(a0.y, b0.y, P0.y, Q0.y, 1); one(a0.z, b0.z, P0.z, Q0.z, 2); one(a0.w, b0.w, P0.w, Q0.w, 3);
+                one(a1.x, b1.x, P1.x, Q1.x, 4); one(a1.y, b1.y, P1.y, Q1.y, 5); one(a1.z, b1.z, P1.z, Q1.z, 6); one(a1.w, b1.w, P1.w, Q1.w, 7);
+                if (live) {
+                    float *g0 = g.gout + pr * g.rw, *g1 = g.gout + (g.out_cap + pr) * g.rw;
+                    *reinterpret_cast<float4 *>(g0 + col0) = a0; *reinterpret_cast<float4 *>(g1 + col0) = b0;
+                    if (in1) { *reinterpret_cast<float4 *>(g0 + col1) = a1; *reinterpret_cast<float4 *>(g1 + col1) = b1; }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float v0 = sb[j], v1 = sq[j], v2 = sp[j];
+                    v0 += __shfl_xor_sync(0xffffffffu, v0, 4); v1 += __shfl_xor_sync(0xffffffffu, v1, 4); v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
+                    v0 += __shfl_xor_sync(0xffffffffu, v0, 8); v1 += __shfl_xor_sync(0xffffffffu, v1, 8); v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
+                    v0 += __shfl_xor_sync(0xffffffffu, v0, 16); v1 += __shfl_xor_sync(0xffffffffu, v1, 16); v2 += __shfl_xor_sync(0xffffffffu, v2, 16);
+                    const int c = (j < 4 ? col0 : col1) + (j & 3);
+                    if (rsub == 0 && c < NPAD) {
+                        atomicAdd(colacc + NPAD + c, v0); atomicAdd(colacc + 2 * NPAD + c, v1); atomicAdd(colacc + 3 * NPAD + c, v2);
+                    }
+                }
+            }
             uint32_t hi[8], lo[8];
             if (MODE == 1) {
                 // hi[0..7]: fp16 of x (same register layout as the bf16 path); lo[0..3]: e4m3 of (x - hi) * 2^9,
@@ -756,6 +891,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                 const int64_t j = i - 1;                           // the tile whose square products are issued in this round
                 const int dj = (int)(j & 1);
                 const uint32_t par_j = (uint32_t)((j >> 1) & 1);
+                if (BWD) {                  // one product per tile: dL/du = dL/dy W2
+                    if (i < T) {
+                        mbar_wait(&d_empty[i & 1], (uint32_t)(((i >> 1) & 1) ^ 1));
+                        tc_fence_after();
+                        layer1(dcol_i, 0, g.nst1);
+                        if (elect_one()) mma_commit(&d_full[i & 1]);
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 if (DPL) {
                     // thirds of layer 1 around the two products: Y_P (needs U), Y_R (needs the epilogue's pass over Y_P)
                     const int c1 = g.nst1 / 3, c2s = 2 * g.nst1 / 3;
@@ -795,7 +940,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             if (T > 0) {
                 for (int k = 0; k < NA; ++k) { mbar_wait(&a_empty[ra.stage], ra.phase ^ 1); ra.advance(); }
                 for (int k = 0; k < NBS; ++k) { mbar_wait(&b_empty[rb.stage], rb.phase ^ 1); rb.advance(); }
-                if (!DPL) mbar_wait(u_empty, (uint32_t)((T & 1) ^ 1));
+                if (!DPL && !BWD) mbar_wait(u_empty, (uint32_t)((T & 1) ^ 1));
             }
             PMARK(7);
             if (lane == 0) PFLUSH(3);
@@ -828,6 +973,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             };
             const int c1 = g.nst1 / 3, c2s = 2 * g.nst1 / 3;           // DPL: the MMA warp's order (thirds of layer 1)
             for (int64_t i = 0; i <= T; ++i) {
+                if (BWD) {
+                    if (i < T) put_l1(0, g.nst1);
+                    continue;
+                }
                 if (DPL) {
                     if (i < T) put_l1(0, c1);
                     if (i >= 1) put_sq(g.w2img);
@@ -869,6 +1018,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == WARP_MMA) tmem_dealloc(tmem, 512);
+    if (BWD && T > 0) {
+        for (int c = tid; c < NPAD; c += NTHREADS) {
+            if (g.db1 && c < g.nb1) atomicAdd(g.db1 + c, colacc[c]);
+            if (g.db2 && c < g.nb2) atomicAdd(g.db2 + c, colacc[NPAD + c]);
+            if (g.dq && c < g.nb2) atomicAdd(g.dq + c, colacc[2 * NPAD + c]);
+            if (g.dpsqrt && c < g.nb2) atomicAdd(g.dpsqrt + c, colacc[3 * NPAD + c] * g.psq2[c]);      // dP * 2 P_sqrt
+        }
+    }
     if (MODE == 0 && g.guard != nullptr && T > 0 && tid == 0) {
         // fallback pass: every CTA read guard[0] when it started; the last one to finish clears the slot
         __threadfence();
@@ -1169,9 +1326,9 @@ static int *guard_slot() {
     return ring[dev] + 2 * (ticket.fetch_add(1, std::memory_order_relaxed) & 1023u);
 }
 
-template <bool PROF, int MODE, bool EMIT = false, bool DPL = false>
+template <bool PROF, int MODE, bool EMIT = false, bool DPL = false, bool BWD = false>
 static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Args &a, int grid, cudaStream_t st) {
-    auto kern = tcg::score_tc_kernel<PROF, MODE, EMIT, DPL>;
+    auto kern = tcg::score_tc_kernel<PROF, MODE, EMIT, DPL, BWD>;
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
     kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
     NPLDA_LAUNCH_CHECK();
@@ -1406,6 +1563,33 @@ int score_tc_rows_emit(const float *xa, const float *xb, int64_t n, int row_widt
     a.trace = nullptr; a.dbg = 0;
     const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
     return launch_tc<false, 0, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
+}
+
+// Middle of NeuralPlda's backward in one launch (BWD instantiation): y rows + a rows + dL/dS in; U, dL/dy, dL/da rows
+// and the b1 / b2 / Q / P_sqrt gradients out.  yrows / arows: [.][rw] fp32 with side 1 `pre_cap` rows after side 0; the
+// outputs with side 1 `out_cap` rows after side 0 (dL/dy may overwrite yrows, dL/da may overwrite arows: every element is
+// read and then written by the same thread).  w2t_img: tc_rows_image_pack of W2 (K = layer-2 index, padded to d_k).
+int score_tc_bwd_mid(const float *yrows, const float *arows, int64_t pre_cap, int64_t n, int rw, int d_k, int d1, int d2,
+                     const uint8_t *w2t_img, const float *p, const float *q, const float *psq2, const float *dscores,
+                     float *U, float *G, float *DA, int64_t out_cap, float *db1, float *db2, float *dq, float *dpsqrt,
+                     cudaStream_t st) {
+    if (d_k % tcg::KST != 0 || d_k < tcg::KST || rw != tcg::NPAD || rw > d_k || d1 > tcg::NPAD || d2 > tcg::NPAD) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (n >= (int64_t)1 << 31 || out_cap < n || pre_cap < n || !U || !G || !DA || !dscores) return NPLDA_ERR_BAD_ARG;
+    CUtensorMap m1, m2;
+    if (!tcg::make_x_map(&m1, yrows, n, rw, rw) || !tcg::make_x_map(&m2, yrows + pre_cap * rw, n, rw, rw)) return NPLDA_ERR_NO_DEVICE;
+    tcg::Args a;
+    a.x1 = yrows; a.x2 = yrows + pre_cap * rw; a.n = n;
+    a.nst1 = d_k / tcg::KST; a.ksteps2 = 0;
+    a.w1img = w2t_img; a.w2img = nullptr; a.w3img = nullptr; a.cbias = nullptr;
+    a.hdr = p; a.hdr16 = p; a.guard = nullptr;
+    a.b1 = p; a.b2 = p; a.p = p; a.q = q;               // b1 / b2 slots are not read by this instantiation
+    a.scores = nullptr; a.aout = nullptr; a.yout = nullptr; a.emit_cap = 0;
+    a.trace = nullptr; a.dbg = 0;
+    a.ds = dscores; a.apre = arows; a.pre_cap = pre_cap; a.out_cap = out_cap; a.rw = rw;
+    a.uout = U; a.gout = G; a.daout = DA;
+    a.db1 = db1; a.db2 = db2; a.dq = dq; a.dpsqrt = dpsqrt; a.psq2 = psq2; a.nb1 = d1; a.nb2 = d2;
+    const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
+    return launch_tc<false, 0, false, false, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
 }
 
 }  // namespace nplda

@@ -5,13 +5,17 @@ import neuralplda_b200 as npl
 import bench
 dev = torch.device("cuda:0")
 kp = bench.kaldi_params()
-def timeit(fn, reps=5):
-    fn(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+def timeit(fn, reps=12):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        fn(); ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+    print(f"    per-iteration ms: min {ts[0]:.2f} median {ts[reps // 2]:.2f} max {ts[-1]:.2f}")
+    return ts[reps // 2]
 class NCX(bench.NC):
     loss = "crossentropy"
 class NCD(bench.NC):
