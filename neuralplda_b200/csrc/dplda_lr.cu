@@ -20,7 +20,7 @@ int gemm_tn_auto(const float *A, int lda, int M, const float *B, int ldb, int N,
 namespace dlr {
 
 constexpr int LD = 176;                   // floats per row (EMIT_LD of score_tc.cu)
-constexpr int64_t CHUNK_PAIRS = 131072;
+constexpr int64_t CHUNK_PAIRS = 524288;
 
 __global__ void __launch_bounds__(256) sd_rows_kernel(const float *__restrict__ U0, const float *__restrict__ U1,
                                                       const float *__restrict__ g, int64_t nc, float *__restrict__ S,

@@ -44,7 +44,7 @@ namespace bwd {
 
 using namespace simt;
 
-constexpr int64_t CHUNK_PAIRS = 131072;
+constexpr int64_t CHUNK_PAIRS = 524288;
 constexpr int COLACC = 4 * NP;                       // floats of per-CTA column accumulators
 constexpr int BWD_SMEM_BYTES = SMEM_BYTES + COLACC * 4 + 16;
 

@@ -73,9 +73,10 @@ constexpr int SM_B = SM_X + NX * X_STAGE;
 constexpr int SM_U = SM_B + NBS * B_STAGE;
 constexpr int SM_PAR = SM_U + 2 * U_HALF;                 // b1, b2, P, Q (NPAD floats each)
 constexpr int SM_BAR = SM_PAR + 4 * NPAD * 4;
-constexpr int N_BARS = 2 * NX + 2 * NA + 2 * NBS + 12;
+constexpr int N_BARS = 2 * NX + 2 * NA + 2 * NBS + 14;
 constexpr int SM_TMEM = SM_BAR + N_BARS * 8;
-constexpr int SMEM_BYTES = SM_TMEM + 16 + 1024;       // + slack for the 1 KB alignment
+constexpr int SM_COL = SM_TMEM + 16;                  // BWD: [4][NPAD] column sums
+constexpr int SMEM_BYTES = SM_COL + 4 * NPAD * 4 + 1024;   // + slack for the 1 KB alignment
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 struct Args {
@@ -168,6 +169,27 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
                  : "memory");
 }
 
+// Reduce-scatter over the eight lanes that differ in lane bits 4, 3, 2 (the rows of a 16x256b fragment): every lane
+// contributes v[0..7]; lane l gets the sum over the eight lanes of v[(l >> 2) & 7].  7 shuffles instead of 24.
+__device__ __forceinline__ float reduce_scatter8(const float (&v)[8], int lane) {
+    const bool u2 = (lane & 16) != 0, u1 = (lane & 8) != 0, u0 = (lane & 4) != 0;
+    float w[4], x[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = (u2 ? v[j + 4] : v[j]) + __shfl_xor_sync(0xffffffffu, u2 ? v[j] : v[j + 4], 16);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) x[j] = (u1 ? w[j + 2] : w[j]) + __shfl_xor_sync(0xffffffffu, u1 ? w[j] : w[j + 2], 8);
+    return (u0 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, u0 ? x[0] : x[1], 4);
+}
+// The same for four values: lane l gets the sum over the eight lanes of v[2 * bit4(l) + bit3(l)] (both lanes of a bit-2 pair).
+__device__ __forceinline__ float reduce_scatter4(const float (&v)[4], int lane) {
+    const bool u2 = (lane & 16) != 0, u1 = (lane & 8) != 0;
+    float w[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) w[j] = (u2 ? v[j + 2] : v[j]) + __shfl_xor_sync(0xffffffffu, u2 ? v[j] : v[j + 2], 16);
+    float x = (u1 ? w[1] : w[0]) + __shfl_xor_sync(0xffffffffu, u1 ? w[0] : w[1], 8);
+    return x + __shfl_xor_sync(0xffffffffu, x, 4);
+}
+
 // Cycle accounting (PROF instantiation only, env NPLDA_TC_PROF): every role keeps a running clock and
 // charges the time since the previous mark to a bucket; CTA 0 writes role * 16 + bucket at exit.
 #define PMARK(b) do { if (PROF) { const long long _t = clock64(); pacc[b] += _t - ptime; ptime = _t; } } while (0)
@@ -198,7 +220,8 @@ constexpr int EMIT_LD = NPAD;  // 176: row stride of the emitted a / y rows (= t
 // a rows pass: every row is read once and written once.
 template <bool PROF, int MODE, bool EMIT, bool DPL = false, bool BWD = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
-score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, Args g) {
+score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                const __grid_constant__ CUtensorMap map3, Args g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: 1 KB aligned
     uint8_t *Xs = smem + SM_X;
@@ -211,6 +234,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
     uint64_t *d_full = b_empty + NBS, *d_empty = d_full + 2, *y_full = d_full + 4;
     uint64_t *u_full = d_full + 6, *u_empty = d_full + 7;
     uint64_t *y2_full = d_full + 8, *p2a_done = d_full + 10;      // DPL: second product published / first one consumed
+    uint64_t *at_full = d_full + 12;                              // BWD: a rows of the tile landed in shared memory
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -230,9 +254,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         mbar_init(u_full, EPI_WARPS * 32);
         mbar_init(u_empty, 1);
         for (int d = 0; d < 2; ++d) { mbar_init(&y2_full[d], 1); mbar_init(&p2a_done[d], EPI_WARPS * 32); }
+        mbar_init(at_full, 1);
         mbar_fence_init();
     }
-    float *colacc = reinterpret_cast<float *>(Us);            // BWD: [4][NPAD] column sums db1, db2, dq, dp (U is not used)
+    float *colacc = reinterpret_cast<float *>(smem + SM_COL);  // BWD: [4][NPAD] column sums db1, db2, dq, dp
     if (BWD)
         for (int i = tid; i < 4 * NPAD; i += NTHREADS) colacc[i] = 0.f;
     if (warp == WARP_MMA) tmem_alloc(tmem_slot, 512);
@@ -376,16 +401,30 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             return v + __shfl_xor_sync(0xffffffffu, v, 16);
         };
+        // BWD: the a rows of a tile ([64 pairs][176] per side = the whole U region) are fetched by TMA while the tile's
+        // product runs: issued by one epilogue thread once all eight warps have finished with the previous tile's rows.
+        // (Loading them from global memory in the column loops left the epilogue latency-bound: 20 us per tile.)
+        auto fetch_a_tile = [&](int64_t i) {
+            const int row0 = (int)((blockIdx.x + i * gridDim.x) * TP);
+            mbar_arrive_expect_tx(at_full, 2 * U_HALF);
+            tma_load_2d(Us, &map3, 0, row0, at_full);
+            tma_load_2d(Us + U_HALF, &map3, 0, (int)g.pre_cap + row0, at_full);
+        };
+        if (BWD && T > 0 && tid == 0) fetch_a_tile(0);
+        float eacc[NPAD / 16];                                   // BWD: running b1-gradient sums, one column per 16-column chunk
+#pragma unroll
+        for (int ci = 0; ci < NPAD / 16; ++ci) eacc[ci] = 0.f;
         if (BWD) for (int64_t i = 0; i < T; ++i) {
             const int d = (int)(i & 1);
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
             const uint32_t taddr = tbase + d * NPAD;
             const int64_t pr = (blockIdx.x + i * gridDim.x) * TP + pl;
             const bool live = pr < g.n;
-            const int64_t prc = live ? pr : g.n - 1;
-            const float *ar0 = g.apre + prc * g.rw + 2 * cq, *ar1 = g.apre + (g.pre_cap + prc) * g.rw + 2 * cq;
+            const float *ar0 = reinterpret_cast<const float *>(Us) + pl * NPAD + 2 * cq;
+            const float *ar1 = reinterpret_cast<const float *>(Us + U_HALF) + pl * NPAD + 2 * cq;
             WAIT_OFFPATH(&d_full[d], par_d);                         // dL/du of this tile
             tc_fence_after();
+            WAIT_OFFPATH(at_full, (uint32_t)(i & 1));                // its a rows
             float ss0 = 0.f, ss1 = 0.f, ad0 = 0.f, ad1 = 0.f;
 #pragma unroll 2
             for (int c0 = 0; c0 < NPAD; c0 += 16) {
@@ -410,15 +449,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const float dot0 = cl0 ? 0.f : ad0 / den0, dot1 = cl1 ? 0.f : ad1 / den1;      // u . du
             float *ur0 = g.uout + pr * g.rw + 2 * cq, *ur1 = g.uout + (g.out_cap + pr) * g.rw + 2 * cq;
             float *dr0 = g.daout + pr * g.rw + 2 * cq, *dr1 = g.daout + (g.out_cap + pr) * g.rw + 2 * cq;
-#pragma unroll 2
-            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+#pragma unroll
+            for (int ci = 0; ci < NPAD / 16; ++ci) {
+                const int c0 = ci * 16;
                 uint32_t v[8];
                 tmem_ld_16x256b_x2(taddr + c0, v);
                 const float2 p0 = *reinterpret_cast<const float2 *>(ar0 + c0), p1 = *reinterpret_cast<const float2 *>(ar0 + c0 + 8);
                 const float2 q0 = *reinterpret_cast<const float2 *>(ar1 + c0), q1 = *reinterpret_cast<const float2 *>(ar1 + c0 + 8);
                 tmem_ld_wait();
-                const float2 u00 = make_float2(p0.x / den0, p0.y / den0), u01 = make_float2(p1.x / den0, p1.y / den0);
-                const float2 u10 = make_float2(q0.x / den1, q0.y / den1), u11 = make_float2(q1.x / den1, q1.y / den1);
+                // u = a / max(|a|, eps) as a * (1 / max(|a|, eps)) (1e12 under the clamp)
+                const float2 u00 = make_float2(p0.x * rr0, p0.y * rr0), u01 = make_float2(p1.x * rr0, p1.y * rr0);
+                const float2 u10 = make_float2(q0.x * rr1, q0.y * rr1), u11 = make_float2(q1.x * rr1, q1.y * rr1);
                 float2 e00, e01, e10, e11;
                 e00.x = (__uint_as_float(v[0]) - u00.x * dot0) * rr0; e00.y = (__uint_as_float(v[1]) - u00.y * dot0) * rr0;
                 e01.x = (__uint_as_float(v[4]) - u01.x * dot0) * rr0; e01.y = (__uint_as_float(v[5]) - u01.y * dot0) * rr0;
@@ -431,16 +472,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     *reinterpret_cast<float2 *>(dr0 + c0) = e00; *reinterpret_cast<float2 *>(dr0 + c0 + 8) = e01;
                     *reinterpret_cast<float2 *>(dr1 + c0) = e10; *reinterpret_cast<float2 *>(dr1 + c0 + 8) = e11;
                 }
-                // b1 gradient: column sums of dL/da over the tile's rows
-                const float t0 = oct8(e00.x + e10.x), t1 = oct8(e00.y + e10.y), t2 = oct8(e01.x + e11.x), t3 = oct8(e01.y + e11.y);
-                if (rsub == 0) {
-                    atomicAdd(colacc + c0 + 2 * cq, t0); atomicAdd(colacc + c0 + 2 * cq + 1, t1);
-                    atomicAdd(colacc + c0 + 8 + 2 * cq, t2); atomicAdd(colacc + c0 + 8 + 2 * cq + 1, t3);
-                }
+                // b1 gradient: this lane keeps the running sum of ONE of the chunk's four columns (eacc_col below)
+                const float t[4] = {e00.x + e10.x, e00.y + e10.y, e01.x + e11.x, e01.y + e11.y};
+                eacc[ci] += reduce_scatter4(t, lane);
             }
             tc_fence_before();
             mbar_arrive(&d_empty[d]);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");      // every epilogue warp is done with the a rows
+            if (tid == 0 && i + 1 < T) fetch_a_tile(i + 1);
         }
+        if (BWD && (lane & 4) == 0) {
+            // the column of chunk ci this lane owns: value index 2 bit4 + bit3 of {2cq, 2cq + 1, 8 + 2cq, 8 + 2cq + 1}
+            const int sel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+            const int coff = (sel >> 1) * 8 + 2 * cq + (sel & 1);
+#pragma unroll
+            for (int ci = 0; ci < NPAD / 16; ++ci) atomicAdd(colacc + ci * 16 + coff, eacc[ci]);
+        }
+        if (BWD) {}
         else if (DPL) for (int64_t i = 0; i < T; ++i) {
             const int d = (int)(i & 1);
             const uint32_t par_d = (uint32_t)((i >> 1) & 1);
@@ -617,6 +665,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         int64_t tile_i = 0;
         int bs_next = 0;        // BWD: stage within the tile / tile of iteration `it`
         int64_t bt_next = 0;
+        float cacc[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // BWD: [slot][db2, dq, dp] column sums
         for (int64_t it = 0; it < total; ++it, rx.advance(), ra.advance()) {
             const int bs = bs_next;
             const int64_t bt = bt_next;
@@ -684,17 +733,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     *reinterpret_cast<float4 *>(g0 + col0) = a0; *reinterpret_cast<float4 *>(g1 + col0) = b0;
                     if (in1) { *reinterpret_cast<float4 *>(g0 + col1) = a1; *reinterpret_cast<float4 *>(g1 + col1) = b1; }
                 }
+                // column sums: after the reduce-scatter lane rsub owns column j = rsub of this thread's eight; the set sees
+                // stage bs of every tile in slot bs / 2, always with the same columns -> running sums in registers
+                const float r0 = reduce_scatter8(sb, lane), r1 = reduce_scatter8(sq, lane), r2 = reduce_scatter8(sp, lane);
+                const int slot = bs >> 1;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float v0 = sb[j], v1 = sq[j], v2 = sp[j];
-                    v0 += __shfl_xor_sync(0xffffffffu, v0, 4); v1 += __shfl_xor_sync(0xffffffffu, v1, 4); v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
-                    v0 += __shfl_xor_sync(0xffffffffu, v0, 8); v1 += __shfl_xor_sync(0xffffffffu, v1, 8); v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
-                    v0 += __shfl_xor_sync(0xffffffffu, v0, 16); v1 += __shfl_xor_sync(0xffffffffu, v1, 16); v2 += __shfl_xor_sync(0xffffffffu, v2, 16);
-                    const int c = (j < 4 ? col0 : col1) + (j & 3);
-                    if (rsub == 0 && c < NPAD) {
-                        atomicAdd(colacc + NPAD + c, v0); atomicAdd(colacc + 2 * NPAD + c, v1); atomicAdd(colacc + 3 * NPAD + c, v2);
-                    }
-                }
+                for (int sl = 0; sl < 3; ++sl)
+                    if (sl == slot) { cacc[sl][0] += r0; cacc[sl][1] += r1; cacc[sl][2] += r2; }
             }
             uint32_t hi[8], lo[8];
             if (MODE == 1) {
@@ -759,6 +804,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             if (lane == 0) mbar_arrive(&a_full[ra.stage]);
             if (tile_end) guard_check();
             PMARK(4);
+        }
+        if (BWD) {
+#pragma unroll
+            for (int sl = 0; sl < 3; ++sl) {
+                const int bs = 2 * sl + cset;                        // nst1 == 6: the set's stages of a tile are cset, cset + 2, cset + 4
+                const int c = bs * KST + 4 * cq + (rsub < 4 ? rsub : 12 + rsub);
+                if (c < NPAD) {
+                    atomicAdd(colacc + NPAD + c, cacc[sl][0]); atomicAdd(colacc + 2 * NPAD + c, cacc[sl][1]);
+                    atomicAdd(colacc + 3 * NPAD + c, cacc[sl][2]);
+                }
+            }
         }
         if ((warp == EPI_WARPS || warp == EPI_WARPS + CONV_WARPS) && lane == 0) PFLUSH(1 + cset);
     } else if (warp == WARP_MMA) {
@@ -1327,10 +1383,11 @@ static int *guard_slot() {
 }
 
 template <bool PROF, int MODE, bool EMIT = false, bool DPL = false, bool BWD = false>
-static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Args &a, int grid, cudaStream_t st) {
+static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Args &a, int grid, cudaStream_t st,
+                     const CUtensorMap *m3 = nullptr) {
     auto kern = tcg::score_tc_kernel<PROF, MODE, EMIT, DPL, BWD>;
     NPLDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES));
-    kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, a);
+    kern<<<grid, tcg::NTHREADS, tcg::SMEM_BYTES, st>>>(m1, m2, m3 ? *m3 : m1, a);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }
@@ -1573,8 +1630,8 @@ int score_tc_bwd_mid(const float *yrows, const float *arows, int64_t pre_cap, in
                      const uint8_t *w2t_img, const float *p, const float *q, const float *psq2, const float *dscores,
                      float *U, float *G, float *DA, int64_t out_cap, float *db1, float *db2, float *dq, float *dpsqrt,
                      cudaStream_t st) {
-    if (d_k % tcg::KST != 0 || d_k < tcg::KST || rw != tcg::NPAD || rw > d_k || d1 > tcg::NPAD || d2 > tcg::NPAD) return NPLDA_ERR_UNSUPPORTED_DIM;
-    if (n >= (int64_t)1 << 31 || out_cap < n || pre_cap < n || !U || !G || !DA || !dscores) return NPLDA_ERR_BAD_ARG;
+    if (d_k != 6 * tcg::KST || rw != tcg::NPAD || d1 > tcg::NPAD || d2 > tcg::NPAD) return NPLDA_ERR_UNSUPPORTED_DIM;   // 6 stages: see the converters' column sums
+    if (pre_cap + n >= (int64_t)1 << 31 || out_cap < n || pre_cap < n || !U || !G || !DA || !dscores) return NPLDA_ERR_BAD_ARG;
     CUtensorMap m1, m2;
     if (!tcg::make_x_map(&m1, yrows, n, rw, rw) || !tcg::make_x_map(&m2, yrows + pre_cap * rw, n, rw, rw)) return NPLDA_ERR_NO_DEVICE;
     tcg::Args a;
@@ -1588,8 +1645,20 @@ int score_tc_bwd_mid(const float *yrows, const float *arows, int64_t pre_cap, in
     a.ds = dscores; a.apre = arows; a.pre_cap = pre_cap; a.out_cap = out_cap; a.rw = rw;
     a.uout = U; a.gout = G; a.daout = DA;
     a.db1 = db1; a.db2 = db2; a.dq = dq; a.dpsqrt = dpsqrt; a.psq2 = psq2; a.nb1 = d1; a.nb2 = d2;
+    // a rows of both sides through one map: [pre_cap + n rows][rw], whole-row boxes of 64 rows, no swizzle
+    CUtensorMap m3;
+    {
+        tcg::EncodeTiledFn enc = tcg::encode_fn();
+        if (!enc) return NPLDA_ERR_NO_DEVICE;
+        cuuint64_t dims[2] = {(cuuint64_t)rw, (cuuint64_t)(pre_cap + n)};
+        cuuint64_t strides[1] = {(cuuint64_t)rw * 4};
+        cuuint32_t box[2] = {(cuuint32_t)rw, tcg::TP}, es[2] = {1, 1};
+        if (enc(&m3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)arows, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return NPLDA_ERR_NO_DEVICE;
+    }
     const int64_t nt = (n + tcg::TP - 1) / tcg::TP;
-    return launch_tc<false, 0, false, false, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st);
+    return launch_tc<false, 0, false, false, true>(m1, m2, a, (int)std::min<int64_t>(nt, sm_count()), st, &m3);
 }
 
 }  // namespace nplda
