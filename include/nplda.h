@@ -197,6 +197,20 @@ int nplda_table_prepare(const float *table, int64_t n_rows, int d_in, int d1, in
                         int is_dplda, float *rowtab, int flags, void *stream);
 int nplda_score_pairs(const float *rowtab, int64_t n_rows, const int64_t *idx1, const int64_t *idx2,
                       int64_t n, float *scores, int32_t *bad_index_flag, void *stream);
+
+/* Dense trial lists (key files written enrol-major, every model against the same segments): when the list covers a
+ * sizeable fraction of (its enrol rows) x (its test rows), one grid product over those rows (nplda_score_grid) and a
+ * 4-byte gather per trial replace the per-trial row gather of nplda_score_pairs (scorefile_generator.py:29-36 / 46-53
+ * gathers and transforms both sides of every trial).
+ *   nplda_trial_rows: flags [2][n_rows] int32 (scratch), pos [2][n_rows] int32 (rank of a row among the rows the list
+ *     uses on that side, -1 if unused), list [2][n_rows] int64 (the used rows, ascending), counts [2] int32; side 0 =
+ *     idx1 (enrol), side 1 = idx2 (test).  The caller reads `counts` to size the grid [counts[0]][counts[1]].
+ *   nplda_trial_grid_gather: scores[t] = grid[pos[0][idx1[t]] * ld + pos[1][idx2[t]]]  (0 for rows outside the table,
+ *     which nplda_trial_rows reported through bad_index_flag). */
+int nplda_trial_rows(const int64_t *idx1, const int64_t *idx2, int64_t n, int64_t n_rows, int32_t *flags, int32_t *pos,
+                     int64_t *list, int32_t *counts, int32_t *bad_index_flag, void *stream);
+int nplda_trial_grid_gather(const float *grid, int64_t ld, const int32_t *pos, int64_t n_rows, const int64_t *idx1,
+                            const int64_t *idx2, int64_t n, float *scores, void *stream);
 /* nplda_score_grid: the full enrol x test grid of a trial list (BASELINE.json configs[2]/[3];
  * the id x cohort matrix utils/adaptive_score_normalization.py:32 reads) as one
  * [n_enrol,176] x [176,n_test] fp32 product over the row table:

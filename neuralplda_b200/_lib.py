@@ -54,6 +54,8 @@ SIGNATURES = {
     "nplda_rowtab_bytes": (c_i64, [c_i64]),
     "nplda_table_prepare": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "nplda_score_pairs": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "nplda_trial_rows": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nplda_trial_grid_gather": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "nplda_embed_fwd": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "nplda_score_from_embeddings": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "dplda_score_from_embeddings": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),

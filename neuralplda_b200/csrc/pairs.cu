@@ -139,9 +139,91 @@ __global__ void __launch_bounds__(256) score_pairs_kernel(const float *__restric
     }
 }
 
+// ---- dense trial lists: sub-grid + gather ------------------------------------------------------------------------
+// A trial list that covers a sizeable fraction of (its enrol rows) x (its test rows) -- key files are written enrol-major,
+// every model against the same segments -- is cheaper as ONE grid product over those rows on the tensor cores
+// (grid_tc.cu: ~2.7 ps per grid entry) followed by a 4-byte gather per trial than as one 704-byte row gather per trial:
+//   1. trial_rows_mark:    flags[0][i1[t]] = flags[1][i2[t]] = 1              (one pass over the index lists)
+//   2. trial_rows_compact: pos[s][row] = rank of the row among the marked ones, list[s][rank] = row, counts[s]
+//   3. nplda_score_grid over list[0] x list[1]   (the caller reads the two counts to size the grid)
+//   4. trial_grid_gather:  scores[t] = grid[pos[0][i1[t]]][pos[1][i2[t]]]
+__global__ void __launch_bounds__(256) trial_rows_mark_kernel(const int64_t *__restrict__ i1, const int64_t *__restrict__ i2, int64_t n,
+                                                              int64_t n_rows, int32_t *__restrict__ flags, int32_t *bad_flag) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = i1[t], b = i2[t];
+        if (a < 0 || a >= n_rows || b < 0 || b >= n_rows) { *bad_flag = 1; continue; }
+        if (flags[a] == 0) flags[a] = 1;                       // benign race: every writer stores 1
+        if (flags[n_rows + b] == 0) flags[n_rows + b] = 1;
+    }
+}
+
+// one CTA per side: every thread owns a contiguous segment of rows
+__global__ void __launch_bounds__(1024) trial_rows_compact_kernel(const int32_t *__restrict__ flags, int64_t n_rows,
+                                                                  int32_t *__restrict__ pos, int64_t *__restrict__ list,
+                                                                  int32_t *__restrict__ counts) {
+    __shared__ int32_t part[1024];
+    const int side = blockIdx.x, tid = threadIdx.x;
+    const int32_t *f = flags + side * n_rows;
+    const int64_t seg = (n_rows + 1023) / 1024, r0 = min(n_rows, tid * seg), r1 = min(n_rows, r0 + seg);
+    int32_t c = 0;
+    for (int64_t r = r0; r < r1; ++r) c += f[r] != 0;
+    part[tid] = c;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                       // inclusive scan
+        const int32_t v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int32_t k = part[tid] - c;
+    for (int64_t r = r0; r < r1; ++r) {
+        if (f[r] != 0) { pos[side * n_rows + r] = k; list[side * n_rows + k] = r; ++k; }
+        else pos[side * n_rows + r] = -1;
+    }
+    if (tid == 1023) counts[side] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) trial_grid_gather_kernel(const float *__restrict__ grid, int64_t ld, const int32_t *__restrict__ pos,
+                                                                int64_t n_rows, const int64_t *__restrict__ i1,
+                                                                const int64_t *__restrict__ i2, int64_t n, float *__restrict__ scores) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = i1[t], b = i2[t];
+        float v = 0.f;                                          // rows outside the table: reported by the mark pass
+        if (a >= 0 && a < n_rows && b >= 0 && b < n_rows) v = grid[(int64_t)pos[a] * ld + pos[n_rows + b]];
+        scores[t] = v;
+    }
+}
+
 }  // namespace nplda
 
 using namespace nplda;
+
+extern "C" int nplda_trial_rows(const int64_t *idx1, const int64_t *idx2, int64_t n, int64_t n_rows, int32_t *flags, int32_t *pos,
+                                int64_t *list, int32_t *counts, int32_t *bad_index_flag, void *stream) {
+    if (n < 0 || n_rows <= 0 || n_rows >= ((int64_t)1 << 31) || !flags || !pos || !list || !counts || !bad_index_flag ||
+        (n > 0 && (!idx1 || !idx2)))
+        return NPLDA_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    NPLDA_CUDA_TRY(cudaMemsetAsync(flags, 0, 2 * n_rows * sizeof(int32_t), st));
+    if (n > 0) {
+        const int grid = (int)std::min<int64_t>((n + 255) / 256, 16 * (int64_t)sm_count());
+        trial_rows_mark_kernel<<<grid, 256, 0, st>>>(idx1, idx2, n, n_rows, flags, bad_index_flag);
+        NPLDA_LAUNCH_CHECK();
+    }
+    trial_rows_compact_kernel<<<2, 1024, 0, st>>>(flags, n_rows, pos, list, counts);
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
+}
+
+extern "C" int nplda_trial_grid_gather(const float *grid, int64_t ld, const int32_t *pos, int64_t n_rows, const int64_t *idx1,
+                                       const int64_t *idx2, int64_t n, float *scores, void *stream) {
+    if (n < 0 || n_rows <= 0 || (n > 0 && (!grid || !pos || !idx1 || !idx2 || !scores))) return NPLDA_ERR_BAD_ARG;
+    if (n == 0) return NPLDA_OK;
+    const int g = (int)std::min<int64_t>((n + 255) / 256, 16 * (int64_t)sm_count());
+    trial_grid_gather_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(grid, ld, pos, n_rows, idx1, idx2, n, scores);
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
+}
 
 extern "C" int64_t nplda_rowtab_bytes(int64_t n_rows) {
     if (n_rows < 0) return NPLDA_ERR_BAD_ARG;

@@ -376,6 +376,34 @@ def score_from_embeddings(kind, e1, e2, params, dims, packed):
 
 
 SPLIT_MIN_TRIALS = 128       # one CTA-pair tile; below, the fp32 kernels are launch-bound either way
+GRID_GATHER_MIN_TRIALS = 1 << 18     # dense-list path: worth its extra launches and the read-back of two row counts
+GRID_GATHER_MAX_FILL = 6             # ... when the sub-grid has at most this many entries per trial
+GRID_GATHER_MAX_BYTES = 2 << 30      # ... and fits this scratch budget
+
+
+def _score_dense_list(rowtab, n_rows, i1, i2, scores, flag_ptr):
+    """Trial list as a sub-grid + gather (csrc/pairs.cu): True if the list was dense enough and `scores` is filled.
+    Reads the two row counts back to the host (one small synchronising copy) to size the grid."""
+    dev = rowtab.device
+    n = i1.numel()
+    flags = torch.empty(2 * n_rows, dtype=torch.int32, device=dev)
+    pos = torch.empty(2 * n_rows, dtype=torch.int32, device=dev)
+    lst = torch.empty(2 * n_rows, dtype=torch.int64, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    with on_device(dev):
+        check(lib().nplda_trial_rows(ptr(i1), ptr(i2), n, n_rows, ptr(flags), ptr(pos), ptr(lst), ptr(counts), flag_ptr,
+                                     stream_ptr()), "nplda_trial_rows")
+        ne, nt = counts.tolist()
+        cells = ne * nt
+        if cells == 0 or cells > GRID_GATHER_MAX_FILL * n or cells * 4 > GRID_GATHER_MAX_BYTES:
+            return False
+        ld = (nt + 3) // 4 * 4
+        grid = torch.empty(ne * ld, dtype=torch.float32, device=dev)
+        check(lib().nplda_score_grid_impl(ptr(rowtab), n_rows, ptr(lst), ne, ptr(lst[n_rows:]), nt, ptr(grid), ld, flag_ptr,
+                                          _lib.IMPL_AUTO, stream_ptr()), "nplda_score_grid")
+        check(lib().nplda_trial_grid_gather(ptr(grid), ld, ptr(pos), n_rows, ptr(i1), ptr(i2), n, ptr(scores), stream_ptr()),
+              "nplda_trial_grid_gather")
+    return True
 
 
 def _flag(dev, flag_ptr):
@@ -414,6 +442,8 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
         scores = torch.empty(n, dtype=torch.float32, device=dev)
         fp, flag = _flag(dev, flag_ptr)
         rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
+        if n >= GRID_GATHER_MIN_TRIALS and impl != _lib.IMPL_SIMT and _score_dense_list(rowtab, table.shape[0], i1, i2, scores, fp):
+            return scores, flag
         with on_device(dev):
             check(lib().nplda_score_pairs(ptr(rowtab), table.shape[0], ptr(i1), ptr(i2), n, ptr(scores), fp,
                                           stream_ptr()), "nplda_score_pairs")

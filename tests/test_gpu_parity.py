@@ -610,6 +610,44 @@ def test_large_properties_1m(kaldi_params):
         assert ok, worst
 
 
+@pytest.mark.parametrize("kind", ["nplda", "dplda"])
+def test_dense_trial_list_subgrid_gather(ref_out, kaldi_params, kind, monkeypatch):
+    """Dense trial lists go through a sub-grid product over the rows the list uses + a 4-byte gather per trial
+    (nplda_trial_rows / nplda_score_grid / nplda_trial_grid_gather); sparse ones through one row gather per trial
+    (nplda_score_pairs).  Same scores either way (both within the bound of the oracle), bad rows reported and scored 0."""
+    kp = kaldi_params
+    table, i1, i2, _ = O.synth_grid(300, 700, 60, seed=77, mean=kp["mean"])
+    g = torch.Generator().manual_seed(5)
+    keep = torch.rand(i1.numel(), generator=g) < 0.4                     # 40 % of a 300 x 700 grid, in list order
+    a, b = i1[keep].clone(), i2[keep].clone()
+    b[1234] = 10_000                                                     # a row outside the table
+    m = make_nplda(kp) if kind == "nplda" else make_dplda(kp, ref_out)
+    t = table.to(DEV)
+    monkeypatch.setattr(F_, "GRID_GATHER_MIN_TRIALS", 1 << 40)
+    s_pairs, f_pairs = m.forward_indexed(t, a.to(DEV), b.to(DEV), embed_once=True)
+    monkeypatch.setattr(F_, "GRID_GATHER_MIN_TRIALS", 1)
+    launches = _lib.lib().nplda_launch_count()
+    s_grid, f_grid = m.forward_indexed(t, a.to(DEV), b.to(DEV), embed_once=True)
+    assert int(f_pairs.item()) == 1 and int(f_grid.item()) == 1
+    assert float(s_grid[1234]) == 0.0 and float(s_pairs[1234]) == 0.0
+    ok = torch.ones(a.numel(), dtype=torch.bool); ok[1234] = False
+    if kind == "nplda":
+        ref = O.nplda_score(table[a[ok]], table[b[ok]], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    else:
+        w, c = dplda_weights(ref_out)
+        ref = O.dplda_score(table[a[ok]], table[b[ok]], kp["W1"], kp["b1"], w, c)
+    for s in (s_pairs, s_grid):
+        good, worst = parity_ok(s.cpu()[ok], ref, rel=1e-4)
+        assert good, worst
+    # a sparse list (one trial per enrol row) stays on the per-trial kernel: the sub-grid would have 300 cells per trial
+    monkeypatch.setattr(F_, "GRID_GATHER_MIN_TRIALS", 1)
+    sp_a, sp_b = torch.arange(300), 300 + torch.arange(300)
+    s_sp, _ = m.forward_indexed(t, sp_a.to(DEV), sp_b.to(DEV), embed_once=True)
+    np.testing.assert_allclose(s_sp.cpu().numpy(), m.forward_grid(t, sp_a.to(DEV), sp_b.to(DEV))[0].diagonal().cpu().numpy(),
+                               rtol=1e-5, atol=1e-5)
+    assert _lib.lib().nplda_launch_count() > launches
+
+
 def test_config3_10m_grid_trial_list(kaldi_params):
     """BASELINE.json configs[2]: 10M trials = 2500 enrol x 4000 test grid over 6500 x-vectors, indexed layout.
     Oracle on a strided subsample; properties: the grid is symmetric under swapping the roles of the two index
@@ -624,10 +662,14 @@ def test_config3_10m_grid_trial_list(kaldi_params):
     ref = O.nplda_score(table[i1[sub]], table[i2[sub]], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
     ok, worst = parity_ok(s[sub.to(DEV)], ref, rel=1e-4)
     assert ok, worst
-    s_swapped, _ = m.forward_indexed(t, b, a)                       # S(i, j) == S(j, i) (models.py:373-375 is symmetric)
-    np.testing.assert_allclose(s_swapped.cpu().numpy(), s.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    # S(i, j) == S(j, i) (models.py:373-375 is symmetric); the list is dense, so it is scored as a sub-grid on the tensor
+    # cores and swapping the lists swaps the roles of the fp16 hi/lo operands: equal up to that rounding (a tenth of the bound)
+    s_swapped, _ = m.forward_indexed(t, b, a)
+    np.testing.assert_allclose(s_swapped.cpu().numpy(), s.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # ragged chunks: the one-trial chunk takes the per-trial fp32 kernel, the large ones their own sub-grids
     parts = [m.forward_indexed(t, a[lo:hi], b[lo:hi])[0] for lo, hi in ((0, 1), (1, 3_333_333), (3_333_333, 10_000_000))]
-    assert torch.equal(torch.cat(parts), s)
+    np.testing.assert_allclose(torch.cat(parts).cpu().numpy(), s.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(torch.cat(parts[1:]), s[1:])                 # the same grid cell gives the same bits in any sub-grid
     # targets score higher than non-targets on this generator: a degenerate kernel would not separate them
     labd = lab.to(DEV).bool()
     assert float(s[labd].mean()) > float(s[~labd].mean()) + 0.5
