@@ -5,111 +5,255 @@
 // With s = u1 + u2, d = u1 - u2 and g = dL/dS:
 //     u1 u1^T + u2 u2^T = (s s^T + d d^T) / 2        u1 u2^T + u2 u1^T = (s s^T - d d^T) / 2
 // so   dWw = (Ps + Pd) / 2,  dWb = (Ps - Pd) / 2,  Ps = sum_p g_p s_p s_p^T,  Pd = sum_p g_p d_p d_p^T
-// -- two batch contractions instead of four (and dws = sum_p g_p s_p, dc = sum_p g_p).  Per chunk of pairs one
-// elementwise kernel writes the rows S, D, gS, gD (and reduces dws, dc), the two contractions run on tcgen05
-// (gemm_tc.cu, bf16x3), and a small kernel folds Ps, Pd into the gradient.
+// -- two SYMMETRIC batch contractions instead of four (and dws = sum_p g_p s_p, dc = sum_p g_p).
+//
+// One kernel (wgrad_kernel), one pass over the rows: a CTA owns a contiguous range of pairs; 24 converter warps read
+// u1, u2 (each element once), form s, d, g s, g d, split them into bf16 hi/lo and store the 16-byte K-runs in the K-major
+// core-matrix layout (K = pairs); one elected thread issues hi*hi + lo*hi + hi*lo into four accumulators in tensor memory:
+// rows [0, 128) x all 176 columns of Ps and Pd, plus their [128, 176) x [128, 176) corner blocks -- the rest follows from
+// symmetry.  The epilogue adds (Ps +- Pd) / 2 to the gradient with fp32 reductions.
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace nplda {
 
-int gemm_tn_auto(const float *A, int lda, int M, const float *B, int ldb, int N, int64_t R, float *C, int ldc,
-                 cudaStream_t st);   // score_bwd.cu: C[m][n] += sum_r A[r][m] B[r][n]
-
 namespace dlr {
 
-constexpr int LD = 176;                   // floats per row (EMIT_LD of score_tc.cu)
-constexpr int64_t CHUNK_PAIRS = 524288;
+using namespace tc;
 
-__global__ void __launch_bounds__(256) sd_rows_kernel(const float *__restrict__ U0, const float *__restrict__ U1,
-                                                      const float *__restrict__ g, int64_t nc, float *__restrict__ S,
-                                                      float *__restrict__ D, float *__restrict__ GS, float *__restrict__ GD,
-                                                      float *__restrict__ dws, int d1, float *__restrict__ dc) {
-    __shared__ float4 col[8][LD / 4];
-    __shared__ float gsum[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-    float gacc = 0.f;
-    for (int64_t p = w0; p < nc; p += nw) {
-        const float gg = g[p];
-        gacc += gg;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int k = lane + 32 * h;
-            if (k >= LD / 4) continue;
-            const float4 a = reinterpret_cast<const float4 *>(U0 + p * LD)[k], b = reinterpret_cast<const float4 *>(U1 + p * LD)[k];
-            const float4 s = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-            const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
-            const float4 gs = make_float4(gg * s.x, gg * s.y, gg * s.z, gg * s.w);
-            reinterpret_cast<float4 *>(S + p * LD)[k] = s;
-            reinterpret_cast<float4 *>(D + p * LD)[k] = d;
-            reinterpret_cast<float4 *>(GS + p * LD)[k] = gs;
-            reinterpret_cast<float4 *>(GD + p * LD)[k] = make_float4(gg * d.x, gg * d.y, gg * d.z, gg * d.w);
-            acc[h].x += gs.x; acc[h].y += gs.y; acc[h].z += gs.z; acc[h].w += gs.w;
-        }
+constexpr int LD = 176;                   // floats per row (EMIT_LD of score_tc.cu) = MMA N of the big blocks
+constexpr int MT = 128;                   // feature rows of the big blocks; the corner block covers [MT, LD)
+constexpr int NC = LD - MT;               // 48
+constexpr int KS = 32;                    // pairs per stage
+constexpr int KCH = (LD / 8) * 128;       // 2816 B: one K-chunk (8 pairs) of an image: 22 core matrices of 8 features x 8 pairs
+constexpr int IMG = (KS / 8) * KCH;       // 11264 B: hi (or lo) image of one of s, d, g s, g d
+constexpr int STAGE_BYTES = 8 * IMG;      // [s hi][s lo][d hi][d lo][gs hi][gs lo][gd hi][gd lo]
+constexpr int NSTAGE = 2;
+constexpr int CONV_WARPS = 24;            // warp w: 8-pair group w & 3, 32-column group w >> 2
+constexpr int NTHREADS = (CONV_WARPS + 1) * 32;
+constexpr int HDR_BYTES = 1024;
+// the corner blocks' A operand (M = 128) starts at feature 128 and reads 80 feature rows past the image: finite bf16
+// values of the following chunks / images, rows whose results are never read; the slack keeps the last one in bounds
+constexpr int SMEM_BYTES = HDR_BYTES + NSTAGE * STAGE_BYTES + 16 * 128;
+// TMEM columns: Ps[0:128][:] | Ps corner | Pd[0:128][:] | Pd corner
+constexpr int COL_S0 = 0, COL_S1 = LD, COL_D0 = LD + NC, COL_D1 = 2 * LD + NC;
+
+struct Args {
+    const float *U0, *U1, *g;      // side 0 / side 1 rows of this launch, dL/dS
+    int64_t n, rows_per_cta;
+    int d1;
+    float *dWb, *dWw, *dws, *dc;   // dWb / dWw: [d1][d1]; any may be null (dWb and dWw together)
+};
+
+__device__ __forceinline__ void wait_or_trap(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_addr(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
     }
-    col[warp][lane] = acc[0];
-    if (lane + 32 < LD / 4) col[warp][lane + 32] = acc[1];
-    if (lane == 0) gsum[warp] = gacc;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(Args a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);            // [NSTAGE] converters -> MMA
+    uint64_t *empty = full + NSTAGE;                                // [NSTAGE] MMA -> converters
+    uint64_t *done = empty + NSTAGE;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+    uint8_t *stages = smem + HDR_BYTES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t r0 = blockIdx.x * a.rows_per_cta, r1 = min(a.n, r0 + a.rows_per_cta);
+    if (r0 >= r1) return;
+    const int nit = (int)((r1 - r0 + KS - 1) / KS);
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], CONV_WARPS); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    // the slack behind the last stage is read (never used): keep it finite
+    for (int i = tid; i < 16 * 128 / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(stages + NSTAGE * STAGE_BYTES)[i] = 0u;
+    fence_proxy_async();
+    if (warp == CONV_WARPS) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
     __syncthreads();
-    if (dws != nullptr)
-        for (int c = threadIdx.x; c < d1; c += blockDim.x) {
-            float v = 0.f;
-            for (int w = 0; w < 8; ++w) v += reinterpret_cast<const float *>(col[w])[c];
-            atomicAdd(dws + c, v);
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t IDESC_BIG = make_idesc_bf16(MT, LD), IDESC_CORNER = make_idesc_bf16(MT, NC);
+
+    if (warp < CONV_WARPS) {
+        // ---------------- converters ----------------
+        const int grp = warp & 3, c = (warp >> 2) * 32 + lane;       // 8-pair group of the stage, column
+        const bool col_ok = c < LD;                                  // the sixth column group is half empty
+        const bool col_live = c < a.d1;
+        const int soff = grp * KCH + (c >> 3) * 128 + (c & 7) * 16;  // this thread's 16-byte K-run inside an image
+        auto load_stage = [&](int it, float (&u0)[8], float (&u1)[8], float (&gg)[8]) {
+            const int64_t rb = r0 + (int64_t)it * KS + grp * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool ok = col_live && rb + j < r1;
+                u0[j] = ok ? __ldg(a.U0 + (rb + j) * LD + c) : 0.f;
+                u1[j] = ok ? __ldg(a.U1 + (rb + j) * LD + c) : 0.f;
+                gg[j] = rb + j < r1 ? __ldg(a.g + rb + j) : 0.f;
+            }
+        };
+        float wsum = 0.f, gsum = 0.f;
+        auto store_stage = [&](const float (&u0)[8], const float (&u1)[8], const float (&gg)[8], uint8_t *st) {
+            float s[8], d[8], gs[8], gd[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] = u0[j] + u1[j]; d[j] = u0[j] - u1[j];
+                gs[j] = gg[j] * s[j]; gd[j] = gg[j] * d[j];
+                wsum += gs[j]; gsum += gg[j];
+            }
+            if (!col_ok) return;
+            auto put = [&](const float (&v)[8], int img) {
+                uint4 hi, lo;
+                split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
+                split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
+                *reinterpret_cast<uint4 *>(st + (2 * img) * IMG + soff) = hi;
+                *reinterpret_cast<uint4 *>(st + (2 * img + 1) * IMG + soff) = lo;
+            };
+            put(s, 0); put(d, 1); put(gs, 2); put(gd, 3);
+        };
+        uint32_t stage = 0, phase = 0;
+        float a0[8], a1[8], ag[8], b0[8], b1[8], bg[8];
+        load_stage(0, a0, a1, ag);
+        for (int it = 0; it < nit; it += 2) {
+            if (it + 1 < nit) load_stage(it + 1, b0, b1, bg);
+            wait_or_trap(&empty[stage], phase ^ 1);
+            store_stage(a0, a1, ag, stages + stage * STAGE_BYTES);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            if (it + 1 >= nit) break;
+            if (it + 2 < nit) load_stage(it + 2, a0, a1, ag);
+            wait_or_trap(&empty[stage], phase ^ 1);
+            store_stage(b0, b1, bg, stages + stage * STAGE_BYTES);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-    if (dc != nullptr && threadIdx.x == 0) {
-        float v = 0.f;
-        for (int w = 0; w < 8; ++w) v += gsum[w];
-        atomicAdd(dc, v);
+        if (a.dws && col_live) atomicAdd(a.dws + c, wsum);
+        // the four row groups of column group 0 cover every pair once, all lanes with the same sum: lane 0 adds it
+        if (a.dc && (warp >> 2) == 0 && lane == 0) atomicAdd(a.dc, gsum);
+        // ---------------- epilogue: dWw += (Ps + Pd) / 2, dWb += (Ps - Pd) / 2 ----------------
+        wait_or_trap(done, 0);
+        tc_fence_after();
+        if (a.dWw != nullptr) {
+            const int q4 = warp & 3, sub = warp >> 2;                 // TMEM quadrant; six warps share it
+            const int m = 32 * q4 + lane;                             // feature row of the big blocks / m - 128 of the corner
+            const uint32_t lane_base = tmem + ((uint32_t)(32 * q4) << 16);
+            for (int blk = sub; blk < LD / 16; blk += CONV_WARPS / 4) {
+                uint32_t ps[16], pd[16];
+                tmem_ld16(lane_base + COL_S0 + blk * 16, ps);
+                tmem_ld16(lane_base + COL_D0 + blk * 16, pd);
+                tmem_ld_wait();
+                if (m < a.d1) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int n = blk * 16 + e;
+                        if (n >= a.d1) continue;
+                        const float vs = __uint_as_float(ps[e]), vd = __uint_as_float(pd[e]);
+                        const float ww = 0.5f * (vs + vd), wb = 0.5f * (vs - vd);
+                        atomicAdd(a.dWw + (int64_t)n * a.d1 + m, ww);         // [n][m]: lanes write consecutive addresses
+                        atomicAdd(a.dWb + (int64_t)n * a.d1 + m, wb);
+                        if (n >= MT) {                                       // the mirror entries [m][n] of rows >= 128
+                            atomicAdd(a.dWw + (int64_t)m * a.d1 + n, ww);
+                            atomicAdd(a.dWb + (int64_t)m * a.d1 + n, wb);
+                        }
+                    }
+                }
+            }
+            // corner blocks: rows / columns [128, 176) (lanes 0..47 of the accumulator)
+            if (q4 < 2) {                                             // warp-uniform: tcgen05.ld is a whole-warp instruction
+                for (int blk = sub; blk < NC / 16; blk += CONV_WARPS / 4) {
+                    uint32_t ps[16], pd[16];
+                    tmem_ld16(lane_base + COL_S1 + blk * 16, ps);
+                    tmem_ld16(lane_base + COL_D1 + blk * 16, pd);
+                    tmem_ld_wait();
+                    if (m >= NC || MT + m >= a.d1) continue;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int n = MT + blk * 16 + e;
+                        if (n >= a.d1) continue;
+                        const float vs = __uint_as_float(ps[e]), vd = __uint_as_float(pd[e]);
+                        atomicAdd(a.dWw + (int64_t)n * a.d1 + MT + m, 0.5f * (vs + vd));
+                        atomicAdd(a.dWb + (int64_t)n * a.d1 + MT + m, 0.5f * (vs - vd));
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------- MMA warp ----------------
+        uint32_t stage = 0, phase = 0;
+        const uint32_t sbase = smem_addr(stages);
+        for (int it = 0; it < nit; ++it) {
+            wait_or_trap(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t st = sbase + stage * STAGE_BYTES;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < KS / 16; ++ks) {
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr) {                  // 0: s (images 0, 2), 1: d (images 1, 3)
+                        const uint32_t x = st + (2 * pr) * IMG + 2 * ks * KCH, gx = st + (2 * (pr + 2)) * IMG + 2 * ks * KCH;
+                        const uint64_t bhi = make_smem_desc(x, KCH, 128), blo = make_smem_desc(x + IMG, KCH, 128);
+                        const uint64_t ahi = make_smem_desc(gx, KCH, 128), alo = make_smem_desc(gx + IMG, KCH, 128);
+                        const uint32_t dbig = tmem + (pr ? COL_D0 : COL_S0), dcor = tmem + (pr ? COL_D1 : COL_S1);
+                        const uint32_t acc = (it | ks) != 0;
+                        mma_ss(dbig, ahi, bhi, IDESC_BIG, acc);
+                        mma_ss(dbig, alo, bhi, IDESC_BIG, 1);
+                        mma_ss(dbig, ahi, blo, IDESC_BIG, 1);
+                        constexpr uint32_t off = (MT / 8) * 128 >> 4;          // feature 128: 16 core matrices into a chunk
+                        mma_ss(dcor, ahi + off, bhi + off, IDESC_CORNER, acc);
+                        mma_ss(dcor, alo + off, bhi + off, IDESC_CORNER, 1);
+                        mma_ss(dcor, ahi + off, blo + off, IDESC_CORNER, 1);
+                    }
+                }
+                mma_commit(&empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) mma_commit(done);
+        __syncwarp();
     }
-}
 
-__global__ void fold_kernel(const float *__restrict__ Ps, const float *__restrict__ Pd, int d1, float *__restrict__ dWb,
-                            float *__restrict__ dWw) {
-    const int total = d1 * d1;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const float a = Ps[e], b = Pd[e];
-        dWw[e] += 0.5f * (a + b);
-        dWb[e] += 0.5f * (a - b);
-    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CONV_WARPS) tmem_dealloc(tmem, 512);
 }
-
-static int64_t cap_for(int64_t n) { return std::min(n, CHUNK_PAIRS); }
-static int64_t p_floats(int d1) { return ((int64_t)d1 * d1 + 63) / 64 * 64; }
 
 }  // namespace dlr
 
-int64_t dplda_lr_workspace_bytes(int64_t n, int d1) { return (4 * dlr::cap_for(n) * dlr::LD + 2 * dlr::p_floats(d1)) * 4; }
+int64_t dplda_lr_workspace_bytes(int64_t, int) { return 256; }      // none needed (kept in the ABI for callers that size one)
 
 // urows: [2 cap][176], side 1 `cap` rows after side 0
 int dplda_lr_grad(const float *urows, int64_t n, int64_t cap, int d1, const float *dscores, float *dw_lr, float *dc_lr,
                   void *workspace, int64_t workspace_bytes, cudaStream_t st) {
-    if (!workspace || ((uintptr_t)workspace & 255) != 0) return NPLDA_ERR_BAD_ARG;
-    if (workspace_bytes < dplda_lr_workspace_bytes(n, d1)) return NPLDA_ERR_WORKSPACE;
-    const int64_t wc = dlr::cap_for(n);
-    float *Ps = (float *)workspace, *Pd = Ps + dlr::p_floats(d1);
-    float *S = Pd + dlr::p_floats(d1), *D = S + wc * dlr::LD, *GS = D + wc * dlr::LD, *GD = GS + wc * dlr::LD;
-    float *dWb = dw_lr, *dWw = dw_lr ? dw_lr + (int64_t)d1 * d1 : nullptr, *dws = dw_lr ? dw_lr + 2 * (int64_t)d1 * d1 : nullptr;
-    if (dw_lr) NPLDA_CUDA_TRY(cudaMemsetAsync(Ps, 0, 2 * dlr::p_floats(d1) * 4, st));
-    for (int64_t c0 = 0; c0 < n; c0 += dlr::CHUNK_PAIRS) {
-        const int64_t nc = std::min(dlr::CHUNK_PAIRS, n - c0);
-        const int grid = (int)std::min<int64_t>((nc + 7) / 8, 8 * (int64_t)sm_count());
-        dlr::sd_rows_kernel<<<grid, 256, 0, st>>>(urows + c0 * dlr::LD, urows + (cap + c0) * dlr::LD, dscores + c0, nc, S, D, GS, GD,
-                                                  dws, d1, dc_lr);
-        NPLDA_LAUNCH_CHECK();
-        if (!dw_lr) continue;
-        int rc = gemm_tn_auto(GS, dlr::LD, d1, S, dlr::LD, d1, nc, Ps, d1, st);
-        if (rc != NPLDA_OK) return rc;
-        rc = gemm_tn_auto(GD, dlr::LD, d1, D, dlr::LD, d1, nc, Pd, d1, st);
-        if (rc != NPLDA_OK) return rc;
-    }
-    if (dw_lr) {
-        dlr::fold_kernel<<<32, 256, 0, st>>>(Ps, Pd, d1, dWb, dWw);
-        NPLDA_LAUNCH_CHECK();
-    }
+    (void)workspace; (void)workspace_bytes;
+    if (d1 > dlr::LD || d1 < 1) return NPLDA_ERR_UNSUPPORTED_DIM;
+    dlr::Args a;
+    a.U0 = urows; a.U1 = urows + cap * dlr::LD; a.g = dscores; a.n = n; a.d1 = d1;
+    a.dWb = dw_lr; a.dWw = dw_lr ? dw_lr + (int64_t)d1 * d1 : nullptr; a.dws = dw_lr ? dw_lr + 2 * (int64_t)d1 * d1 : nullptr;
+    a.dc = dc_lr;
+    int64_t rows = (n + sm_count() - 1) / sm_count();
+    rows = std::max<int64_t>((rows + dlr::KS - 1) / dlr::KS * dlr::KS, 4 * dlr::KS);
+    a.rows_per_cta = rows;
+    const int grid = (int)((n + rows - 1) / rows);
+    NPLDA_CUDA_TRY(cudaFuncSetAttribute(dlr::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dlr::SMEM_BYTES));
+    dlr::wgrad_kernel<<<grid, dlr::NTHREADS, dlr::SMEM_BYTES, st>>>(a);
+    NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }
 

@@ -120,6 +120,9 @@ extern "C" int nplda_pack_weights(const float *W1, const float *b1, const float 
     PackLayout L = make_pack_layout(d_in, d1, d2);
     if (pack_bytes < L.total) return NPLDA_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    // the slot this pack adds into starts from zero whatever the caller's epoch sequence was (a captured CUDA graph
+    // replays ONE parity: without this its replays would keep adding into the same slot)
+    NPLDA_CUDA_TRY(cudaMemsetAsync((char *)pack + L.fp + 8 * ((flags >> 1) & 1), 0, 8, st));
     pack_nplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack, (flags >> 1) & 1);
     NPLDA_LAUNCH_CHECK();
     const int rc = tc_pack_nplda(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack, flags, st);
@@ -135,6 +138,7 @@ extern "C" int dplda_pack_weights(const float *W1, const float *b1, const float 
     PackLayout L = make_pack_layout(d_in, d1, d1);
     if (pack_bytes < L.total) return NPLDA_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    NPLDA_CUDA_TRY(cudaMemsetAsync((char *)pack + L.fp + 8 * ((flags >> 1) & 1), 0, 8, st));
     pack_dplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, w_lr, c_lr, L, (char *)pack, (flags >> 1) & 1);
     NPLDA_LAUNCH_CHECK();
     return tc_pack_dplda(W1, b1, w_lr, c_lr, L, (char *)pack, st);

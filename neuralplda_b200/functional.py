@@ -56,6 +56,8 @@ class PackedWeights:
         check(rc, "pack_weights")
         return self.buf
 
+    dense_skip = 0            # dense-list probe (score_indexed): calls left to skip / current back-off
+    dense_backoff = 0
     rowtab = None
     rowtab_key = None
     rowtab_table = None       # strong reference to the table the cached rows were built from
@@ -442,8 +444,17 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
         scores = torch.empty(n, dtype=torch.float32, device=dev)
         fp, flag = _flag(dev, flag_ptr)
         rowtab = packed.get_rowtab(kind, table, params, d_in, d1, d2)
-        if n >= GRID_GATHER_MIN_TRIALS and impl != _lib.IMPL_SIMT and _score_dense_list(rowtab, table.shape[0], i1, i2, scores, fp):
-            return scores, flag
+        if n >= GRID_GATHER_MIN_TRIALS and impl != _lib.IMPL_SIMT:
+            # lists over this table that turned out sparse are not probed again for a while (the probe costs one pass
+            # over the index lists and a small synchronising read-back): back-off doubles up to 1024 calls
+            if packed.dense_skip > 0:
+                packed.dense_skip -= 1
+            elif _score_dense_list(rowtab, table.shape[0], i1, i2, scores, fp):
+                packed.dense_backoff = 0
+                return scores, flag
+            else:
+                packed.dense_backoff = min(1024, max(8, 2 * packed.dense_backoff))
+                packed.dense_skip = packed.dense_backoff
         with on_device(dev):
             check(lib().nplda_score_pairs(ptr(rowtab), table.shape[0], ptr(i1), ptr(i2), n, ptr(scores), fp,
                                           stream_ptr()), "nplda_score_pairs")
