@@ -480,7 +480,7 @@ def _run_ours(args, saved_stdout):
 
     # ---- end to end: the reference's own call path from HOST data (xvector_NeuralPlda_pytorch.py:36-41) ----------
     from neuralplda_b200 import sv_trials_loaders as L
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
     mega, spk = synth_corpus(kp)
     num_to_id = {i: j for i, j in enumerate(list(mega))}
     hi1, hi2, hlab = (v.pin_memory() for v in synth_trials(spk, n, seed=77 + rank))
@@ -572,7 +572,8 @@ def _run_ours(args, saved_stdout):
                     "table": {"utterances": TABLE_UTTS, "one_off_upload_bytes": TABLE_UTTS * D_IN * 4, "one_off_upload_s": upload_s,
                               "amortisation": "uploaded once per (dict, device) and kept; not in the timed steps -- the "
                                               "reference's loop gathers from the same dict for every batch of every epoch"},
-                    "libnplda_launches_per_step": launches_e2e},
+                    "libnplda_launches_per_step": launches_e2e,
+                    "h2d_gb_per_s_all_ranks": world * n * 20 * e2e_steps / e2e_s / 1e9},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "loss": {"softcdet": loss_vals[0], "bce": loss_vals[1], "cdet": loss_vals[2], "e2e_softcdet": e2e_loss},
@@ -689,7 +690,7 @@ def multi_gpu_legs(model, kp, dev, world, rank):
         with torch.no_grad():
             return model.softcdet(model(x1, x2), t)        # K1 + K2 + all-reduce of the 12 fp64 accumulators + finalize
 
-    for _ in range(2):
+    for _ in range(3):
         step3()
     dist.barrier(); torch.cuda.synchronize()
     ms = sync_max(_event_time(step3, 5, stream))
@@ -725,7 +726,7 @@ def multi_gpu_legs(model, kp, dev, world, rank):
         ndist.allreduce_gradients(d)                           # NCCL sum of the 57 972 parameter gradients
         return loss
 
-    for _ in range(2):
+    for _ in range(3):
         step4()
     dist.barrier(); torch.cuda.synchronize()
     ms4 = sync_max(_event_time(step4, 5, stream))
@@ -740,7 +741,7 @@ def multi_gpu_legs(model, kp, dev, world, rank):
 def train_leg(kp, dev, x1, x2, t):
     """Extra, separately-labelled measurement: one training step (forward + BCE loss + backward into .grad) through the
     module API on the resident 1M-pair batch, for NeuralPlda and for DPlda with the LDA frozen
-    (BASELINE.json configs[4]; its per-GPU share at 8 GPUs is 1.25M pairs).  CUDA events, 5 steps after one warm-up."""
+    (BASELINE.json configs[4]; its per-GPU share at 8 GPUs is 1.25M pairs), each against its HBM floor."""
     import neuralplda_b200 as npl
 
     class NCX(NC):
@@ -750,19 +751,28 @@ def train_leg(kp, dev, x1, x2, t):
         loss = "crossentropy"
         beta = [99.0]
 
-    def timeit(fn, reps=5):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
+    def timeit(fn, reps=10):
+        for _ in range(3):               # the caching allocator settles on the step's GB-sized buffers after two steps
             fn()
-        e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        return float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]))
 
     n = x1.shape[0]
-    out = {"pairs": n, "loss": "crossentropy", "api": "model(x1, x2) -> model.loss(...) -> .backward()"}
+    peak = measured_peaks()["hbm"] * 1e9
+
+    def entry(ms, floor_bytes_per_pair, what):
+        floor_ms = n * floor_bytes_per_pair / peak * 1e3
+        return {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "pairs/s", "hbm_floor_ms": floor_ms, "frac_of_hbm_floor": floor_ms / ms,
+                "floor": what}
+
+    out = {"pairs": n, "loss": "crossentropy", "api": "model(x1, x2) -> model.loss(...) -> .backward()",
+           "timing": "median of 10 steps (CUDA events) after 3 warm-up steps"}
     m = load_kaldi_init(npl.NeuralPlda(NCX).to(dev), kp)
 
     def nstep():
@@ -770,7 +780,7 @@ def train_leg(kp, dev, x1, x2, t):
         m.loss(m(x1, x2), t).backward()
 
     ms = timeit(nstep)
-    out["nplda"] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "pairs/s"}
+    out["nplda"] = entry(ms, 2 * 4096 + 4, "x read by the forward and again by dW1 = dA^T X: 8196 B per pair")
     d = npl.DPlda(NCDP).to(dev)
     sd = d.state_dict()
     sd["centering_and_LDA.weight"].copy_(kp["W1"]); sd["centering_and_LDA.bias"].copy_(kp["b1"])
@@ -782,10 +792,10 @@ def train_leg(kp, dev, x1, x2, t):
         d.loss(d(x1, x2), t).backward()
 
     ms = timeit(dstep)
-    out["dplda_lda_frozen"] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "pairs/s"}
+    out["dplda_lda_frozen"] = entry(ms, 4096 + 4, "x read once (no gradient reaches the frozen LDA): 4100 B per pair")
     with torch.no_grad():
         ms = timeit(lambda: d(x1, x2))
-    out["dplda_forward"] = {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "pairs/s"}
+    out["dplda_forward"] = entry(ms, 4096 + 4, "4100 B per pair")
     return out
 
 
@@ -793,8 +803,9 @@ def trial_list_leg(model, kp, dev):
     """Extra, separately-labelled measurement (never mixed into `value` / `roofline`): BASELINE.json
     configs[2] in the INDEXED layout the reference's scoring loop actually has (a table of unique
     x-vectors + a trial list, scorefile_generator.py:29-36): 10 M trials = 2500 enrol x 4000 test over 6500
-    utterances, every utterance transformed once (nplda_table_prepare) and each trial scored as
-    r[i] + r[j] + A[i].B[j] (nplda_score_pairs)."""
+    utterances, every utterance transformed once (nplda_table_prepare); the list is dense, so forward_indexed scores it
+    as a sub-grid product over the rows it uses + a 4-byte gather per trial (nplda_trial_rows / nplda_score_grid /
+    nplda_trial_grid_gather); sparse lists take one row gather per trial (nplda_score_pairs)."""
     from oracle import nplda_oracle as O
     table, i1, i2, _ = O.synth_grid(2500, 4000, 500, seed=1003, mean=kp["mean"])
     t, a, b = table.to(dev), i1.to(dev), i2.to(dev)
@@ -860,11 +871,11 @@ def trial_list_leg(model, kp, dev):
                     "api": "NeuralPlda.forward_grid, scores copied back to pinned host memory"},
             "bytes_per_trial": {"hbm_score": 4}, "parity_worst_over_bound_strided_sample": worst_g}
     return {"grid": grid, "workload": "configs[2] indexed: 10M trials = 2500 x 4000 grid over 6500 x-vectors (table resident in HBM), "
-                        "table prepare + pair scoring every step",
+                        "table prepare + trial scoring (dense list: sub-grid product + gather) every step",
             "value": n / (ms * 1e-3), "unit": "trials/s", "ms_per_step": ms,
             "e2e": {"value": n / dt, "unit": "trials/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 4 * n,
                     "api": "NeuralPlda.forward_indexed on pinned host index tensors, scores copied back to pinned host memory"},
-            "bytes_per_trial": {"hbm_indices_and_score": 20, "l2_row_gather": 1408},
+            "bytes_per_trial": {"hbm_indices_and_score": 36, "note": "index lists read twice (row marking, gather) + 4 B score"},
             "parity_worst_over_bound_strided_sample": worst}
 
 

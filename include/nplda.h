@@ -325,6 +325,15 @@ int nplda_minc_sweep(const float *tgt_sorted, int64_t n_t, const float *non_sort
                      float sum_t, float sum_n, const double *betas_host, int K, float *out_min,
                      int64_t *out_arg, void *stream);
 
+/* The two sorted score populations the sweep takes (models.py:407-408: torch.sort(output[target > 0.5]) and
+ * torch.sort(output[target < 0.5])), hand-written:
+ *   nplda_split_by_label: scores with label > 0.5 -> tgt, < 0.5 -> non (capacity n each, order unspecified),
+ *     counts[0] / counts[1] = how many (device uint64 pair, zeroed by the call);
+ *   nplda_sort_f32: in-place ascending sort of n floats (bitonic network, NaN last like torch.sort). */
+int nplda_split_by_label(const float *scores, const float *labels, int64_t n, float *tgt, float *non,
+                         unsigned long long *counts, void *stream);
+int nplda_sort_f32(float *keys, int64_t n, void *stream);
+
 /* ---------------------------------------------------------------------------
  * Host-buffer entry (what a non-PyTorch caller binds, and what bench.py's e2e
  * leg times): x1_host/x2_host are host buffers (pinned for full speed), scores

@@ -80,6 +80,8 @@ SIGNATURES = {
     "dplda_lr_bwd": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "nplda_minc_sweep": (c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
                                  ctypes.POINTER(ctypes.c_double), c_int, c_vp, c_vp, c_vp]),
+    "nplda_split_by_label": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "nplda_sort_f32": (c_int, [c_vp, c_i64, c_vp]),
     "nplda_score_grid": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "nplda_score_grid_impl": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_vp]),
     "nplda_cohort_stats": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),

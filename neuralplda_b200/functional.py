@@ -589,6 +589,27 @@ class LossFn(torch.autograd.Function):
         return ds, None, dthr, dthx, None, None, None, None
 
 
+def sorted_populations(scores, target):
+    """(sorted target scores, sorted non-target scores) of models.py:407-408 -- `torch.sort(output[target > 0.5])`,
+    `torch.sort(output[target < 0.5])` -- with the library's own split and sort kernels (csrc/sort.cu).  Reads the two
+    population sizes back to the host (the sweep's caller synchronises anyway for the label sums)."""
+    require_cuda(scores, target)
+    s, t = _f32c(scores.detach()).reshape(-1), _f32c(target.detach()).reshape(-1)
+    if s.shape != t.shape:
+        raise RuntimeError("scores and targets must have the same shape")
+    n = s.numel()
+    dev = s.device
+    tgt = torch.empty(n, dtype=torch.float32, device=dev)
+    non = torch.empty(n, dtype=torch.float32, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
+    with on_device(dev):
+        check(lib().nplda_split_by_label(ptr(s), ptr(t), n, ptr(tgt), ptr(non), ptr(counts), stream_ptr()), "nplda_split_by_label")
+        n_t, n_n = counts.tolist()
+        check(lib().nplda_sort_f32(ptr(tgt), n_t, stream_ptr()), "nplda_sort_f32")
+        check(lib().nplda_sort_f32(ptr(non), n_n, stream_ptr()), "nplda_sort_f32")
+    return tgt[:n_t], non[:n_n]
+
+
 def minc_sweep(tgt_sorted, non_sorted, sum_t, sum_n, betas):
     """(min cost [K] fp32, argmin index [K] int64 into tgt_sorted); models.py:406-421."""
     require_cuda(tgt_sorted, non_sorted)

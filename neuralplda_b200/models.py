@@ -151,8 +151,7 @@ class _PldaBase(nn.Module):
         with torch.no_grad():
             output = output.detach().float()
             target = target.detach().float()
-            scores_target, _ = torch.sort(output[target > 0.5])
-            scores_nontarget, _ = torch.sort(output[target < 0.5])
+            scores_target, scores_nontarget = F_.sorted_populations(output, target)
             if scores_target.numel() == 0:
                 raise RuntimeError("minc: no target trials (the reference fails in torch.min on an empty tensor)")
             sums = torch.stack((target.sum(), (1 - target).sum())).tolist()          # synchronises ...

@@ -451,6 +451,22 @@ def test_minc_quirks_gpu(ref_out, kaldi_params):
     assert [float(th[b]) for b in NC.beta] == [float(oth[b]) for b in NC.beta]
 
 
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 1000, 2048, 2049, 4097, 100_003, 1 << 20, (1 << 20) + 5])
+def test_sorted_populations_match_torch_sort(n):
+    """csrc/sort.cu (label split + bitonic sort in its flip / disperse form, virtual +inf tail for lengths that are not
+    a power of two) against `torch.sort(output[target > 0.5])` / `torch.sort(output[target < 0.5])` (models.py:407-408):
+    bit-identical, labels of exactly 0.5 in neither population."""
+    g = torch.Generator().manual_seed(n)
+    s = torch.randn(n, generator=g)
+    t = (torch.rand(n, generator=g) < 0.1).float()
+    if n > 10:
+        t[7] = 0.5
+        s[3] = s[4]                                            # ties
+    sd, td = s.to(DEV), t.to(DEV)
+    tgt, non = F_.sorted_populations(sd, td)
+    assert torch.equal(tgt.cpu(), torch.sort(s[t > 0.5])[0]) and torch.equal(non.cpu(), torch.sort(s[t < 0.5])[0])
+
+
 def _check_grads(model, ref_out, prefix, names, rtol=1e-4):
     got = dict(model.named_parameters())
     for n in names:
