@@ -64,7 +64,7 @@ __device__ __forceinline__ void wait_or_trap(uint64_t *bar, uint32_t parity) {
             "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
             : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if (clock64() - t0 > NPLDA_WAIT_TRAP_CYCLES) __trap();
     }
 }
 

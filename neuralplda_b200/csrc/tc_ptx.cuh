@@ -29,6 +29,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) after ~10 s of wall clock instead of hanging the
 // device.  The timer is only read every 256 failed polls (a failing try_wait already parks the warp for a while).
+#ifndef NPLDA_WAIT_TRAP_NS
+#define NPLDA_WAIT_TRAP_NS 10000000000ull      // builds for compute-sanitizer's racecheck (~100x slower kernels) raise it
+#endif
+#ifndef NPLDA_WAIT_TRAP_CYCLES
+#define NPLDA_WAIT_TRAP_CYCLES 4000000000ll     // the clock64-based waits of gemm_tc.cu / dplda_lr.cu (~2 s)
+#endif
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -49,7 +55,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if ((++spins & 255u) == 0) {
             const uint64_t t = global_timer_ns();
             if (t0 == 0) t0 = t;
-            else if (t - t0 > 10000000000ull) __trap();
+            else if (t - t0 > NPLDA_WAIT_TRAP_NS) __trap();
         }
     }
 }

@@ -56,8 +56,9 @@ class PackedWeights:
         check(rc, "pack_weights")
         return self.buf
 
-    dense_skip = 0            # dense-list probe (score_indexed): calls left to skip / current back-off
+    dense_skip = 0            # dense-list probe (score_indexed): calls left to skip / current back-off, per table
     dense_backoff = 0
+    dense_table = None
     rowtab = None
     rowtab_key = None
     rowtab_table = None       # strong reference to the table the cached rows were built from
@@ -447,6 +448,9 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
         if n >= GRID_GATHER_MIN_TRIALS and impl != _lib.IMPL_SIMT:
             # lists over this table that turned out sparse are not probed again for a while (the probe costs one pass
             # over the index lists and a small synchronising read-back): back-off doubles up to 1024 calls
+            if packed.dense_table is None or packed.dense_table() is not table:       # another table: forget the back-off
+                packed.dense_table = weakref.ref(table)
+                packed.dense_skip = packed.dense_backoff = 0
             if packed.dense_skip > 0:
                 packed.dense_skip -= 1
             elif _score_dense_list(rowtab, table.shape[0], i1, i2, scores, fp):

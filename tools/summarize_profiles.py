@@ -1,4 +1,4 @@
-"""Turns the raw ncu outputs a `tools/gpu_validate.sh <tag>` run left in gpurun_out/ into the small committed
+"""Turns the raw ncu outputs a `tools/r2_profiles.sh <tag>` run left in gpurun_out/ into the small committed
 summaries under profiles/: launch list with per-kernel shares, key metrics of the --set full captures, and
 profiles/k1_traffic.json (DRAM bytes per K1 launch, read by bench.py for roofline.traffic).
 Usage: python tools/summarize_profiles.py <tag> [round-name]"""
@@ -31,7 +31,7 @@ if os.path.exists(src):
         unit = r[ix["Metric Unit"]]
         v_us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v_us
-    ours = {k: v for k, v in agg.items() if "nplda" in k or "tcg::" in k}
+    ours = {k: v for k, v in agg.items() if "nplda" in k or "::" in k and "at::" not in k}
     tot = sum(v[1] for v in ours.values())
     with open(os.path.join(P, f"{rnd}_launches.csv"), "w") as f:
         f.write(f"# ncu launch list, {rnd} (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare shares)\n")
@@ -56,33 +56,36 @@ if os.path.exists(src):
         unit = r[ix["Metric Unit"]]
         v_us = v / 1e3 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1e3)
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v_us
-    ours = {k: v for k, v in agg.items() if "nplda" in k or "tcg::" in k or "gtc::" in k or "bwd::" in k or "simt::" in k}
+    ours = {k: v for k, v in agg.items() if "nplda" in k or "::" in k and "at::" not in k}
     tot = sum(v[1] for v in ours.values())
     with open(os.path.join(P, f"{rnd}_train_launches.csv"), "w") as f:
         f.write(f"# ncu launch list of training steps, {rnd} (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare shares)\n")
-        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv python tools/quick_train.py 131072\n")
-        f.write("# first 120 launches: warm-up + timed NeuralPlda steps (forward, BCE, backward) on 131072 pairs; libnplda kernels only\n")
+        f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/ncu_train.py 1000000 d\n")
+        f.write("# one NeuralPlda step and one DPlda step (LDA frozen) on 1M pairs: forward, BCE, backward; libnplda kernels only\n")
         f.write("share_pct,launches,avg_us,kernel\n")
         for k, v in sorted(ours.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{100 * v[1] / tot:.2f},{v[0]},{v[1] / v[0]:.1f},\"{k[:110]}\"\n")
     print("wrote train launches", len(ours))
 
-# ---- full captures
+# ---- full captures: every gpurun_out/<tag>_<name>.ncu-rep -> profiles/<rnd>_<name>_ncu.csv (first launch in the report)
 def raw(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
-for name, outname in ((f"{tag}_score_tc.ncu-rep", f"{rnd}_score_tc_kernel_ncu.csv"), (f"{tag}_score_pairs.ncu-rep", f"{rnd}_score_pairs_kernel_ncu.csv"),
-                      (f"{tag}_score_grid.ncu-rep", f"{rnd}_score_grid_kernel_ncu.csv"), (f"{tag}_gemm_tc.ncu-rep", f"{rnd}_gemm_tc_kernel_ncu.csv")):
-    rep = os.path.join(G, name)
-    if not os.path.exists(rep):
+def git_head():
+    return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+
+for fn in sorted(os.listdir(G)):
+    if not (fn.startswith(tag + "_") and fn.endswith(".ncu-rep")):
         continue
-    hdr, units, launches = raw(rep)
+    name = fn[len(tag) + 1:-len(".ncu-rep")]
+    outname = f"{rnd}_{name}_ncu.csv"
+    hdr, units, launches = raw(os.path.join(G, fn))
     vals = launches[0]
     kname = vals[hdr.index("Kernel Name")]
     with open(os.path.join(P, outname), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on, {rnd}: {kname[:100]}, B200\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on, {rnd} (captured at commit {git_head()}): {kname[:120]}, B200\n")
         f.write("metric,unit,value\n")
         got = {}
         for h, u, v in zip(hdr, units, vals):
@@ -90,13 +93,13 @@ for name, outname in ((f"{tag}_score_tc.ncu-rep", f"{rnd}_score_tc_kernel_ncu.cs
             if any(base == k for k in KEYS):
                 f.write(f"{base},{u},{v}\n"); got[base] = (u, v)
     print("wrote", outname)
-    if "score_tc" in name and "dram__bytes_read.sum" in got:
+    if name == "score_tc" and "dram__bytes_read.sum" in got:
         def tobytes(u, v):
             v = float(v.replace(",", ""))
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         rd, wr = tobytes(*got["dram__bytes_read.sum"]), tobytes(*got["dram__bytes_write.sum"])
-        json.dump({"kernel": kname[:80], "pairs": 1000000, "dram_bytes_read": rd, "dram_bytes_write": wr,
+        json.dump({"kernel": kname[:80], "pairs": 1000000, "dram_bytes_read": rd, "dram_bytes_write": wr, "commit": git_head(),
                    "source": f"ncu --set full --clock-control none, one launch of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline "
-                             f"--skip-e2e` (tools/gpu_validate.sh {tag}); summary in profiles/{outname}"},
+                             f"--skip-e2e` (tools/r2_profiles.sh); summary in profiles/{outname}"},
                   open(os.path.join(P, "k1_traffic.json"), "w"), indent=1)
         print("wrote k1_traffic.json", rd, wr)
