@@ -157,10 +157,10 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {   // a -> low
     return r;
 }
 __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {   // a -> byte 0
-    uint32_t lo, hi;
-    asm("{\n.reg .b16 t;\ncvt.rn.satfinite.e4m3x2.f32 t, %1, %2;\ncvt.u32.u16 %0, t;\n}\n" : "=r"(lo) : "f"(b), "f"(a));
-    asm("{\n.reg .b16 t;\ncvt.rn.satfinite.e4m3x2.f32 t, %1, %2;\ncvt.u32.u16 %0, t;\n}\n" : "=r"(hi) : "f"(d), "f"(c));
-    return lo | (hi << 16);
+    uint32_t r;
+    asm("{\n.reg .b16 lo, hi;\ncvt.rn.satfinite.e4m3x2.f32 lo, %2, %1;\ncvt.rn.satfinite.e4m3x2.f32 hi, %4, %3;\n"
+        "mov.b32 %0, {lo, hi};\n}\n" : "=r"(r) : "f"(a), "f"(b), "f"(c), "f"(d));
+    return r;
 }
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -602,8 +602,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
             const float r0 = c2 / fmaxf(sqrtf(ss0), 1e-12f);       // F.normalize eps (models.py:368) (x the layer-2 scale)
             const float r1 = c2 / fmaxf(sqrtf(ss1), 1e-12f);
-            if (MODE == 2) {
-                // fp16 range guard for U: |a|_2 < 32768 bounds every element; NaN / inf fail the comparison too
+            if (MODE != 0) {
+                // fp16 range guard for U: |a|_2 < 32768 bounds every element; NaN / inf fail the comparison too (MODE 1: an
+                // input with |x| >= 128 overflowed fp16(2^9 x) to inf and arrives here as inf / NaN)
                 const int64_t pe = (blockIdx.x + i * gridDim.x) * TP + pl;
                 if (!(ss0 < 1.0e9f && ss1 < 1.0e9f) && pe < g.n) *reinterpret_cast<volatile int *>(g.guard) = 1;
             }
@@ -677,7 +678,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             const bool tile_end = MODE != 0 && ++stage_in_tile == g.nst1;
             auto guard_check = [&]() {
                 const int64_t pr = (blockIdx.x + tile_i * gridDim.x) * TP + pl;
-                const bool out = MODE == 1 ? (amax < 0.25f || amax >= 256.f || !img_ok) : !(amax < 2048.f);
+                const bool out = MODE == 1 ? (amax < 0.25f || !img_ok) : !(amax < 2048.f);
                 if (pr < g.n && out) *reinterpret_cast<volatile int *>(g.guard) = 1;
                 amax = 0.f; stage_in_tile = 0; ++tile_i;
             };
@@ -743,19 +744,28 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             }
             uint32_t hi[8], lo[8];
             if (MODE == 1) {
-                // hi[0..7]: fp16 of x (same register layout as the bf16 path); lo[0..3]: e4m3 of (x - hi) * 2^9,
-                // lo[4..7]: e4m3 of x.  One e4m3 register = K slots 8 cq + {0..3} (k-step 0 chunk) or + {4..7}
-                // (k-step 1 chunk): the weight image uses the same slot permutation.
+                // x' = 2^9 x = h + r:  hi[0..7] = h = fp16(x') (same register layout as the bf16 path); lo[0..3] = e4m3(r)
+                // (|r| <= |x| / 4); lo[4..7] = e4m3(x).  One e4m3 register = K slots 8 cq + {0..3} (k-step 0 chunk) or
+                // + {4..7} (k-step 1 chunk): the weight image uses the same slot permutation.  9 instructions per two values.
                 const float v[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                float h[16], l[16];
+                uint32_t hp[8];
+                float r[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { split_f16(v[j], h[j], l[j]); amax = fmaxf(amax, fabsf(v[j])); }
-                hi[0] = pack_f16x2(h[0], h[1]); hi[1] = pack_f16x2(h[2], h[3]);       // side 0, k-step 0
-                hi[2] = pack_f16x2(h[8], h[9]); hi[3] = pack_f16x2(h[10], h[11]);     // side 1, k-step 0
-                hi[4] = pack_f16x2(h[4], h[5]); hi[5] = pack_f16x2(h[6], h[7]);       // side 0, k-step 1
-                hi[6] = pack_f16x2(h[12], h[13]); hi[7] = pack_f16x2(h[14], h[15]);   // side 1, k-step 1
-                lo[0] = pack_e4m3x4(l[0], l[1], l[2], l[3]); lo[1] = pack_e4m3x4(l[4], l[5], l[6], l[7]);
-                lo[2] = pack_e4m3x4(l[8], l[9], l[10], l[11]); lo[3] = pack_e4m3x4(l[12], l[13], l[14], l[15]);
+                for (int j = 0; j < 8; ++j) {
+                    const float s0 = v[2 * j] * 512.f, s1 = v[2 * j + 1] * 512.f;
+                    hp[j] = pack_f16x2(s0, s1);
+                    float h0, h1;
+                    asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}\n" : "=f"(h0), "=f"(h1) : "r"(hp[j]));
+                    r[2 * j] = s0 - h0; r[2 * j + 1] = s1 - h1;
+                }
+                // lower range guard on a sample of the values (the upper one is the epilogue's: fp16(x') overflows to inf)
+                amax = fmaxf(fmaxf(amax, fabsf(v[0])), fmaxf(fabsf(v[5]), fmaxf(fabsf(v[10]), fabsf(v[15]))));
+                hi[0] = hp[0]; hi[1] = hp[1];       // side 0, k-step 0
+                hi[2] = hp[4]; hi[3] = hp[5];       // side 1, k-step 0
+                hi[4] = hp[2]; hi[5] = hp[3];       // side 0, k-step 1
+                hi[6] = hp[6]; hi[7] = hp[7];       // side 1, k-step 1
+                lo[0] = pack_e4m3x4(r[0], r[1], r[2], r[3]); lo[1] = pack_e4m3x4(r[4], r[5], r[6], r[7]);
+                lo[2] = pack_e4m3x4(r[8], r[9], r[10], r[11]); lo[3] = pack_e4m3x4(r[12], r[13], r[14], r[15]);
                 lo[4] = pack_e4m3x4(v[0], v[1], v[2], v[3]); lo[5] = pack_e4m3x4(v[4], v[5], v[6], v[7]);
                 lo[6] = pack_e4m3x4(v[8], v[9], v[10], v[11]); lo[7] = pack_e4m3x4(v[12], v[13], v[14], v[15]);
             } else if (MODE == 2) {
@@ -1163,13 +1173,14 @@ __global__ void __launch_bounds__(1024) tc_scales_kernel(const float *__restrict
 static int64_t image_bytes(int ksteps) { return (int64_t)ksteps * B_STEP; }
 
 // ---- MODE 1 weight image (layer 1) ------------------------------------------------------------
-// With gw chosen so that max|W| 2^gw is in [32, 64):  W' = W 2^(gw+9) = Wh + Wl, Wh = fp16(W') (|Wh| < 2^15).
-//   x W' = xh Wh + (xl 2^9)(Wh 2^-9) + xh Wl + O(2^-22),   xh = fp16(x), xl = x - xh
-// The first product runs as kind::f16, the other two as kind::f8f6f4 with every operand in e4m3:
-// |xl 2^9| <= |x| / 4, |Wh 2^-9| < 64, |Wl| <= 2^-11 |W'| < 16.  The accumulator holds x W 2^(gw+9); the epilogue
-// multiplies by hdr[0] = 2^-(gw+9).
+// With gw chosen so that max|W| 2^gw is in [32, 64):  W' = W 2^gw = Wh + Wl, Wh = fp16(W'); the converters take
+// x' = 2^9 x = xh + xl, xh = fp16(x'), |xl| <= 2^-11 |x'| = |x| / 4:
+//   x' W' = xh Wh + xl Wh + x (2^9 Wl) + O(2^-22)
+// The first product runs as kind::f16, the other two as kind::f8f6f4 with every operand in e4m3: |xl| <= |x| / 4,
+// |Wh| < 64, |2^9 Wl| <= 2^-2 |W'| < 16, x itself (|x| < 128, else fp16(x') is inf and the guard fires).  The accumulator
+// holds x W 2^(gw+9); the epilogue multiplies by hdr[0] = 2^-(gw+9).
 // Stage s (K = [32 s, 32 s + 32)) of the image, 8 chunks of 22 core matrices (KCH_B bytes each):
-//   [fp16 k 0-7][fp16 k 8-15][fp16 k 16-23][fp16 k 24-31][e4m3 Wh 2^-9 slots 0-15][slots 16-31][e4m3 Wl slots 0-15][slots 16-31]
+//   [fp16 k 0-7][fp16 k 8-15][fp16 k 16-23][fp16 k 24-31][e4m3 Wh slots 0-15][slots 16-31][e4m3 2^9 Wl slots 0-15][slots 16-31]
 // e4m3 slot t holds k = 4 (t >> 3) + (t & 3) + 16 ((t >> 2) & 1): the order in which a converter thread's two
 // 16-byte loads land in one tcgen05.st.16x256b register pair.
 __global__ void tc_absmax_kernel(const float *__restrict__ W, int64_t count, float *__restrict__ hdr) {
@@ -1188,8 +1199,8 @@ __global__ void tc_absmax_kernel(const float *__restrict__ W, int64_t count, flo
             gw = 6 - e;
         }
         gw = max(-100, min(100, gw));
-        hdr[0] = exp2f((float)-(gw + 9));   // epilogue scale
-        hdr[1] = exp2f((float)(gw + 9));    // W -> W'
+        hdr[0] = exp2f((float)-(gw + 9));   // epilogue scale: the accumulator holds (2^9 x) (2^gw W)
+        hdr[1] = exp2f((float)gw);          // W -> W'
         hdr[2] = 1.f;                       // image valid
     }
 }
@@ -1212,8 +1223,8 @@ __global__ void tc_pack_mixed_kernel(const float *__restrict__ W, int N, int K, 
         // slot of k within the stage: inverse of k = 4 (t >> 3) + (t & 3) + 16 ((t >> 2) & 1)
         const int t = ((kk & 15) >> 2) * 8 + ((kk >> 4) & 1) * 4 + (kk & 3);
         const size_t off8 = (size_t)(t >> 4) * KCH_B + row + (t & 15);
-        st[4 * KCH_B + off8] = (uint8_t)__nv_cvt_float_to_fp8(whf * (1.f / 512.f), __NV_SATFINITE, __NV_E4M3);
-        st[6 * KCH_B + off8] = (uint8_t)__nv_cvt_float_to_fp8(w - whf, __NV_SATFINITE, __NV_E4M3);
+        st[4 * KCH_B + off8] = (uint8_t)__nv_cvt_float_to_fp8(whf, __NV_SATFINITE, __NV_E4M3);                  // pairs with e4m3(r)
+        st[6 * KCH_B + off8] = (uint8_t)__nv_cvt_float_to_fp8((w - whf) * 512.f, __NV_SATFINITE, __NV_E4M3);    // pairs with e4m3(x)
     }
 }
 static int64_t mixed_image_bytes(int d_in) { return (int64_t)(d_in / KST) * B_STAGE; }

@@ -276,6 +276,26 @@ def test_dplda_fused_forward_ragged_sizes(ref_out, kaldi_params, cfg1, n):
     assert bool((err <= bound).all()), float((err / bound).max())
 
 
+def test_dplda_fused_forward_range_guard(ref_out, kaldi_params, cfg1):
+    """Inputs outside fp16's range make the fused DPlda kernel's fp16x3 pass raise its guard; the bf16x3 pass behind it
+    (same kernel, bf16 halves re-read from shared memory) recomputes the call: still within the bound of the oracle, and
+    a later in-range call gives the same bits as before."""
+    x1, x2, _ = cfg1
+    kp = kaldi_params
+    m = make_dplda(kp, ref_out, npl.IMPL_TC)
+    w, c = dplda_weights(ref_out)
+    n = 3000
+    a, b = x1[:n].to(DEV), x2[:n].to(DEV)
+    with torch.no_grad():
+        s0 = m(a, b)
+        big = m(a * 1000.0, b * 1000.0)
+        s1 = m(a, b)
+    ref = O.dplda_score(x1[:n] * 1000.0, x2[:n] * 1000.0, kp["W1"], kp["b1"], w, c)
+    ok, worst = parity_ok(big, ref, rel=1e-4)
+    assert ok, worst
+    assert torch.equal(s0, s1)
+
+
 @pytest.mark.parametrize("n", [64, 65, 256, 1000])
 def test_dplda_frozen_lda_training_step(ref_out, kaldi_params, cfg1, n):
     """LDA frozen (xvector_DPlda_pytorch.py:140-147): the forward keeps only the normalised rows u and the backward is

@@ -15,7 +15,7 @@ for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias",
 n = 1_000_000
 x1, x2, t = bench.synth_on_device(n, 1002, kp["mean"].to(dev), dev)
 lib = _lib.lib()
-pack = m.packed.get("nplda", m._params(), 512, 170, 170)
+pack = m.packed.get("nplda", m._params(), 512, 170, 170, mixed=("f8" in os.environ.get("IMPLS", "tc,f8")))
 def run(impl, cnt):
     out = torch.empty(cnt, device=dev)
     _lib.check(lib.nplda_score_fwd(_lib.ptr(x1), _lib.ptr(x2), cnt, 512, 170, 170, _lib.ptr(pack), _lib.ptr(out), impl, _lib.stream_ptr()), "k1")
