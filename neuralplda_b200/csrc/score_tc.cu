@@ -53,10 +53,16 @@ constexpr int KST = 32;                         // K per x / A stage (two MMA K-
 constexpr int KCH_B = (NPAD / 8) * 128;         // 2816 B: one 8-wide k-chunk of B (22 core matrices)
 constexpr int B_STEP = 4 * KCH_B;               // 11264 B: hi (2 chunks) + lo (2 chunks), K = 16
 constexpr int B_STAGE = 2 * B_STEP;             // 22528 B: two K=16 steps
-constexpr int NBS = 3;                          // B ring stages (K = 32 each)
+#ifndef TC_NBS
+#define TC_NBS 3
+#endif
+#ifndef TC_NX
+#define TC_NX 4
+#endif
+constexpr int NBS = TC_NBS;                     // B ring stages (K = 32 each)
 constexpr int X_BOX = TP * KST * 4;             // 8192 B: [64 rows x 32 floats]
 constexpr int X_STAGE = 2 * X_BOX;              // x1 box + x2 box
-constexpr int NX = 4;                           // x ring stages
+constexpr int NX = TC_NX;                       // x ring stages
 constexpr int KCH_U = (128 / 8) * 128;          // 2048 B: one k-chunk of U (16 core matrices)
 constexpr int U_HALF = (NPAD / 8) * KCH_U;      // 45056 B (hi or lo), K = 176
 constexpr int NA = 5;                           // A ring stages in TMEM
@@ -200,7 +206,11 @@ __device__ __forceinline__ float reduce_scatter4(const float (&v)[4], int lane) 
 // Waits of the roles off the critical path.  Measured on B200: neither the suspend-time hint of try_wait nor a
 // nanosleep back-off between polls changes the issued-instruction count or the kernel time (a try_wait that
 // fails already parks the warp for ~60 cycles), so these are plain polling waits.
+#ifdef TC_WAIT_SLEEP_NS
+#define WAIT_OFFPATH(bar, par) mbar_wait_sleep(bar, par, TC_WAIT_SLEEP_NS)
+#else
 #define WAIT_OFFPATH(bar, par) mbar_wait(bar, par)
+#endif
 
 constexpr int EMIT_LD = NPAD;  // 176: row stride of the emitted a / y rows (= the backward's row pitch for these shapes)
 

@@ -60,6 +60,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// The same with a back-off between failed polls (experiment switch TC_WAIT_SLEEP_NS: roles off the critical path)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    const uint32_t addr = smem_addr(bar);
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(ns);
+        if ((++spins & 255u) == 0) {
+            const uint64_t t = global_timer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > NPLDA_WAIT_TRAP_NS) __trap();
+        }
+    }
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
