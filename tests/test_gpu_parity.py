@@ -531,7 +531,7 @@ def test_dplda_training_step_gradients(ref_out, kaldi_params, cfg1):
 def test_backward_linearity_large(kaldi_params, cfg1):
     """Size-independent property at a multi-chunk size: grads are linear in dS."""
     x1, x2, _ = cfg1
-    reps = 14                                  # 140k pairs > one backward chunk (131072)
+    reps = 56                                  # 560k pairs > one backward chunk (524288)
     X1 = x1.repeat(reps, 1).to(DEV); X2 = x2.repeat(reps, 1).to(DEV)
     m = make_nplda(kaldi_params)
     g = torch.Generator().manual_seed(4)
@@ -544,7 +544,7 @@ def test_backward_linearity_large(kaldi_params, cfg1):
         if p.grad is None:
             continue
         scale = float(p.grad.abs().max()) * reps + 1e-30
-        assert float((big[n] - reps * p.grad).abs().max()) <= 2e-3 * scale, n
+        assert float((big[n] - reps * p.grad).abs().max()) <= 2e-4 * scale, n
 
 
 def test_optimizer_step_repacks_weights(kaldi_params, cfg1):
