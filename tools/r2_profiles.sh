@@ -10,9 +10,12 @@ timeout 300 ncu $F -k regex:score_tc_kernel -s 3 -c 1 -o $O/${TAG}_score_tc pyth
 # BASELINE configs[2] materialised: 10M pairs = 41 GB through K1 (achieved-GB/s evidence)
 timeout 400 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.avg.per_second \
     --clock-control none -k regex:score_tc_kernel -s 3 -c 1 --csv --log-file $O/${TAG}_cfg3_10m.csv python bench.py --pairs 10000000 --steps 1 --warmup 3 --no-cpu-baseline --skip-e2e > $O/${TAG}_cfg3.out 2>&1; echo "cfg3 rc=$?"
-# training kernels on 1M pairs: launch order of tools/ncu_train.py: score_tc_kernel #0 fwd EMIT, #1 guarded fallback, #2 BWD form (chunk 0), ...; then DPlda
-timeout 300 ncu $F -k regex:score_tc_kernel -s 2 -c 1 -o $O/${TAG}_bwd_mid python tools/ncu_train.py > $O/${TAG}_bwd.out 2>&1; echo "BWD rc=$?"
-timeout 300 ncu $F -k regex:score_tc_kernel -s 4 -c 1 -o $O/${TAG}_dplda_fused python tools/ncu_train.py 1000000 d > $O/${TAG}_dpl.out 2>&1; echo "DPL rc=$?"
+# training kernels (262144 pairs: ncu saves and restores everything a kernel writes, GBs per pass at 1M): launch order of tools/ncu_train.py: score_tc_kernel #0 fwd EMIT, #1 guarded fallback, #2 BWD form; then DPlda #3
+# (kernel replay ends in LaunchFailed after two passes on these two instantiations -- they write hundreds of MB per launch, which
+# ncu saves and restores around every pass -- so they are captured with application replay and the sections that need no patching)
+A="--replay-mode application --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section LaunchStats --section Occupancy --section WarpStateStats --section SchedulerStats --clock-control none -f"
+timeout 350 ncu $A -k regex:score_tc_kernel -s 2 -c 1 -o $O/${TAG}_bwd_mid python tools/ncu_train.py 262144 > $O/${TAG}_bwd.out 2>&1; echo "BWD rc=$?"
+timeout 350 ncu $A -k regex:score_tc_kernel -s 3 -c 1 -o $O/${TAG}_dplda_fused python tools/ncu_train.py 262144 d > $O/${TAG}_dpl.out 2>&1; echo "DPL rc=$?"
 timeout 300 ncu $F -k regex:gemm_tn_tc -s 0 -c 1 -o $O/${TAG}_gemm_tc python tools/ncu_train.py > $O/${TAG}_gemm.out 2>&1; echo "gemm rc=$?"
 timeout 300 ncu $F -k regex:wgrad_kernel -c 1 -o $O/${TAG}_dplda_wgrad python tools/ncu_train.py 1000000 d > $O/${TAG}_wgrad.out 2>&1; echo "wgrad rc=$?"
 QUICK=1 timeout 300 ncu $F -k regex:score_tcx_kernel -s 2 -c 1 -o $O/${TAG}_score_tcx python tools/quick_split.py 2 > $O/${TAG}_tcx.out 2>&1; echo "K1x rc=$?"

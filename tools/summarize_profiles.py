@@ -85,7 +85,7 @@ for fn in sorted(os.listdir(G)):
     vals = launches[0]
     kname = vals[hdr.index("Kernel Name")]
     with open(os.path.join(P, outname), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on, {rnd} (captured at commit {git_head()}): {kname[:120]}, B200\n")
+        f.write(f"# ncu capture, {rnd} (commit {git_head()}; exact command in tools/r2_profiles.sh): {kname[:120]}, B200\n")
         f.write("metric,unit,value\n")
         got = {}
         for h, u, v in zip(hdr, units, vals):
