@@ -734,7 +734,7 @@ def multi_gpu_legs(model, kp, dev, world, rank):
     res["cfg4_dplda_train"] = {"workload": "configs[4]: DPlda 512-170 (LDA frozen), 10M synthetic trial pairs split over the ranks, "
                                            "forward + BCE + backward + NCCL all-reduce of the parameter gradients",
                                "value": total4 / (ms4 * 1e-3), "unit": "pairs/s", "ms_per_step": ms4, "pairs_per_rank": m4,
-                               "scaling": "strong", "bce": float(step4()), "grad_norm_after_allreduce": gnorm}
+                               "scaling": "strong", "bce": float(step4().detach()), "grad_norm_after_allreduce": gnorm}
     return res
 
 
