@@ -46,6 +46,9 @@ extern "C" {
                                range at pack time; inputs outside fp16's range are detected on the device and the call is
                                recomputed by the bf16x3 kernel on the same stream); error if shape unsupported */
 #define NPLDA_IMPL_TC_BF16 4 /* tcgen05 kernel, both layers as split bf16 (any fp32 range, ~8x the rounding error of fp16x3) */
+#define NPLDA_IMPL_TC_PAIR 5 /* NPLDA_IMPL_TC_BF16 arithmetic by CTA pairs (tcgen05.mma.cta_group::2, csrc/score_tcp.cu): each CTA of a
+                               cluster converts its own 128 rows and holds half of the weight rows.  What NPLDA_IMPL_AUTO takes
+                               for materialised NeuralPlda pairs from 9 472 pairs on (one 64-pair tile per SM); same scores */
 #define NPLDA_IMPL_TC_F8 3  /* tcgen05 kernel, layer 1 as fp16*fp16 + two e4m3*e4m3 correction products on the same
                                accumulator (same MAC count, 2/3 of the MMA instructions).  Inputs outside the range the
                                e4m3 terms cover (typical |x| in [2^-3, 2^8)) are detected on the device and the call is

@@ -8,7 +8,7 @@ reference's driver scripts.
 from .models import NeuralPlda, DPlda  # noqa: F401
 from . import _lib  # noqa: F401
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8, IMPL_TC_BF16 = (_lib.IMPL_AUTO, _lib.IMPL_SIMT, _lib.IMPL_TC, _lib.IMPL_TC_F8,
-                                                            _lib.IMPL_TC_BF16)
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8, IMPL_TC_BF16, IMPL_TC_PAIR = (_lib.IMPL_AUTO, _lib.IMPL_SIMT, _lib.IMPL_TC,
+                                                                          _lib.IMPL_TC_F8, _lib.IMPL_TC_BF16, _lib.IMPL_TC_PAIR)
 
-__all__ = ["NeuralPlda", "DPlda", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_F8", "IMPL_TC_BF16"]
+__all__ = ["NeuralPlda", "DPlda", "IMPL_AUTO", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_F8", "IMPL_TC_BF16", "IMPL_TC_PAIR"]

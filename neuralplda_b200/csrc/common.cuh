@@ -30,11 +30,14 @@ struct PackLayout {
     int64_t tc_bytes;
     int64_t tcx;   // CTA-pair weight images of the pre-split-table kernel, see score_tcx.cu (built with NPLDA_PACK_PAIR)
     int64_t tcx_bytes;
+    int64_t tcp;   // bf16 CTA-pair weight images of the materialised-pairs kernel, see score_tcp.cu (always built)
+    int64_t tcp_bytes;
     int64_t total;
 };
 
 int64_t tc_image_bytes(int d_in, int d1, int d2);   // score_tc.cu
 int64_t tcx_image_bytes(int d_in, int d1, int d2);  // score_tcx.cu
+int64_t tcp_image_bytes(int d_in, int d1, int d2);  // score_tcp.cu
 
 inline PackLayout make_pack_layout(int d_in, int d1, int d2) {
     PackLayout L;
@@ -56,6 +59,8 @@ inline PackLayout make_pack_layout(int d_in, int d1, int d2) {
     L.tc = take(L.tc_bytes);
     L.tcx_bytes = tcx_image_bytes(d_in, d1, d2);
     L.tcx = take(L.tcx_bytes);
+    L.tcp_bytes = tcp_image_bytes(d_in, d1, d2);
+    L.tcp = take(L.tcp_bytes);
     L.total = o;
     return L;
 }

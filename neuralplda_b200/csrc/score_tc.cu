@@ -865,6 +865,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     const uint32_t acol = tmem + A_COL0 + ra.stage * A_STAGE_COLS;
                     const uint32_t bs = b_base + rb.stage * B_STAGE;
                     const uint64_t bhi0 = make_smem_desc(bs, KCH_B, 128);
+                    Ring na = ra, nb = rb;
+                    na.advance();
+                    nb.advance();
+                    // Probes of the next stage's barriers, issued BEFORE this stage's MMAs and looked at after the first
+                    // K step: an already-complete try_wait still takes ~90 cycles to answer, and two of them between
+                    // the issue blocks were a third of this warp's time per stage.
+                    uint32_t ok_a = 1, ok_b = 1;
+                    if (s + 1 < s_end) { ok_a = mbar_try(&a_full[na.stage], na.phase); ok_b = mbar_try(&b_full[nb.stage], nb.phase); }
                     if (elect_one() && !skip_mma) {
                         if (MODE == 1) {        // fp16 x fp16, K steps 0 and 1
                             mma_ts(dcol, acol, bhi0, IDESC_F16, s != 0);
@@ -876,16 +884,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                         }
                     }
                     __syncwarp();
-                    Ring na = ra, nb = rb;
-                    na.advance();
-                    nb.advance();
                     PMARK(3);
-                    if (s + 1 < s_end) {
-                        mbar_wait(&a_full[na.stage], na.phase);
-                        PMARK(1);
-                        mbar_wait(&b_full[nb.stage], nb.phase);
-                        PMARK(2);
-                    }
+                    if (!ok_a) mbar_wait(&a_full[na.stage], na.phase);
+                    PMARK(1);
+                    if (!ok_b) mbar_wait(&b_full[nb.stage], nb.phase);
+                    __syncwarp();
+                    PMARK(2);
                     if (elect_one()) {
                         if (!skip_mma) {
                             const uint64_t bhi1 = bhi0 + (B_STEP >> 4);
@@ -930,16 +934,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                         const uint64_t bhi0 = make_smem_desc(bs, KCH_B, 128);
                         const uint64_t uhi0 = make_smem_desc(u_base + ks * 2 * KCH_U, KCH_U, 128);
                         const uint64_t ulo0 = make_smem_desc(u_base + U_HALF + ks * 2 * KCH_U, KCH_U, 128);
+                        Ring nb = rb;
+                        nb.advance();
+                        const uint32_t ok_b = ks + 2 < g.ksteps2 ? mbar_try(&b_full[nb.stage], nb.phase) : 1u;   // see layer1
                         if (elect_one() && !skip_mma) {
                             mma_ss(dcol, uhi0, bhi0, IDESC_L2, ks != 0);
                             mma_ss(dcol, ulo0, bhi0, IDESC_L2, 1);
                             mma_ss(dcol, uhi0, bhi0 + ((2 * KCH_B) >> 4), IDESC_L2, 1);
                         }
                         __syncwarp();
-                        Ring nb = rb;
-                        nb.advance();
                         PMARK(5);
-                        if (ks + 2 < g.ksteps2) mbar_wait(&b_full[nb.stage], nb.phase);
+                        if (!ok_b) mbar_wait(&b_full[nb.stage], nb.phase);
+                        __syncwarp();
                         PMARK(2);
                         if (elect_one()) {
                             if (nst == 2 && !skip_mma) {

@@ -242,7 +242,7 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             fence_proxy_async();      // U is read by tcgen05.mma (async proxy)
             tc_fence_before();        // our TMEM reads of D are done before Y overwrites it
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(u_full, 0);          // one arrival per warp, on the leader's barrier
+            if (lane == 0) mbar_arrive_remote(u_full, 0);          // one arrival per warp, on the leader's barrier
             // ---- layer-2 accumulator: y = Y / |a| + b2, pair score ----
             mbar_wait(&y_full[d], par_d);
             tc_fence_after();
@@ -264,7 +264,7 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&d_empty[d], 0);     // D buffer free before the shuffles / store
+            if (lane == 0) mbar_arrive_remote(&d_empty[d], 0);     // D buffer free before the shuffles / store
             float s = sc[0] + sc[1];
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -290,19 +290,22 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tc_fence_after();
                     const uint64_t ad = make_smem_desc_sw128(a_base + ra.stage * A_STAGE);
                     const uint64_t bd = make_smem_desc(b_base + rb.stage * B_HALF, KCH_BH, 128);
+                    Ring na = ra, nb = rb;
+                    na.advance();
+                    nb.advance();
+                    // probes of the next stage's barriers: issued before this stage's MMAs, looked at after the first K step
+                    // (an already-complete try_wait still takes ~90 cycles to answer)
+                    uint32_t ok_a = 1, ok_b = 1;
+                    if (s + 1 < s_end && !(g.variant & 1)) { ok_a = mbar_try(&a_full[na.stage], na.phase); ok_b = mbar_try(&b_full[nb.stage], nb.phase); }
                     if (elect_one()) {
                         mma2_ss(dcol, ad, bd, IDESC, s != 0);
                         mma2_ss(dcol, ad + 4, bd, IDESC, 1);
                         mma2_ss(dcol, ad, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
                     }
                     __syncwarp();
-                    Ring na = ra, nb = rb;
-                    na.advance();
-                    nb.advance();
-                    if (s + 1 < s_end && !(g.variant & 1)) {
-                        mbar_wait(&a_full[na.stage], na.phase);
-                        mbar_wait(&b_full[nb.stage], nb.phase);
-                    }
+                    if (!ok_a) mbar_wait(&a_full[na.stage], na.phase);
+                    if (!ok_b) mbar_wait(&b_full[nb.stage], nb.phase);
+                    __syncwarp();
                     if (elect_one()) {
                         mma2_ss(dcol, ad + 2, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
                         mma2_ss(dcol, ad + 6, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
@@ -338,15 +341,17 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         const uint64_t bd = make_smem_desc(b_base + rb.stage * B_HALF, KCH_BH, 128);
                         const uint64_t uhi = make_smem_desc(u_base + ks * 2 * KCH_U, KCH_U, 128);
                         const uint64_t ulo = make_smem_desc(u_base + U_HALF + ks * 2 * KCH_U, KCH_U, 128);
+                        Ring nb = rb;
+                        nb.advance();
+                        const uint32_t ok_b = ks + 2 < g.ksteps2 ? mbar_try(&b_full[nb.stage], nb.phase) : 1u;
                         if (elect_one()) {
                             mma2_ss(dcol, uhi, bd, IDESC, ks != 0);
                             mma2_ss(dcol, ulo, bd, IDESC, 1);
                             mma2_ss(dcol, uhi, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
                         }
                         __syncwarp();
-                        Ring nb = rb;
-                        nb.advance();
-                        if (ks + 2 < g.ksteps2) mbar_wait(&b_full[nb.stage], nb.phase);
+                        if (!ok_b) mbar_wait(&b_full[nb.stage], nb.phase);
+                        __syncwarp();
                         if (elect_one()) {
                             if (ks + 1 < g.ksteps2) {
                                 const uint64_t uhi1 = uhi + ((2 * KCH_U) >> 4), ulo1 = ulo + ((2 * KCH_U) >> 4);

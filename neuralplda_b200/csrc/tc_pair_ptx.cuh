@@ -36,6 +36,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
         : "memory");
 }
 
+// The same with the default semantics (.release at CTA scope): no cluster-wide fence in front of the arrive.  For
+// producers whose data is ordered by other means -- tensor-memory stores completed by tcgen05.wait::st +
+// tcgen05.fence::before_thread_sync, shared memory made visible to the async proxy by fence.proxy.async and read by this
+// CTA's own tensor core.  Measured in score_tcp.cu: the .release.cluster form costs a converter warp ~1700 cycles per
+// arrive (it waits for the warp's outstanding memory traffic at cluster scope), this one ~100.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
+    asm volatile(
+        "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(smem_addr(bar)),
+        "r"(cta)
+        : "memory");
+}
+
 // 2-D tiled TMA load into THIS CTA's shared memory whose completion bytes are posted on the LEADER's barrier
 // (bit 24 of a shared::cluster address selects the odd CTA of the pair)
 __device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {

@@ -474,7 +474,7 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
     scores = torch.empty(n, dtype=torch.float32, device=dev)
     fp, flag = _flag(dev, flag_ptr)
     pack = packed.get(kind, params, d_in, d1, d2, mixed=(impl == _lib.IMPL_TC_F8))
-    if impl in (_lib.IMPL_TC, _lib.IMPL_TC_F8):
+    if impl in (_lib.IMPL_TC, _lib.IMPL_TC_F8, _lib.IMPL_TC_BF16, _lib.IMPL_TC_PAIR):
         impl = _lib.IMPL_AUTO                     # the materialised-pair tcgen05 kernel has no gather; fp32 kernel
     with on_device(dev):
         if kind == "nplda":

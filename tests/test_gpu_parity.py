@@ -96,6 +96,62 @@ def test_nplda_forward_ragged_sizes(kaldi_params, cfg1, impl, n):
     assert bool((err <= bound).all()), float((err / bound).max())
 
 
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 127, 128, 129, 4097, 9471, 9473, 10000])
+def test_pair_kernel_ragged_sizes_identical_to_one_cta(kaldi_params, cfg1, n):
+    """K1p (csrc/score_tcp.cu: two CTAs of a cluster share every M = 256 MMA, each converting its own 128 rows and holding
+    half of the weight rows) on ragged batches -- one CTA of the pair without a single live row, partial tiles, an odd
+    number of tiles: against the oracle (1e-4) and BIT-identical to the one-CTA bf16x3 kernel (same products, same
+    accumulation order).  It is what IMPL_AUTO takes for materialised pairs from 9 472 pairs on."""
+    x1, x2, _ = cfg1
+    kp = kaldi_params
+    m = make_nplda(kp, npl.IMPL_TC_PAIR)
+    a, b = x1[:n].to(DEV), x2[:n].to(DEV)
+    with torch.no_grad():
+        s = m(a, b)
+        m.impl = npl.IMPL_TC_BF16
+        one = m(a, b)
+        m.impl = npl.IMPL_AUTO
+        auto = m(a, b)
+    assert s.shape == (n,) and torch.equal(s, one) and torch.equal(s, auto)
+    ref = O.nplda_score(x1[:n], x2[:n], kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"])
+    full = O.nplda_score(x1, x2, kp["W1"], kp["b1"], kp["W2"], kp["b2"], kp["P_sqrt"], kp["Q"]).double()
+    bound = 1e-4 * torch.maximum(ref.double().abs(), full.pow(2).mean().sqrt())
+    err = (s.cpu().double() - ref.double()).abs()
+    assert bool((err <= bound).all()), float((err / bound).max())
+
+
+def test_pair_kernel_deterministic_any_range_and_dims(kaldi_params, cfg1):
+    """Back-to-back launches of the pair kernel give the same bits (no races in the cross-CTA mbarrier protocol); inputs
+    far outside fp16's range score like the fp32 kernel (bf16 halves keep fp32's exponent); NaN rows give NaN scores;
+    a shape it does not take (fewer than two 32-wide stages) fails loudly when asked for explicitly."""
+    x1, x2, _ = cfg1
+    a, b = x1.to(DEV), x2.to(DEV)
+    m = make_nplda(kaldi_params, npl.IMPL_TC_PAIR)
+    with torch.no_grad():
+        first = m(a, b)
+        for _ in range(20):
+            again = m(a, b)
+        torch.cuda.synchronize()
+        assert torch.equal(first, again)
+        for scale in (1e-4, 3e4):
+            s = m(a * scale, b * scale)
+            m.impl = npl.IMPL_SIMT
+            ref = m(a * scale, b * scale)
+            m.impl = npl.IMPL_TC_PAIR
+            ok, worst = parity_ok(s, ref.cpu(), rel=1e-4)
+            assert ok, (scale, worst)
+        bad = a.clone()
+        bad[5, 17] = float("nan")
+        s = m(bad, b)
+        assert torch.isnan(s[5]) and torch.isfinite(s[:5]).all() and torch.isfinite(s[6:]).all()
+    class C(NC):
+        xvector_dim = 32
+    m2 = npl.NeuralPlda(C).to(DEV)
+    m2.impl = npl.IMPL_TC_PAIR
+    with pytest.raises(RuntimeError):
+        m2(torch.zeros(300, 32, device=DEV), torch.zeros(300, 32, device=DEV))
+
+
 def test_tc_kernel_is_selected_and_deterministic(kaldi_params, cfg1):
     """IMPL_TC must run (no silent fallback) for the reference dims, agree with the SIMT kernel, and be
     bit-reproducible over back-to-back launches (the mbarrier pipelines have no data races)."""
