@@ -399,7 +399,17 @@ def _run_ours(args, saved_stdout):
 
     kp = kaldi_params()
     model = load_kaldi_init(npl.NeuralPlda(NC).to(dev), kp)
-    model.impl = {"auto": npl.IMPL_AUTO, "simt": npl.IMPL_SIMT, "tc": npl.IMPL_TC, "f8": npl.IMPL_TC_F8}[args.kernel]
+    model.impl = {"auto": npl.IMPL_AUTO, "simt": npl.IMPL_SIMT, "tc": npl.IMPL_TC, "f8": npl.IMPL_TC_F8, "bf16": npl.IMPL_TC_BF16,
+                  "pair": npl.IMPL_TC_PAIR, "pairf8": _lib.IMPL_TC_PAIR_F8}[args.kernel]
+    # what NPLDA_IMPL_AUTO launches for materialised pairs (csrc/api.cu: the CTA-pair kernel from one 64-pair tile per SM on)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    k1_name = {"simt": "K1-SIMT fp32 score kernel (simt::score_kernel)", "tc": "K1 fused score kernel, fp16x3 (tcg::score_tc_kernel)",
+               "f8": "K1 fused score kernel, fp16 + 2 x e4m3 (tcg::score_tc_kernel)", "bf16": "K1 fused score kernel, bf16x3 (tcg::score_tc_kernel)",
+               "pair": "K1p fused score kernel, CTA pairs, bf16x3 (tcp::score_tcp_kernel)",
+               "pairf8": "K1p fused score kernel, CTA pairs, fp16 + 2 x e4m3 (tcp::score_tcp_kernel)"}.get(args.kernel)
+    if k1_name is None:
+        k1_name = ("K1p fused score kernel, CTA pairs, bf16x3 (tcp::score_tcp_kernel)" if args.pairs >= 64 * sms
+                   else "K1 fused score kernel, bf16x3 (tcg::score_tc_kernel)")
     model.process_group = group
     model.eval()
 
@@ -559,7 +569,7 @@ def _run_ours(args, saved_stdout):
                        "one all-reduce of 12 fp64 accumulators per step" if world > 1 else "single GPU",
                        "l2": "inputs (4.1 GB per step) larger than L2 (126 MB); no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
-                         "traffic": measured_traffic(), "kernel": "K1 fused score kernel (score_tc_kernel)", "k1_ms": k1_ms,
+                         "traffic": measured_traffic(), "kernel": k1_name, "k1_ms": k1_ms,
                          "bytes_per_pair": BYTES_PER_PAIR, "peak_source": pk["source"],
                          "tensor": {"flops_per_pair_bf16x3": FLOPS_PER_PAIR_BF16X3,
                                     "achieved_tflops": n * FLOPS_PER_PAIR_BF16X3 / (k1_ms * 1e-3) / 1e12,
@@ -885,7 +895,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc", "f8"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc", "f8", "bf16", "pair", "pairf8"])
     ap.add_argument("--skip-trial-list", action="store_true", help="skip the extra separately-labelled legs (N = 1)")
     ap.add_argument("--skip-multi", action="store_true", help="skip the configs[3] / configs[4] legs (N > 1)")
     ap.add_argument("--skip-sustained", action="store_true")

@@ -49,6 +49,8 @@ extern "C" {
 #define NPLDA_IMPL_TC_PAIR 5 /* NPLDA_IMPL_TC_BF16 arithmetic by CTA pairs (tcgen05.mma.cta_group::2, csrc/score_tcp.cu): each CTA of a
                                cluster converts its own 128 rows and holds half of the weight rows.  What NPLDA_IMPL_AUTO takes
                                for materialised NeuralPlda pairs from 9 472 pairs on (one 64-pair tile per SM); same scores */
+#define NPLDA_IMPL_TC_PAIR_F8 6 /* the CTA-pair kernel with NPLDA_IMPL_TC_F8's layer-1 arithmetic (fp16 + two e4m3 products: four MMAs
+                               per K = 32 instead of six); inputs outside its range are recomputed by NPLDA_IMPL_TC_PAIR on the stream */
 #define NPLDA_IMPL_TC_F8 3  /* tcgen05 kernel, layer 1 as fp16*fp16 + two e4m3*e4m3 correction products on the same
                                accumulator (same MAC count, 2/3 of the MMA instructions).  Inputs outside the range the
                                e4m3 terms cover (typical |x| in [2^-3, 2^8)) are detected on the device and the call is

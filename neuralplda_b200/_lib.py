@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NPLDA_LIB") or os.path.join(_HERE, "libnplda.so")    # NPLDA_LIB: an experiment build (csrc/Makefile)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8, IMPL_TC_BF16, IMPL_TC_PAIR = 0, 1, 2, 3, 4, 5
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_F8, IMPL_TC_BF16, IMPL_TC_PAIR, IMPL_TC_PAIR_F8 = 0, 1, 2, 3, 4, 5, 6
 LOSS_SOFTCDET, LOSS_CROSSENTROPY = 0, 1
 PACK_MIXED, PACK_EPOCH_ODD, PACK_PAIR, PREPARE_IF_CHANGED = 1, 2, 4, 1
 ERR_UNSUPPORTED_DIM = -2

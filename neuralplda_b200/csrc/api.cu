@@ -32,7 +32,7 @@ int score_tc(bool dplda, const float *x1, const float *x2, const int64_t *i1, co
              int64_t emit_cap = 0);   // score_tc.cu
 
 bool tcp_shape_ok(const PackLayout &L);   // score_tcp.cu
-int score_tcp(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores,
+int score_tcp(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores, bool mixed,
               cudaStream_t st);   // score_tcp.cu
 
 int table_split(const float *table, int64_t n_rows, int d_in, void *split, cudaStream_t st);   // score_tcx.cu
@@ -80,7 +80,7 @@ static int score_dispatch(bool dplda, const float *x1, const float *x2, const in
     if (indexed && (!i1 || !i2 || !bad_flag || n_rows <= 0)) return NPLDA_ERR_BAD_ARG;
     if (!indexed && n > 0 && !x2) return NPLDA_ERR_BAD_ARG;
     if (impl != NPLDA_IMPL_AUTO && impl != NPLDA_IMPL_SIMT && impl != NPLDA_IMPL_TC && impl != NPLDA_IMPL_TC_F8 &&
-        impl != NPLDA_IMPL_TC_BF16 && impl != NPLDA_IMPL_TC_PAIR)
+        impl != NPLDA_IMPL_TC_BF16 && impl != NPLDA_IMPL_TC_PAIR && impl != NPLDA_IMPL_TC_PAIR_F8)
         return NPLDA_ERR_BAD_ARG;
     if (!dims_supported(d_in, d1, d2)) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n == 0) return NPLDA_OK;
@@ -91,9 +91,10 @@ static int score_dispatch(bool dplda, const float *x1, const float *x2, const in
     const bool want_tc = impl == NPLDA_IMPL_TC || impl == NPLDA_IMPL_TC_F8 || impl == NPLDA_IMPL_TC_BF16;
     // CTA-pair form of the bf16x3 kernel: from one 64-pair tile per SM on (below that the one-CTA form spreads over more SMs)
     const bool pair_ok = tc_ok && tcp_shape_ok(L);
-    if (impl == NPLDA_IMPL_TC_PAIR && !pair_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
-    if (impl == NPLDA_IMPL_TC_PAIR || (impl == NPLDA_IMPL_AUTO && pair_ok && n >= (int64_t)TILE_PAIRS * sm_count()))
-        return score_tcp(x1, x2, n, L, (const char *)pack, scores, st);
+    if ((impl == NPLDA_IMPL_TC_PAIR || impl == NPLDA_IMPL_TC_PAIR_F8) && !pair_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
+    if (impl == NPLDA_IMPL_TC_PAIR || impl == NPLDA_IMPL_TC_PAIR_F8 ||
+        (impl == NPLDA_IMPL_AUTO && pair_ok && n >= (int64_t)TILE_PAIRS * sm_count()))
+        return score_tcp(x1, x2, n, L, (const char *)pack, scores, impl == NPLDA_IMPL_TC_PAIR_F8, st);
     if (want_tc && !tc_ok) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (want_tc || (impl == NPLDA_IMPL_AUTO && tc_ok))
         return score_tc(dplda, x1, x2, i1, i2, n_rows, bad_flag, n, L, (const char *)pack, scores,

@@ -670,37 +670,33 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
         const int offk1 = pl * 128 + (((4 + cq) ^ rsub) << 4);   // k-step 1: chunks 4-7
         const int off0 = odd ? offk1 : offk0, off1 = odd ? offk0 : offk1;
         const int64_t total = T * g.nst1;
+        // Set s owns stages it = s, s + 2, ...; NX is even, so it owns the x slots of its own parity and is the ONLY waiter
+        // of their barriers.  (Both sets used to wait for every stage's x_full and skip the other set's data: a parity wait
+        // is only unambiguous for a waiter that is never a whole phase late, and a set that merely skips a stage can be --
+        // seen as a hang in the CTA-pair kernel, score_tcp.cu, when a slow arrive delayed one set.)  The A slots (NA odd)
+        // alternate between the sets; a set reaches stage `it` only after the MMA warp has consumed stage it - 2 - NA, so
+        // that barrier is at most one phase behind the one waited for.
+        static_assert(NX % 2 == 0 && NA % 2 == 1 && NA >= 3, "converter sets own the x slots of their parity");
         Ring rx(NX), ra(NA);
-        float amax = 0.f;       // MODE 1 range guard: largest |x| this thread saw in the current tile
-        int stage_in_tile = 0;
-        int64_t tile_i = 0;
-        int bs_next = 0;        // BWD: stage within the tile / tile of iteration `it`
-        int64_t bt_next = 0;
+        if (cset) { rx.stage = 1; ra.stage = 1; }
+        auto advance2 = [](Ring &r) { r.stage += 2; if (r.stage >= (uint32_t)r.n) { r.stage -= (uint32_t)r.n; r.phase ^= 1; } };
+        float amax = 0.f;       // MODE 1 / 2 range guard: largest |x| this thread saw in the stages it converted of the current tile
+        int bs = cset;          // stage within the tile / tile of iteration `it`
+        int64_t bt = 0;
+        while (bs >= g.nst1) { bs -= g.nst1; ++bt; }
         float cacc[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // BWD: [slot][db2, dq, dp] column sums
-        for (int64_t it = 0; it < total; ++it, rx.advance(), ra.advance()) {
-            const int bs = bs_next;
-            const int64_t bt = bt_next;
-            if (BWD && ++bs_next == g.nst1) { bs_next = 0; ++bt_next; }
-            // MODE 1 range guard, evaluated after the last stage of every tile: both converter sets count
-            // stages and each checks the values it converted (its pair's two rows, 8 columns of every other
-            // stage).  The e4m3 terms need typical |x| in about [2^-3, 2^8); outside that, the call is flagged and
-            // the bf16x3 pass that follows on the stream recomputes it.
-            const bool tile_end = MODE != 0 && ++stage_in_tile == g.nst1;
+        for (int64_t it = cset; it < total; it += 2, advance2(rx), advance2(ra)) {
+            // MODE 1 / 2 range guard, evaluated after the set's last stage of every tile: each set checks the values it
+            // converted (its pair's two rows, 8 columns of every other stage).  MODE 1: the e4m3 terms need typical |x| in
+            // about [2^-3, 2^8); outside the mode's range the call is flagged and the bf16x3 pass that follows on the
+            // stream recomputes it.
+            const bool tile_end = MODE != 0 && bs + 2 >= g.nst1;
             auto guard_check = [&]() {
-                const int64_t pr = (blockIdx.x + tile_i * gridDim.x) * TP + pl;
+                const int64_t pr = (blockIdx.x + bt * gridDim.x) * TP + pl;
                 const bool out = MODE == 1 ? (amax < 0.25f || !img_ok) : !(amax < 2048.f);
                 if (pr < g.n && out) *reinterpret_cast<volatile int *>(g.guard) = 1;
-                amax = 0.f; stage_in_tile = 0; ++tile_i;
+                amax = 0.f;
             };
-            // mbarrier parity waits are only unambiguous for a waiter that observes EVERY phase of a
-            // barrier, so both sets wait for every stage's x_full in order and skip the other set's data.
-            if ((it & 1) != cset) {
-                PMARK(5);
-                if (!(g.dbg & 1)) WAIT_OFFPATH(&x_full[rx.stage], rx.phase);
-                PMARK(1);
-                if (tile_end) guard_check();
-                continue;
-            }
             const uint8_t *xs = Xs + rx.stage * X_STAGE;
             PMARK(5);
             if (!(g.dbg & 1)) WAIT_OFFPATH(&x_full[rx.stage], rx.phase);
@@ -823,6 +819,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[ra.stage]);
             if (tile_end) guard_check();
+            bs += 2;
+            while (bs >= g.nst1) { bs -= g.nst1; ++bt; }
             PMARK(4);
         }
         if (BWD) {
@@ -1408,6 +1406,8 @@ static int *guard_slot() {
     }
     return ring[dev] + 2 * (ticket.fetch_add(1, std::memory_order_relaxed) & 1023u);
 }
+
+int *tc_guard_slot() { return guard_slot(); }     // score_tcp.cu
 
 template <bool PROF, int MODE, bool EMIT = false, bool DPL = false, bool BWD = false>
 static int launch_tc(const CUtensorMap &m1, const CUtensorMap &m2, const tcg::Args &a, int grid, cudaStream_t st,

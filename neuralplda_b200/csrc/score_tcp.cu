@@ -16,8 +16,11 @@
 // stage, completing on the leader's barrier), MMA warp (leader only: issues for the pair, releases stages and
 // publishes accumulators with multicast commits), 8 epilogue warps (this CTA's 128 rows, as in score_tc.cu).
 #include <algorithm>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -73,8 +76,18 @@ struct Args {
     int ksteps2;            // layer-2 K steps = round_up(d1, 16) / 16
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
     float *scores;
+    const float *hdr16;     // MODE 1: {2^gw1, 2^-gw1, ...} of the pack (tc_scales_kernel): max|W1| 2^gw1 is in [8192, 16384)
+    int *guard;             // MODE 1: guard[0] is set when an input leaves the range the mode covers; MODE 0 with guard != nullptr:
+                            //         run only if guard[0] is set (fallback pass behind a MODE 1 launch), then clear it
+    int dbg;                // TCP_DBG builds (bottleneck experiments, env NPLDA_TCP_DEBUG): 4 no MMAs, 8 no TMEM stores, 16 no LDS / conversion, 32 idle epilogue
     int *trace;             // TCP_TRACE builds: host-mapped progress table [2 CTAs][32 warps] (post-mortem of a protocol hang)
 };
+
+#ifdef TCP_DBG
+#define DBG(bit) ((g.dbg & (bit)) != 0)
+#else
+#define DBG(bit) false
+#endif
 
 #ifdef TCP_TRACE
 #define TWAIT(bar, par, code) do { if (g.trace && lane == 0 && blockIdx.x < 2) { ((volatile int *)g.trace)[blockIdx.x * 32 + warp] = (code); __threadfence_system(); } \
@@ -127,6 +140,40 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
                  : "memory");
 }
 
+// kind::f8f6f4 pair MMA with the A operand in tensor memory (four e4m3 per 32-bit cell), K = 32 per instruction
+__device__ __forceinline__ void mma2_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x1(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {   // a -> low half
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {   // a -> byte 0
+    uint32_t r;
+    asm("{\n.reg .b16 lo, hi;\ncvt.rn.satfinite.e4m3x2.f32 lo, %2, %1;\ncvt.rn.satfinite.e4m3x2.f32 hi, %4, %3;\n"
+        "mov.b32 %0, {lo, hi};\n}\n" : "=r"(r) : "f"(a), "f"(b), "f"(c), "f"(d));
+    return r;
+}
+// D fp32, A/B format code 0 (kind::f16: fp16; kind::f8f6f4: e4m3), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_fmt0(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// MODE 0: bf16x3 on both layers.  MODE 1 ("mixed"): layer 1 as fp16(2^9 x) fp16(W') + e4m3(residual) e4m3(W'h) + e4m3(x)
+// e4m3(2^9 W'l) on one accumulator -- four MMAs per stage instead of six (an e4m3 MMA covers K = 32) -- with W' = W1 2^gw,
+// max|W'| in [32, 64); layer 2 stays bf16x3.  Inputs outside the range the e4m3 terms cover raise the guard and the
+// MODE 0 launch that follows on the stream recomputes the call (see score_tc.cu's MODE 1 for the error analysis).
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
                  const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2, Args g) {
@@ -149,6 +196,9 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
     const int64_t nsuper = (g.n + 2 * TP - 1) / (2 * TP);
     const int64_t T = nsuper > cid ? (nsuper - cid + ncl - 1) / ncl : 0;       // the same in both CTAs of a pair
     auto tile_base = [&](int64_t i) { return ((cid + i * ncl) * 2 + rank) * TP; };
+    // fallback pass behind a MODE 1 launch: nothing to do unless its range guard fired (every CTA reads the flag here;
+    // the last CTA to finish clears it, so no CTA can see it cleared)
+    if (MODE == 0 && g.guard != nullptr && *reinterpret_cast<volatile int *>(g.guard) == 0) return;
 
     // ---- one-time setup ----
     for (int i = tid; i < NPAD; i += NTHREADS) {
@@ -168,7 +218,10 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
     cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / TMA completion
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t IDESC = make_idesc_bf16(256, NPAD);
+    constexpr uint32_t IDESC = make_idesc_bf16(256, NPAD);        // layer 2, and layer 1 of MODE 0
+    constexpr uint32_t IDESC0 = make_idesc_fmt0(256, NPAD);       // MODE 1 layer 1: fp16 x fp16 and e4m3 x e4m3
+    // MODE 1: the accumulator holds (2^9 x) (2^gm W) with 2^gm = 2^gw1 / 256 (max|W| 2^gm in [32, 64))
+    const float s1 = MODE == 1 ? g.hdr16[1] * 0.5f : 1.f;
 #ifdef TCP_PROF
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ptime = clock64();
 #endif
@@ -189,10 +242,10 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
 
         auto pass1 = [&](const uint32_t (&v)[8], int c0, float (&ss)[4]) {
             const float2 ba = b1s[(c0 >> 1) + cq], bb = b1s[(c0 >> 1) + 4 + cq];
-            const float a00 = __uint_as_float(v[0]) + ba.x, a01 = __uint_as_float(v[1]) + ba.y;
-            const float a10 = __uint_as_float(v[2]) + ba.x, a11 = __uint_as_float(v[3]) + ba.y;
-            const float a02 = __uint_as_float(v[4]) + bb.x, a03 = __uint_as_float(v[5]) + bb.y;
-            const float a12 = __uint_as_float(v[6]) + bb.x, a13 = __uint_as_float(v[7]) + bb.y;
+            const float a00 = fmaf(__uint_as_float(v[0]), s1, ba.x), a01 = fmaf(__uint_as_float(v[1]), s1, ba.y);   // MODE 0: s1 = 1
+            const float a10 = fmaf(__uint_as_float(v[2]), s1, ba.x), a11 = fmaf(__uint_as_float(v[3]), s1, ba.y);
+            const float a02 = fmaf(__uint_as_float(v[4]), s1, bb.x), a03 = fmaf(__uint_as_float(v[5]), s1, bb.y);
+            const float a12 = fmaf(__uint_as_float(v[6]), s1, bb.x), a13 = fmaf(__uint_as_float(v[7]), s1, bb.y);
             ss[0] = fmaf(a00, a00, ss[0]); ss[1] = fmaf(a01, a01, ss[1]);
             ss[0] = fmaf(a02, a02, ss[0]); ss[1] = fmaf(a03, a03, ss[1]);
             ss[2] = fmaf(a10, a10, ss[2]); ss[3] = fmaf(a11, a11, ss[3]);
@@ -237,8 +290,9 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
             TWAIT(u_empty, (uint32_t)((i & 1) ^ 1), 0x102);
             PMARK(1);           // layer 2 of the previous tile has read U
             float ss[4] = {0.f, 0.f, 0.f, 0.f};
+            const int cend = DBG(32) ? 0 : NPAD - 16;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NPAD - 16; c0 += 32) {           // two 16-column loads per wait
+            for (int c0 = 0; c0 < cend; c0 += 32) {           // two 16-column loads per wait
                 uint32_t va[8], vb[8];
                 tmem_ld_16x256b_x2(taddr + c0, va);
                 tmem_ld_16x256b_x2(taddr + c0 + 16, vb);
@@ -257,6 +311,11 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
             ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
             const float r0 = 1.f / fmaxf(sqrtf(ss0), 1e-12f);      // F.normalize eps (models.py:368)
             const float r1 = 1.f / fmaxf(sqrtf(ss1), 1e-12f);
+            if (MODE == 1) {
+                // upper range guard: an input with |x| >= 128 overflowed fp16(2^9 x) to inf and arrives here as inf / NaN
+                // (a NaN input too: the fallback pass then gives the NaN score the reference gives)
+                if (!(ss0 < 1.0e30f && ss1 < 1.0e30f) && tile_base(i) + pl < g.n) *reinterpret_cast<volatile int *>(g.guard) = 1;
+            }
             fence_proxy_async();      // U is read by tcgen05.mma (async proxy)
             tc_fence_before();        // our TMEM reads of D are done before Y overwrites it
             __syncwarp();
@@ -268,7 +327,7 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
             PMARK(3);
             float sc[2] = {0.f, 0.f};
 #pragma unroll 1
-            for (int c0 = 0; c0 < NPAD - 16; c0 += 32) {
+            for (int c0 = 0; c0 < cend; c0 += 32) {
                 uint32_t va[8], vb[8];
                 tmem_ld_16x256b_x2(taddr + c0, va);
                 tmem_ld_16x256b_x2(taddr + c0 + 16, vb);
@@ -317,24 +376,62 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
         // barrier is at most one phase behind the one waited for.
         Ring rx(NX), ra(NA);
         if (cset) { rx.stage = 1; ra.stage = 1; }
+        float amax = 0.f;                 // MODE 1 lower range guard: largest sampled |x| of this thread's pair in the current tile
+        int sit = cset;                   // stage within the tile
+        int64_t tile_i = 0;
         auto advance2 = [](Ring &r) { r.stage += 2; if (r.stage >= (uint32_t)r.n) { r.stage -= (uint32_t)r.n; r.phase ^= 1; } };
         for (int64_t it = cset; it < total; it += 2, advance2(rx), advance2(ra)) {
             PMARK(5);
             TWAIT(&x_full[rx.stage], rx.phase, 0x104 | ((int)it << 20));
             PMARK(0);
             const uint8_t *xs = Xs + rx.stage * X_STAGE;
-            float4 a0 = *reinterpret_cast<const float4 *>(xs + off0);
-            float4 a1 = *reinterpret_cast<const float4 *>(xs + off1);
-            float4 b0 = *reinterpret_cast<const float4 *>(xs + X_BOX + off0);
-            float4 b1 = *reinterpret_cast<const float4 *>(xs + X_BOX + off1);
+            float4 a0, a1, b0, b1;
+            if (!DBG(16)) {
+                a0 = *reinterpret_cast<const float4 *>(xs + off0);
+                a1 = *reinterpret_cast<const float4 *>(xs + off1);
+                b0 = *reinterpret_cast<const float4 *>(xs + X_BOX + off0);
+                b1 = *reinterpret_cast<const float4 *>(xs + X_BOX + off1);
+            } else {
+                a0 = a1 = b0 = b1 = make_float4(1.f, 2.f, 3.f, 4.f);
+            }
             if (odd) { float4 t = a0; a0 = a1; a1 = t; t = b0; b0 = b1; b1 = t; }
             // registers of tcgen05.st.16x256b.x2: r0,r1 -> (row, cols 2j,2j+1)  r2,r3 -> (row+8, same cols);
             // r4..r7 the same for the next 8 columns (k + 16)
             uint32_t hi[8], lo[8];
-            split_bf16x2(a0.x, a0.y, hi[0], lo[0]); split_bf16x2(a0.z, a0.w, hi[1], lo[1]);
-            split_bf16x2(b0.x, b0.y, hi[2], lo[2]); split_bf16x2(b0.z, b0.w, hi[3], lo[3]);
-            split_bf16x2(a1.x, a1.y, hi[4], lo[4]); split_bf16x2(a1.z, a1.w, hi[5], lo[5]);
-            split_bf16x2(b1.x, b1.y, hi[6], lo[6]); split_bf16x2(b1.z, b1.w, hi[7], lo[7]);
+            if (DBG(16)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { hi[j] = 0x3c003c00u; lo[j] = 0u; }
+            } else if (MODE == 1) {
+                // x' = 2^9 x = h + r:  hi[0..7] = h = fp16(x') (same register layout as the bf16 path); lo[0..3] = e4m3(r)
+                // (|r| <= |x| / 4); lo[4..7] = e4m3(x).  One e4m3 register = K slots 8 cq + {0..3} (k-step 0 chunk) or
+                // + {4..7} (k-step 1 chunk): the weight image uses the same slot permutation.
+                const float v[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t hp[8];
+                float r[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float s0 = v[2 * j] * 512.f, s1v = v[2 * j + 1] * 512.f;
+                    hp[j] = pack_f16x2(s0, s1v);
+                    float h0, h1;
+                    asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}\n" : "=f"(h0), "=f"(h1) : "r"(hp[j]));
+                    r[2 * j] = s0 - h0; r[2 * j + 1] = s1v - h1;
+                }
+                // lower range guard on a sample of the values (the upper one is the epilogue's)
+                amax = fmaxf(fmaxf(amax, fabsf(v[0])), fmaxf(fabsf(v[5]), fmaxf(fabsf(v[10]), fabsf(v[15]))));
+                hi[0] = hp[0]; hi[1] = hp[1];       // side 0, k-step 0
+                hi[2] = hp[4]; hi[3] = hp[5];       // side 1, k-step 0
+                hi[4] = hp[2]; hi[5] = hp[3];       // side 0, k-step 1
+                hi[6] = hp[6]; hi[7] = hp[7];       // side 1, k-step 1
+                lo[0] = pack_e4m3x4(r[0], r[1], r[2], r[3]); lo[1] = pack_e4m3x4(r[4], r[5], r[6], r[7]);
+                lo[2] = pack_e4m3x4(r[8], r[9], r[10], r[11]); lo[3] = pack_e4m3x4(r[12], r[13], r[14], r[15]);
+                lo[4] = pack_e4m3x4(v[0], v[1], v[2], v[3]); lo[5] = pack_e4m3x4(v[4], v[5], v[6], v[7]);
+                lo[6] = pack_e4m3x4(v[8], v[9], v[10], v[11]); lo[7] = pack_e4m3x4(v[12], v[13], v[14], v[15]);
+            } else {
+                split_bf16x2(a0.x, a0.y, hi[0], lo[0]); split_bf16x2(a0.z, a0.w, hi[1], lo[1]);
+                split_bf16x2(b0.x, b0.y, hi[2], lo[2]); split_bf16x2(b0.z, b0.w, hi[3], lo[3]);
+                split_bf16x2(a1.x, a1.y, hi[4], lo[4]); split_bf16x2(a1.z, a1.w, hi[5], lo[5]);
+                split_bf16x2(b1.x, b1.y, hi[6], lo[6]); split_bf16x2(b1.z, b1.w, hi[7], lo[7]);
+            }
 #ifdef TCP_PROF
             if (hi[0] == 0x12345678u && lo[7] == 0x9abcdefu) g.scores[0] = 0.f;   // pin the conversion before the mark
 #endif
@@ -343,8 +440,18 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
             tc_fence_after();
             PMARK(2);
             const uint32_t col = st_addr + ra.stage * A_STAGE_COLS;
+            if (DBG(8)) {
+                if (hi[0] == 0x12345678u && lo[7] == 0x9abcdefu) g.scores[0] = 0.f;   // keep the conversion alive
+            } else {
             tmem_st_16x256b_x2(col, hi);
-            tmem_st_16x256b_x2(col + 16, lo);
+            if (MODE == 1) {
+                const uint32_t e0[4] = {lo[0], lo[1], lo[2], lo[3]}, e1[4] = {lo[4], lo[5], lo[6], lo[7]};
+                tmem_st_16x256b_x1(col + 16, e0);
+                tmem_st_16x256b_x1(col + 24, e1);
+            } else {
+                tmem_st_16x256b_x2(col + 16, lo);
+            }
+            }
             // Release the x slot only now: the stores above consume every register the four LDS wrote, so the
             // shared-memory reads have completed.
             __syncwarp();
@@ -354,6 +461,15 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&a_full[ra.stage], 0);
+            if (MODE == 1) {
+                // after this set's last stage of a tile: the e4m3 terms need typical |x| of at least ~2^-2 (each set checks
+                // the stages it converted); nst1 is even, so the sets keep their stage parity in every tile
+                sit += 2;
+                if (sit >= g.nst1) {
+                    if (tile_base(tile_i) + pl < g.n && amax < 0.25f) *reinterpret_cast<volatile int *>(g.guard) = 1;
+                    amax = 0.f; sit -= g.nst1; ++tile_i;
+                }
+            }
             PMARK(4);
         }
         PFLUSH();
@@ -386,10 +502,15 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                     // probes of the next stage's barriers: issued before this stage's MMAs, answered under them
                     uint32_t ok_a = 1, ok_b = 1;
                     if (s + 1 < s_end) { ok_a = mbar_try(&a_full[na.stage], na.phase); ok_b = mbar_try(&b_full[nb.stage], nb.phase); }
-                    if (elect_one()) {
-                        mma2_ts(dcol, acol, bd, IDESC, s != 0);
-                        mma2_ts(dcol, acol + 16, bd, IDESC, 1);
-                        mma2_ts(dcol, acol, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
+                    if (elect_one() && !DBG(4)) {
+                        if (MODE == 1) {        // fp16 x fp16, K steps 0 and 1 (chunks 0-1, 2-3)
+                            mma2_ts(dcol, acol, bd, IDESC0, s != 0);
+                            mma2_ts(dcol, acol + 8, bd + ((2 * KCH_BH) >> 4), IDESC0, 1);
+                        } else {
+                            mma2_ts(dcol, acol, bd, IDESC, s != 0);
+                            mma2_ts(dcol, acol + 16, bd, IDESC, 1);
+                            mma2_ts(dcol, acol, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
+                        }
                     }
                     __syncwarp();
                     PMARK(3);
@@ -399,9 +520,15 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                     __syncwarp();
                     PMARK(2);
                     if (elect_one()) {
-                        mma2_ts(dcol, acol + 8, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
-                        mma2_ts(dcol, acol + 24, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
-                        mma2_ts(dcol, acol + 8, bd + ((6 * KCH_BH) >> 4), IDESC, 1);
+                        if (DBG(4)) {
+                        } else if (MODE == 1) {        // e4m3(residual) x e4m3(W'h) and e4m3(x) x e4m3(2^9 W'l), K = 32 each (chunks 4-5, 6-7)
+                            mma2_f8_ts(dcol, acol + 16, bd + ((4 * KCH_BH) >> 4), IDESC0, 1);
+                            mma2_f8_ts(dcol, acol + 24, bd + ((6 * KCH_BH) >> 4), IDESC0, 1);
+                        } else {
+                            mma2_ts(dcol, acol + 8, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
+                            mma2_ts(dcol, acol + 24, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
+                            mma2_ts(dcol, acol + 8, bd + ((6 * KCH_BH) >> 4), IDESC, 1);
+                        }
                         mma2_commit_mc(&a_empty[ra.stage], 3);
                         mma2_commit_mc(&b_empty[rb.stage], 3);
                     }
@@ -440,7 +567,7 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                         Ring nb = rb;
                         nb.advance();
                         const uint32_t ok_b = ks + 2 < g.ksteps2 ? mbar_try(&b_full[nb.stage], nb.phase) : 1u;
-                        if (elect_one()) {
+                        if (elect_one() && !DBG(4)) {
                             mma2_ss(dcol, uhi, bd, IDESC, ks != 0);
                             mma2_ss(dcol, ulo, bd, IDESC, 1);
                             mma2_ss(dcol, uhi, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
@@ -451,7 +578,7 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                         __syncwarp();
                         PMARK(2);
                         if (elect_one()) {
-                            if (ks + 1 < g.ksteps2) {
+                            if (ks + 1 < g.ksteps2 && !DBG(4)) {
                                 const uint64_t uhi1 = uhi + ((2 * KCH_U) >> 4), ulo1 = ulo + ((2 * KCH_U) >> 4);
                                 mma2_ss(dcol, uhi1, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
                                 mma2_ss(dcol, ulo1, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
@@ -542,6 +669,10 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
     cluster_sync_all();           // the leader's MMAs read the peer's tensor / shared memory: nobody leaves early
     TMARK(0x1ff);
     if (warp == WARP_MMA) tmem_dealloc2(tmem, 512);
+    if (MODE == 0 && g.guard != nullptr && tid == 0) {
+        __threadfence();
+        if (atomicAdd(g.guard + 1, 1) == (int)gridDim.x - 1) { g.guard[1] = 0; g.guard[0] = 0; }
+    }
 }
 
 // ---- pair weight images (bf16) ------------------------------------------------------------------
@@ -570,6 +701,34 @@ __global__ void pair_pack_bf16_kernel(const float *__restrict__ W1, int N1, int 
         const size_t off = (size_t)(kk >> 3) * KCH_BH + (nn >> 3) * 128 + (nn & 7) * 16 + (kk & 7) * 2;
         *reinterpret_cast<__nv_bfloat16 *>(st + off) = hi;
         *reinterpret_cast<__nv_bfloat16 *>(st + 4 * KCH_BH + off) = lo;
+    }
+}
+
+// MODE 1 image of W1 (see score_tc.cu's tc_pack_mixed_kernel for the scaling): W' = W 2^gm with max|W'| in [32, 64),
+// W' = Wh + Wl, Wh = fp16(W').  Stage s, half h: 8 chunks of 11 core matrices
+//   [fp16 Wh k 0-7][k 8-15][k 16-23][k 24-31][e4m3 Wh slots 0-15][slots 16-31][e4m3 2^9 Wl slots 0-15][slots 16-31]
+// e4m3 slot t holds k = 4 (t >> 3) + (t & 3) + 16 ((t >> 2) & 1): the order in which a converter thread's two 16-byte
+// loads land in one tcgen05.st.16x256b register pair.  hdr16[0] = 2^gw1 with max|W| 2^gw1 in [8192, 16384): 2^gm = 2^gw1 / 256.
+__global__ void pair_pack_mixed_kernel(const float *__restrict__ W, int N, int K, int nstages, const float *__restrict__ hdr16,
+                                       uint8_t *__restrict__ img) {
+    const float up = hdr16[0] * (1.f / 256.f);
+    const int64_t total = (int64_t)nstages * NPAD * KST;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(e % KST);
+        const int n = (int)((e / KST) % NPAD);
+        const int s = (int)(e / ((int64_t)KST * NPAD));
+        const int k = s * KST + kk;
+        const float w = (n < N && k < K) ? W[(int64_t)n * K + k] * up : 0.f;
+        const __half wh = __float2half_rn(w);
+        const float whf = __half2float(wh);
+        const int hsel = n / NH, nn = n % NH;
+        uint8_t *st = img + ((size_t)s * 2 + hsel) * B_HALF;
+        const size_t row = (size_t)(nn >> 3) * 128 + (nn & 7) * 16;
+        *reinterpret_cast<__half *>(st + (size_t)(kk >> 3) * KCH_BH + row + (kk & 7) * 2) = wh;
+        const int t = ((kk & 15) >> 2) * 8 + ((kk >> 4) & 1) * 4 + (kk & 3);      // slot of k within the stage
+        const size_t off8 = (size_t)(t >> 4) * KCH_BH + row + (t & 15);
+        st[4 * KCH_BH + off8] = (uint8_t)__nv_cvt_float_to_fp8(whf, __NV_SATFINITE, __NV_E4M3);                  // pairs with e4m3(residual)
+        st[6 * KCH_BH + off8] = (uint8_t)__nv_cvt_float_to_fp8((w - whf) * 512.f, __NV_SATFINITE, __NV_E4M3);    // pairs with e4m3(x)
     }
 }
 
@@ -619,18 +778,25 @@ static int tcp_nst2(int d1) { return (round_up(d1, 16) / 16 + 1) / 2; }
 
 int64_t tcp_image_bytes(int d_in, int d1, int d2) {
     if (!tcp_dims_ok(d_in, d1, d2)) return 0;
-    return tcp_pair_image_bytes(d_in / tcp::KST) + tcp_pair_image_bytes(tcp_nst2(d1));
+    return 2 * tcp_pair_image_bytes(d_in / tcp::KST) + tcp_pair_image_bytes(tcp_nst2(d1));     // bf16 W1, bf16 W2, mixed W1
 }
 
 bool tcp_shape_ok(const PackLayout &L) { return tcp_dims_ok(L.d_in, L.d1, L.d2) && L.tcp_bytes > 0; }
 
-// bf16 pair images of a NeuralPlda pack: [W1: d_in / 32 stages][W2: ceil(ksteps2 / 2) stages], one launch
+const float *tc_hdr16(const PackLayout &L, const char *pack);   // score_tc.cu: weight scales (tc_scales_kernel)
+int *tc_guard_slot();                                           // score_tc.cu: range-guard slots of the mixed-precision paths
+
+// pair images of a NeuralPlda pack: [bf16 W1: d_in / 32 stages][bf16 W2: ceil(ksteps2 / 2) stages][mixed W1], two launches
+// (the mixed image reads the scales the tensor-core pack left on this stream)
 int tcp_pack_nplda(const float *W1, const float *W2, const PackLayout &L, char *pack, cudaStream_t st) {
     if (!tcp_shape_ok(L)) return NPLDA_OK;
     uint8_t *img1 = (uint8_t *)pack + L.tcp;
     uint8_t *img2 = img1 + tcp_pair_image_bytes(L.d_in / tcp::KST);
+    uint8_t *img1m = img2 + tcp_pair_image_bytes(tcp_nst2(L.d1));
     tcp::pair_pack_bf16_kernel<<<sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / tcp::KST, img1, W2, L.d2, L.d1,
                                                           tcp_nst2(L.d1), img2);
+    NPLDA_LAUNCH_CHECK();
+    tcp::pair_pack_mixed_kernel<<<sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / tcp::KST, tc_hdr16(L, pack), img1m);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
 }
@@ -640,14 +806,28 @@ static int *g_tcp_trace = nullptr;
 extern "C" void nplda_debug_set_tcp_trace(void *p) { g_tcp_trace = (int *)p; }
 #endif
 
-int score_tcp(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores, cudaStream_t st) {
+template <int MODE>
+static int launch_tcp(const CUtensorMap &mX1, const CUtensorMap &mX2, const CUtensorMap &mW1, const CUtensorMap &mW2,
+                      const tcp::Args &a, int grid, cudaStream_t st) {
+    NPLDA_CUDA_TRY(cudaFuncSetAttribute(tcp::score_tcp_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::SMEM_BYTES));
+    tcp::score_tcp_kernel<MODE><<<grid, tcp::NTHREADS, tcp::SMEM_BYTES, st>>>(mX1, mX2, mW1, mW2, a);
+    NPLDA_LAUNCH_CHECK();
+    return NPLDA_OK;
+}
+
+// mixed = false: bf16x3 (any fp32 range).  mixed = true: MODE 1 for layer 1, then the bf16x3 kernel as a guarded fallback
+// pass on the same stream (its CTAs return at once unless the range guard fired).
+int score_tcp(const float *x1, const float *x2, int64_t n, const PackLayout &L, const char *pack, float *scores, bool mixed,
+              cudaStream_t st) {
     if (!tcp_shape_ok(L)) return NPLDA_ERR_UNSUPPORTED_DIM;
     if (n >= ((int64_t)1 << 31) - 4 * tcp::TP) return NPLDA_ERR_UNSUPPORTED_DIM;   // TMA row coordinates are int32
     const uint8_t *img1 = (const uint8_t *)pack + L.tcp;
     const uint8_t *img2 = img1 + tcp_pair_image_bytes(L.d_in / tcp::KST);
-    CUtensorMap mX1, mX2, mW1, mW2;
+    const uint8_t *img1m = img2 + tcp_pair_image_bytes(tcp_nst2(L.d1));
+    CUtensorMap mX1, mX2, mW1, mW2, mW1m;
     if (!tcp::make_x_map(&mX1, x1, n, L.d_in) || !tcp::make_x_map(&mX2, x2, n, L.d_in) ||
-        !tcp::make_image_map(&mW1, img1, L.d_in / tcp::KST) || !tcp::make_image_map(&mW2, img2, tcp_nst2(L.d1)))
+        !tcp::make_image_map(&mW1, img1, L.d_in / tcp::KST) || !tcp::make_image_map(&mW2, img2, tcp_nst2(L.d1)) ||
+        !tcp::make_image_map(&mW1m, img1m, L.d_in / tcp::KST))
         return NPLDA_ERR_NO_DEVICE;
     tcp::Args a;
     a.n = n;
@@ -655,16 +835,26 @@ int score_tcp(const float *x1, const float *x2, int64_t n, const PackLayout &L, 
     a.b1 = (const float *)(pack + L.b1); a.b2 = (const float *)(pack + L.b2);
     a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.q);
     a.scores = scores;
+    a.hdr16 = tc_hdr16(L, pack);
+    a.guard = nullptr;
+    a.dbg = 0;
+#ifdef TCP_DBG
+    { static const int v = getenv("NPLDA_TCP_DEBUG") ? atoi(getenv("NPLDA_TCP_DEBUG")) : 0; a.dbg = v; }
+#endif
     a.trace = nullptr;
 #if defined(TCP_TRACE) || defined(TCP_PROF)
     a.trace = g_tcp_trace;
 #endif
     const int64_t nsuper = (n + 2 * tcp::TP - 1) / (2 * tcp::TP);
     const int grid = 2 * (int)std::min<int64_t>(nsuper, sm_count() / 2);
-    NPLDA_CUDA_TRY(cudaFuncSetAttribute(tcp::score_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::SMEM_BYTES));
-    tcp::score_tcp_kernel<<<grid, tcp::NTHREADS, tcp::SMEM_BYTES, st>>>(mX1, mX2, mW1, mW2, a);
-    NPLDA_LAUNCH_CHECK();
-    return NPLDA_OK;
+    if (!mixed) return launch_tcp<0>(mX1, mX2, mW1, mW2, a, grid, st);
+    int *slot = tc_guard_slot();
+    if (!slot) return NPLDA_ERR_NO_DEVICE;
+    a.guard = slot;
+    const int rc = launch_tcp<1>(mX1, mX2, mW1m, mW2, a, grid, st);
+    if (rc != NPLDA_OK) return rc;
+    a.trace = nullptr;
+    return launch_tcp<0>(mX1, mX2, mW1, mW2, a, grid, st);
 }
 
 }  // namespace nplda

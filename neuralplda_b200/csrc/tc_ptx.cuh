@@ -60,14 +60,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
-// One probe (returns at once when the phase has completed; otherwise the hardware may park the warp for its time
-// limit before answering 0).  The MMA warps issue the probes of stage s + 1 BEFORE the MMAs of stage s and look at the
-// answers after them: an already-complete try_wait still takes ~90 cycles to answer, and two of them between two
-// issue blocks were a quarter of that warp's time per stage.
+// One NON-BLOCKING probe (mbarrier.test_wait: a try_wait on a phase that has not completed parks the warp for the
+// hardware's time limit, and the MMA warps must not sleep in front of MMAs they could issue).  The MMA warps issue the
+// probes of stage s + 1 BEFORE the MMAs of stage s and look at the answers after them: an already-complete wait still
+// takes ~90-150 cycles to answer, and two of them between two issue blocks were a quarter of that warp's time per stage.
 __device__ __forceinline__ uint32_t mbar_try(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
         : "r"(smem_addr(bar)), "r"(parity)
         : "memory");

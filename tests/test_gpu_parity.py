@@ -152,6 +152,31 @@ def test_pair_kernel_deterministic_any_range_and_dims(kaldi_params, cfg1):
         m2(torch.zeros(300, 32, device=DEV), torch.zeros(300, 32, device=DEV))
 
 
+def test_pair_kernel_mixed_mode_parity_and_range_guard(ref_out, kaldi_params, cfg1):
+    """IMPL_TC_PAIR_F8 (the pair kernel with layer 1 as fp16*fp16 + two e4m3*e4m3 products, four MMAs per K = 32 instead of
+    six): 1e-4 parity on the golden 10k pairs; inputs outside the range the e4m3 terms cover (too small, too large, NaN)
+    are recomputed on the device by the bf16x3 pair kernel behind it -- bit-identical to IMPL_TC_PAIR -- and a later
+    in-range call takes the mixed path again (the guard slot was cleared)."""
+    x1, x2, _ = cfg1
+    a, b = x1.to(DEV), x2.to(DEV)
+    m8 = make_nplda(kaldi_params, _lib.IMPL_TC_PAIR_F8)
+    mp = make_nplda(kaldi_params, npl.IMPL_TC_PAIR)
+    with torch.no_grad():
+        s = m8(a, b)
+        ok, worst = parity_ok(s, torch.from_numpy(ref_out["c1_scores"]), rel=1e-4)
+        assert ok and worst <= 0.5, worst
+        base = mp(a, b)
+        assert not torch.equal(s, base)                       # the mixed path really ran
+        for scale in (1e-3, 300.0):
+            assert torch.equal(m8(a * scale, b * scale), mp(a * scale, b * scale))
+        bad = a.clone()
+        bad[7, 100] = float("nan")
+        s_nan, p_nan = m8(bad, b), mp(bad, b)
+        assert torch.isnan(s_nan[7]) and torch.equal(s_nan[:7], p_nan[:7]) and torch.equal(s_nan[8:], p_nan[8:])
+        again = m8(a, b)
+        assert torch.equal(again, s)
+
+
 def test_tc_kernel_is_selected_and_deterministic(kaldi_params, cfg1):
     """IMPL_TC must run (no silent fallback) for the reference dims, agree with the SIMT kernel, and be
     bit-reproducible over back-to-back launches (the mbarrier pipelines have no data races)."""

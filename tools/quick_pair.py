@@ -23,7 +23,7 @@ def run(impl, cnt, a=None, b=None):
     _lib.check(lib.nplda_score_fwd(_lib.ptr(a), _lib.ptr(b), cnt, 512, 170, 170, _lib.ptr(pack), _lib.ptr(out), impl, _lib.stream_ptr()), "k1")
     torch.cuda.synchronize()
     return out
-PAIR, BF16 = 5, npl.IMPL_TC_BF16
+PAIR, BF16, PAIRF8 = 5, npl.IMPL_TC_BF16, 6
 worst_all, ident_all = 0.0, True
 for cnt in (1, 63, 64, 65, 127, 128, 129, 9471, 9472, 9473, 100_003, 1_000_000):
     ref = run(npl.IMPL_SIMT, cnt).double()
@@ -31,18 +31,24 @@ for cnt in (1, 63, 64, 65, 127, 128, 129, 9471, 9472, 9473, 100_003, 1_000_000):
     got = run(PAIR, cnt); one = run(BF16, cnt)
     w = float(((got.double() - ref).abs() / bound).max()); worst_all = max(worst_all, w)
     ident = bool((got == one).all()); ident_all &= ident
+    g8 = run(PAIRF8, cnt).double()
+    w8 = float(((g8 - ref).abs() / bound).max()); worst_all = max(worst_all, w8)
     print(f"parity pair n={cnt}: worst/bound {w:.3f} {'OK' if w <= 1 else 'FAIL'}  identical to one-CTA bf16x3: {ident}"
-          f"  max|diff| {float((got - one).abs().max()):.3e}", flush=True)
+          f"  max|diff| {float((got - one).abs().max()):.3e}   pair-f8 worst/bound {w8:.3f} {'OK' if w8 <= 1 else 'FAIL'}", flush=True)
 for sc in (1e-3, 300.0):          # any fp32 range
     a, b = x1[:200_000] * sc, x2[:200_000] * sc
     ref = run(npl.IMPL_SIMT, 200_000, a, b).double(); got = run(PAIR, 200_000, a, b).double()
     bound = 1e-4 * torch.maximum(ref.abs(), ref.pow(2).mean().sqrt())
     w = float(((got - ref).abs() / bound).max()); worst_all = max(worst_all, w)
-    print(f"range x*{sc}: worst/bound {w:.3f}", flush=True)
+    g8 = run(PAIRF8, 200_000, a, b)
+    w8 = float(((g8.double() - ref).abs() / bound).max()); worst_all = max(worst_all, w8)
+    print(f"range x*{sc}: worst/bound {w:.3f}; pair-f8 (guard -> bf16x3 pass) worst/bound {w8:.3f}, identical to pair bf16x3: {bool((g8 == got.float()).all())}", flush=True)
+chk = run(PAIRF8, 100_003)        # an in-range call after the guarded ones takes the mixed path again
+print("pair-f8 after guard: differs from bf16x3 (mixed path taken):", bool((chk != run(PAIR, 100_003)).any()), flush=True)
 scores = torch.empty(n, device=dev)
 def k1(impl):
     _lib.check(lib.nplda_score_fwd(_lib.ptr(x1), _lib.ptr(x2), n, 512, 170, 170, _lib.ptr(pack), _lib.ptr(scores), impl, _lib.stream_ptr()), "k1")
-which = {"pair": PAIR, "one": BF16}
+which = {"pair": PAIR, "pairf8": PAIRF8, "one": BF16}
 res = {nm: [] for nm in which}
 for r in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     for nm, impl in which.items():        # interleaved, with an idle pause: burst-regime numbers
