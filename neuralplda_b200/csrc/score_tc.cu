@@ -867,8 +867,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant_
                     na.advance();
                     nb.advance();
                     // Probes of the next stage's barriers, issued BEFORE this stage's MMAs and looked at after the first
-                    // K step: an already-complete try_wait still takes ~90 cycles to answer, and two of them between
-                    // the issue blocks were a third of this warp's time per stage.
+                    // K step: an already-complete wait still takes ~90 cycles to answer, and two of them between the
+                    // issue blocks were a third of this warp's time per stage.  (Two issue blocks per stage on purpose:
+                    // the single block that gains 3-4 % in the CTA-pair kernels loses 1-5 % here, A/B on one box.)
                     uint32_t ok_a = 1, ok_b = 1;
                     if (s + 1 < s_end) { ok_a = mbar_try(&a_full[na.stage], na.phase); ok_b = mbar_try(&b_full[nb.stage], nb.phase); }
                     if (elect_one() && !skip_mma) {

@@ -297,16 +297,11 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     // (an already-complete try_wait still takes ~90 cycles to answer)
                     uint32_t ok_a = 1, ok_b = 1;
                     if (s + 1 < s_end && !(g.variant & 1)) { ok_a = mbar_try(&a_full[na.stage], na.phase); ok_b = mbar_try(&b_full[nb.stage], nb.phase); }
+                    // one issue block per stage (the probes made the mid-stage waits unnecessary)
                     if (elect_one()) {
                         mma2_ss(dcol, ad, bd, IDESC, s != 0);
                         mma2_ss(dcol, ad + 4, bd, IDESC, 1);
                         mma2_ss(dcol, ad, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
-                    }
-                    __syncwarp();
-                    if (!ok_a) mbar_wait(&a_full[na.stage], na.phase);
-                    if (!ok_b) mbar_wait(&b_full[nb.stage], nb.phase);
-                    __syncwarp();
-                    if (elect_one()) {
                         mma2_ss(dcol, ad + 2, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
                         mma2_ss(dcol, ad + 6, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
                         mma2_ss(dcol, ad + 2, bd + ((6 * KCH_BH) >> 4), IDESC, 1);
@@ -314,6 +309,8 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         mma2_commit_mc(&b_empty[rb.stage], 3);
                     }
                     __syncwarp();
+                    if (!ok_a) mbar_wait(&a_full[na.stage], na.phase);
+                    if (!ok_b) mbar_wait(&b_full[nb.stage], nb.phase);
                     if (s + 1 < s_end && (g.variant & 1)) {
                         mbar_wait(&a_full[na.stage], na.phase);
                         mbar_wait(&b_full[nb.stage], nb.phase);
@@ -348,11 +345,6 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             mma2_ss(dcol, uhi, bd, IDESC, ks != 0);
                             mma2_ss(dcol, ulo, bd, IDESC, 1);
                             mma2_ss(dcol, uhi, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
-                        }
-                        __syncwarp();
-                        if (!ok_b) mbar_wait(&b_full[nb.stage], nb.phase);
-                        __syncwarp();
-                        if (elect_one()) {
                             if (ks + 1 < g.ksteps2) {
                                 const uint64_t uhi1 = uhi + ((2 * KCH_U) >> 4), ulo1 = ulo + ((2 * KCH_U) >> 4);
                                 mma2_ss(dcol, uhi1, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
@@ -361,6 +353,8 @@ score_tcx_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             }
                             mma2_commit_mc(&b_empty[rb.stage], 3);
                         }
+                        __syncwarp();
+                        if (!ok_b) mbar_wait(&b_full[nb.stage], nb.phase);
                         __syncwarp();
                         rb = nb;
                     }
