@@ -109,6 +109,8 @@ struct Args {
 #define PFLUSH() do { } while (0)
 #endif
 
+__device__ __forceinline__ int pair_of_row(int rsub) { return ((rsub & 1) << 2) | (rsub >> 1); }
+
 struct Ring {
     uint32_t stage = 0, phase = 0;
     int n;
@@ -231,7 +233,7 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
         const int q = warp & 3, h = warp >> 2;                  // TMEM quadrant, 16-lane half
         const int rsub = lane >> 2, cq = lane & 3;
         const int mrow = q * 32 + h * 16 + rsub;                 // side-0 row; side 1 is mrow + 8
-        const int pl = q * 16 + h * 8 + rsub;                    // pair within the tile
+        const int pl = q * 16 + h * 8 + pair_of_row(rsub);       // pair within the tile (the converters' row permutation)
         const uint32_t tbase = tmem + ((uint32_t)(q * 32 + h * 16) << 16);
         uint8_t *u0 = Us + (mrow >> 3) * 128 + (mrow & 7) * 16 + cq * 4;   // + kchunk * KCH_U
         uint8_t *u1 = u0 + 128;                                            // row + 8: next core matrix
@@ -359,15 +361,15 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
         const int cset = (warp - EPI_WARPS) >> 3;
         const int q = warp & 3, h = ((warp - EPI_WARPS) >> 2) & 1;
         const int rsub = lane >> 2, cq = lane & 3;
-        const int pl = q * 16 + h * 8 + rsub;                    // pair within the tile = row of both x boxes
+        // MMA row rsub of a 16-row group holds pair pair_of_row(rsub) = 0, 4, 1, 5, 2, 6, 3, 7 of the group's eight: the two
+        // rows a quarter-warp reads with one LDS.128 (rsub = 2j, 2j + 1) then differ in bit 2, and under the 128-byte swizzle
+        // of the x boxes (16-byte chunk c of row r sits at chunk c ^ (r & 7)) one of them reads chunks 0-3 and the other
+        // chunks 4-7 -- conflict-free without the register swap that fetching the chunks in opposite order needed (a fifth
+        // of the converters' instructions).  The epilogue stores a row's score to the pair it belongs to.
+        const int pl = q * 16 + h * 8 + pair_of_row(rsub);       // pair within the tile = row of both x boxes
         const uint32_t st_addr = tmem + ((uint32_t)(q * 32 + h * 16) << 16) + A_COL0;
-        // 128-byte swizzle of the x boxes: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)).  Odd rows fetch their
-        // two chunks in the opposite order: within a quarter-warp (2 rows x 4 lanes) the even row then reads one half
-        // of the banks and the odd row the other (conflict-free LDS.128).
-        const bool odd = (rsub & 1) != 0;
-        const int offk0 = pl * 128 + ((cq ^ rsub) << 4);         // k-step 0: chunks 0-3
-        const int offk1 = pl * 128 + (((4 + cq) ^ rsub) << 4);   // k-step 1: chunks 4-7
-        const int off0 = odd ? offk1 : offk0, off1 = odd ? offk0 : offk1;
+        const int off0 = pl * 128 + ((cq ^ (pl & 7)) << 4);      // k-step 0: chunks 0-3
+        const int off1 = pl * 128 + (((4 + cq) ^ (pl & 7)) << 4);   // k-step 1: chunks 4-7
         const int64_t total = T * g.nst1;
         // Set s owns stages it = s, s + 2, ...; NX is even, so it owns the x slots of its own parity and is the ONLY waiter
         // of their barriers: it observes every phase (a parity wait is ambiguous for a waiter that can fall a whole
@@ -394,7 +396,6 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
             } else {
                 a0 = a1 = b0 = b1 = make_float4(1.f, 2.f, 3.f, 4.f);
             }
-            if (odd) { float4 t = a0; a0 = a1; a1 = t; t = b0; b0 = b1; b1 = t; }
             // registers of tcgen05.st.16x256b.x2: r0,r1 -> (row, cols 2j,2j+1)  r2,r3 -> (row+8, same cols);
             // r4..r7 the same for the next 8 columns (k + 16)
             uint32_t hi[8], lo[8];

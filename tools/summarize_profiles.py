@@ -93,13 +93,13 @@ for fn in sorted(os.listdir(G)):
             if any(base == k for k in KEYS):
                 f.write(f"{base},{u},{v}\n"); got[base] = (u, v)
     print("wrote", outname)
-    if name == "score_tc" and "dram__bytes_read.sum" in got:
+    if name == "score_tcp" and "dram__bytes_read.sum" in got:       # the kernel the bench step launches (K1p)
         def tobytes(u, v):
             v = float(v.replace(",", ""))
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         rd, wr = tobytes(*got["dram__bytes_read.sum"]), tobytes(*got["dram__bytes_write.sum"])
         json.dump({"kernel": kname[:80], "pairs": 1000000, "dram_bytes_read": rd, "dram_bytes_write": wr, "commit": git_head(),
                    "source": f"ncu --set full --clock-control none, one launch of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline "
-                             f"--skip-e2e` (tools/r2_profiles.sh); summary in profiles/{outname}"},
+                             f"--skip-e2e` (tools/r2_profiles_final.sh); summary in profiles/{outname}"},
                   open(os.path.join(P, "k1_traffic.json"), "w"), indent=1)
         print("wrote k1_traffic.json", rd, wr)
