@@ -77,7 +77,7 @@ int64_t nplda_launch_count(void);
  * reference's own idiom, models.py:449-457, :420) nor fused optimisers bump
  * tensor._version.  nplda_pack_bytes() gives the workspace size for given dims;
  * ZERO the workspace once when it is allocated.
- * flags: NPLDA_PACK_MIXED also builds the layer-1 image of NPLDA_IMPL_TC_F8
+ * flags: NPLDA_PACK_MIXED also builds the layer-1 images of NPLDA_IMPL_TC_F8 / NPLDA_IMPL_TC_PAIR_F8
  * (two more kernels; without it that impl falls back to NPLDA_IMPL_TC on the
  * device); NPLDA_PACK_EPOCH_ODD selects which of the two fingerprint slots this
  * call fills -- alternate it between successive packs of one workspace.  The

@@ -10,7 +10,7 @@ int tc_pack_nplda(const float *W1, const float *b1, const float *W2, const float
 int tc_pack_dplda(const float *W1, const float *b1, const float *w_lr, const float *c_lr,
                   const PackLayout &L, char *pack, cudaStream_t st);   // score_tc.cu
 int tcx_pack_nplda(const float *W1, const float *b1, const float *W2, const PackLayout &L, char *pack, cudaStream_t st);   // score_tcx.cu
-int tcp_pack_nplda(const float *W1, const float *W2, const PackLayout &L, char *pack, cudaStream_t st);   // score_tcp.cu
+int tcp_pack_nplda(const float *W1, const float *W2, const PackLayout &L, char *pack, int flags, cudaStream_t st);   // score_tcp.cu
 
 // Content fingerprint of the packed parameters.  Callers cannot be trusted to say when parameters changed:
 // the reference itself writes them through `.data.copy_()` (models.py:449-457, :420) and fused optimisers update
@@ -127,7 +127,7 @@ extern "C" int nplda_pack_weights(const float *W1, const float *b1, const float 
     pack_nplda_kernel<<<2 * sm_count(), 256, 0, st>>>(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack, (flags >> 1) & 1);
     NPLDA_LAUNCH_CHECK();
     int rc = tc_pack_nplda(W1, b1, W2, b2, p_sqrt, q, L, (char *)pack, flags, st);
-    if (rc == NPLDA_OK) rc = tcp_pack_nplda(W1, W2, L, (char *)pack, st);
+    if (rc == NPLDA_OK) rc = tcp_pack_nplda(W1, W2, L, (char *)pack, flags, st);
     if (rc != NPLDA_OK || !(flags & NPLDA_PACK_PAIR)) return rc;
     return tcx_pack_nplda(W1, b1, W2, L, (char *)pack, st);
 }

@@ -1307,6 +1307,8 @@ int64_t tc_image_bytes(int d_in, int d1, int d2) {
 
 // {2^gw1, 2^-gw1, 2^gw2, 2^-gw2, max_j ||W1_j||_1, max|b1|} of a NeuralPlda pack (score_tcx.cu reads it too)
 const float *tc_hdr16(const PackLayout &L, const char *pack) { return (const float *)(pack + L.tc + tc_area(L.d_in, L.d1).hdr16); }
+// MODE 1 header: [2] != 0 when the pack built the mixed images (NPLDA_PACK_MIXED); score_tcp.cu's mixed mode reads it too
+const float *tc_hdr_mixed(const PackLayout &L, const char *pack) { return (const float *)(pack + L.tc + tc_area(L.d_in, L.d1).hdr); }
 
 bool tc_shape_ok(bool dplda, const PackLayout &L, bool indexed) {
     return !dplda && !indexed && tc_dims_ok(L.d_in, L.d1, L.d2) && L.tc_bytes > 0;

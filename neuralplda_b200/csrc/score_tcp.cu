@@ -76,6 +76,7 @@ struct Args {
     int ksteps2;            // layer-2 K steps = round_up(d1, 16) / 16
     const float *b1, *b2, *p, *q;   // padded to >= NPAD floats
     float *scores;
+    const float *hdrm;      // MODE 1: hdrm[2] != 0 when this pack built the mixed images (flag NPLDA_PACK_MIXED); else every tile is flagged
     const float *hdr16;     // MODE 1: {2^gw1, 2^-gw1, ...} of the pack (tc_scales_kernel): max|W1| 2^gw1 is in [8192, 16384)
     int *guard;             // MODE 1: guard[0] is set when an input leaves the range the mode covers; MODE 0 with guard != nullptr:
                             //         run only if guard[0] is set (fallback pass behind a MODE 1 launch), then clear it
@@ -224,6 +225,7 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
     constexpr uint32_t IDESC0 = make_idesc_fmt0(256, NPAD);       // MODE 1 layer 1: fp16 x fp16 and e4m3 x e4m3
     // MODE 1: the accumulator holds (2^9 x) (2^gm W) with 2^gm = 2^gw1 / 256 (max|W| 2^gm in [32, 64))
     const float s1 = MODE == 1 ? g.hdr16[1] * 0.5f : 1.f;
+    const bool img_ok = MODE != 1 || g.hdrm[2] != 0.f;
 #ifdef TCP_PROF
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ptime = clock64();
 #endif
@@ -467,7 +469,7 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                 // the stages it converted); nst1 is even, so the sets keep their stage parity in every tile
                 sit += 2;
                 if (sit >= g.nst1) {
-                    if (tile_base(tile_i) + pl < g.n && amax < 0.25f) *reinterpret_cast<volatile int *>(g.guard) = 1;
+                    if (tile_base(tile_i) + pl < g.n && (amax < 0.25f || !img_ok)) *reinterpret_cast<volatile int *>(g.guard) = 1;
                     amax = 0.f; sit -= g.nst1; ++tile_i;
                 }
             }
@@ -835,11 +837,12 @@ int64_t tcp_image_bytes(int d_in, int d1, int d2) {
 bool tcp_shape_ok(const PackLayout &L) { return tcp_dims_ok(L.d_in, L.d1, L.d2) && L.tcp_bytes > 0; }
 
 const float *tc_hdr16(const PackLayout &L, const char *pack);   // score_tc.cu: weight scales (tc_scales_kernel)
+const float *tc_hdr_mixed(const PackLayout &L, const char *pack);   // score_tc.cu: [2] != 0 when the pack built the mixed images
 int *tc_guard_slot();                                           // score_tc.cu: range-guard slots of the mixed-precision paths
 
-// pair images of a NeuralPlda pack: [bf16 W1: d_in / 32 stages][bf16 W2: ceil(ksteps2 / 2) stages][mixed W1], two launches
-// (the mixed image reads the scales the tensor-core pack left on this stream)
-int tcp_pack_nplda(const float *W1, const float *W2, const PackLayout &L, char *pack, cudaStream_t st) {
+// pair images of a NeuralPlda pack: [bf16 W1: d_in / 32 stages][bf16 W2: ceil(ksteps2 / 2) stages] in one launch; with
+// NPLDA_PACK_MIXED also [mixed W1] (it reads the scales the tensor-core pack left on this stream)
+int tcp_pack_nplda(const float *W1, const float *W2, const PackLayout &L, char *pack, int flags, cudaStream_t st) {
     if (!tcp_shape_ok(L)) return NPLDA_OK;
     uint8_t *img1 = (uint8_t *)pack + L.tcp;
     uint8_t *img2 = img1 + tcp_pair_image_bytes(L.d_in / tcp::KST);
@@ -847,6 +850,7 @@ int tcp_pack_nplda(const float *W1, const float *W2, const PackLayout &L, char *
     tcp::pair_pack_bf16_kernel<<<sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / tcp::KST, img1, W2, L.d2, L.d1,
                                                           tcp_nst2(L.d1), img2);
     NPLDA_LAUNCH_CHECK();
+    if (!(flags & NPLDA_PACK_MIXED)) return NPLDA_OK;      // the mixed images are opt-in (tc_pack_nplda marks them valid / invalid)
     tcp::pair_pack_mixed_kernel<<<sm_count(), 256, 0, st>>>(W1, L.d1, L.d_in, L.d_in / tcp::KST, tc_hdr16(L, pack), img1m);
     NPLDA_LAUNCH_CHECK();
     return NPLDA_OK;
@@ -887,6 +891,7 @@ int score_tcp(const float *x1, const float *x2, int64_t n, const PackLayout &L, 
     a.p = (const float *)(pack + L.p); a.q = (const float *)(pack + L.q);
     a.scores = scores;
     a.hdr16 = tc_hdr16(L, pack);
+    a.hdrm = tc_hdr_mixed(L, pack);
     a.guard = nullptr;
     a.dbg = 0;
 #ifdef TCP_DBG

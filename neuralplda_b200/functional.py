@@ -215,7 +215,7 @@ class NpldaScoreFn(torch.autograd.Function):
         _check_pair_inputs(x1, x2, d_in)
         x1c, x2c = _f32c(x1), _f32c(x2)
         n = x1c.shape[0]
-        pack = packed.get("nplda", (W1, b1, W2, b2, P_sqrt, Q), d_in, d1, d2, mixed=(impl == _lib.IMPL_TC_F8))
+        pack = packed.get("nplda", (W1, b1, W2, b2, P_sqrt, Q), d_in, d1, d2, mixed=(impl in (_lib.IMPL_TC_F8, _lib.IMPL_TC_PAIR_F8)))
         scores = torch.empty(n, dtype=torch.float32, device=x1c.device)
         ctx.act = None
         with on_device(x1c.device):
@@ -473,7 +473,7 @@ def score_indexed(kind, table, i1, i2, params, dims, packed, impl=_lib.IMPL_AUTO
     table = _f32c(table)
     scores = torch.empty(n, dtype=torch.float32, device=dev)
     fp, flag = _flag(dev, flag_ptr)
-    pack = packed.get(kind, params, d_in, d1, d2, mixed=(impl == _lib.IMPL_TC_F8))
+    pack = packed.get(kind, params, d_in, d1, d2, mixed=(impl in (_lib.IMPL_TC_F8, _lib.IMPL_TC_PAIR_F8)))
     if impl in (_lib.IMPL_TC, _lib.IMPL_TC_F8, _lib.IMPL_TC_BF16, _lib.IMPL_TC_PAIR):
         impl = _lib.IMPL_AUTO                     # the materialised-pair tcgen05 kernel has no gather; fp32 kernel
     with on_device(dev):

@@ -1078,6 +1078,10 @@ def test_mixed_impl_without_and_with_mixed_image(kaldi_params, cfg1):
     with torch.no_grad():
         s_tc = m(a, b)
     assert torch.equal(out, s_tc)                                # the fallback pass is the bf16x3 kernel
+    # the same for the CTA-pair kernel's mixed mode: stale / absent mixed pair image -> every tile flagged -> bf16x3 pair pass
+    _lib.check(_lib.lib().nplda_score_fwd(_lib.ptr(a), _lib.ptr(b), 4096, 512, 170, 170, _lib.ptr(pack), _lib.ptr(out),
+                                          _lib.IMPL_TC_PAIR_F8, _lib.stream_ptr()), "nplda_score_fwd")
+    assert torch.equal(out, s_tc)
 
 
 def test_loader_gather_bit_exact(ref_out):

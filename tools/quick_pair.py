@@ -16,7 +16,7 @@ for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias",
 n = 1_000_000
 x1, x2, t = bench.synth_on_device(n, 1002, kp["mean"].to(dev), dev)
 lib = _lib.lib()
-pack = m.packed.get("nplda", m._params(), 512, 170, 170)
+pack = m.packed.get("nplda", m._params(), 512, 170, 170, mixed=True)
 def run(impl, cnt, a=None, b=None):
     a = x1 if a is None else a; b = x2 if b is None else b
     out = torch.full((cnt,), float("nan"), device=dev)
