@@ -1,5 +1,6 @@
 """Small run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck): the tcgen05 score kernel in
-all its forms (plain, fp16x3 + guarded fallback, f8, EMIT, DPL, BWD), SIMT, the CTA-pair kernel over a pre-split table,
+all its forms (plain, fp16x3 + guarded fallback, f8, EMIT, DPL, BWD), the CTA-pair kernel on materialised pairs (bf16x3 and mixed +
+guarded fallback), SIMT, the CTA-pair kernel over a pre-split table,
 trial lists (per-trial and sub-grid + gather), grids, losses, both backward paths, the DPlda gradient kernel, sort.
 SANITIZE_SMALL=1 shrinks the batches (racecheck is ~100x slower than memcheck)."""
 import os, sys, numpy as np, torch
@@ -18,7 +19,7 @@ for name, key in (("centering_and_LDA.weight", "W1"), ("centering_and_LDA.bias",
 SMALL = os.environ.get("SANITIZE_SMALL") == "1"
 x1, x2, t = O.synth_pairs((2000 if SMALL else 20000) + 37, 50, seed=3, mean=kp["mean"])
 a, b, y = x1.to(dev), x2.to(dev), t.to(dev)
-for impl in (npl.IMPL_TC, npl.IMPL_TC_F8, npl.IMPL_SIMT):
+for impl in (npl.IMPL_TC, npl.IMPL_TC_F8, npl.IMPL_SIMT, npl.IMPL_TC_BF16, npl.IMPL_TC_PAIR, _lib.IMPL_TC_PAIR_F8):
     m.impl = impl
     with torch.no_grad():
         s = m(a, b); s2 = m(a * 1000, b * 1000)
