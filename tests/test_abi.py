@@ -59,3 +59,19 @@ def test_bad_arguments_are_rejected_without_a_device():
     assert L.nplda_minc_sweep(null, 0, null, 0, 1.0, 1.0, _lib.betas_array([99.0]), 1, null, null, null) == -1
     with pytest.raises(RuntimeError):
         _lib.check(-3, "x")
+
+
+def test_header_constants_match_the_python_binding():
+    """Every NPLDA_IMPL_* / NPLDA_PACK_* / NPLDA_LOSS_* constant of include/nplda.h has the same value in _lib.py (the
+    ctypes layer passes them through as plain ints), and an impl id the header does not define is rejected."""
+    hdr = open(os.path.join(ROOT, "include", "nplda.h")).read()
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+NPLDA_((?:IMPL|PACK|LOSS)_[A-Z0-9_]+)\s+(-?\d+)", hdr)}
+    assert {"IMPL_AUTO", "IMPL_SIMT", "IMPL_TC", "IMPL_TC_F8", "IMPL_TC_BF16", "IMPL_TC_PAIR", "IMPL_TC_PAIR_F8",
+            "PACK_MIXED", "PACK_EPOCH_ODD", "PACK_PAIR"} <= set(consts)
+    for name, value in consts.items():
+        assert getattr(_lib, name) == value, name
+    impls = sorted(v for k, v in consts.items() if k.startswith("IMPL_"))
+    assert impls == list(range(len(impls)))                       # dense ids: the dispatcher's range check covers them all
+    L = _lib.lib()
+    one = ctypes.c_void_p(16)
+    assert L.nplda_score_fwd(one, one, 5, 512, 170, 170, one, one, len(impls), ctypes.c_void_p(None)) == -1
