@@ -486,8 +486,8 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
             const uint32_t b_base = smem_addr(Bs), u_base = smem_addr(Us);
             const int half = g.nst1 / 2;
             // One stage: K = 32 as two K = 16 steps, each hi*Whi + lo*Whi + hi*Wlo.  A: TMEM columns of the stage (same
-            // address in both CTAs); B: chunks 0-3 hi, 4-7 lo of this CTA's half, two chunks per step.  The barrier waits
-            // of stage s + 1 sit between the two K steps of stage s (they run under the MMAs already queued).
+            // address in both CTAs); B: chunks 0-3 hi, 4-7 lo of this CTA's half, two chunks per step.  The barriers of
+            // stage s + 1 are probed before the MMAs of stage s are issued (the answers arrive under them).
             auto layer1 = [&](uint32_t dcol, int s_begin, int s_end) {
                 if (s_begin >= s_end) return;
                 PMARK(6);
@@ -505,38 +505,6 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                     // probes of the next stage's barriers: issued before this stage's MMAs, answered under them
                     uint32_t ok_a = 1, ok_b = 1;
                     if (s + 1 < s_end) { ok_a = mbar_try(&a_full[na.stage], na.phase); ok_b = mbar_try(&b_full[nb.stage], nb.phase); }
-#ifdef TCP_TWOBLOCKS
-                    if (elect_one() && !DBG(4)) {
-                        if (MODE == 1) {        // fp16 x fp16, K steps 0 and 1 (chunks 0-1, 2-3)
-                            mma2_ts(dcol, acol, bd, IDESC0, s != 0);
-                            mma2_ts(dcol, acol + 8, bd + ((2 * KCH_BH) >> 4), IDESC0, 1);
-                        } else {
-                            mma2_ts(dcol, acol, bd, IDESC, s != 0);
-                            mma2_ts(dcol, acol + 16, bd, IDESC, 1);
-                            mma2_ts(dcol, acol, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
-                        }
-                    }
-                    __syncwarp();
-                    PMARK(3);
-                    if (!ok_a) TWAIT(&a_full[na.stage], na.phase, 0x108 | ((s + 1) << 20));
-                    PMARK(1);
-                    if (!ok_b) TWAIT(&b_full[nb.stage], nb.phase, 0x109 | ((s + 1) << 20));
-                    __syncwarp();
-                    PMARK(2);
-                    if (elect_one()) {
-                        if (DBG(4)) {
-                        } else if (MODE == 1) {        // e4m3(residual) x e4m3(W'h) and e4m3(x) x e4m3(2^9 W'l), K = 32 each (chunks 4-5, 6-7)
-                            mma2_f8_ts(dcol, acol + 16, bd + ((4 * KCH_BH) >> 4), IDESC0, 1);
-                            mma2_f8_ts(dcol, acol + 24, bd + ((6 * KCH_BH) >> 4), IDESC0, 1);
-                        } else {
-                            mma2_ts(dcol, acol + 8, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
-                            mma2_ts(dcol, acol + 24, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
-                            mma2_ts(dcol, acol + 8, bd + ((6 * KCH_BH) >> 4), IDESC, 1);
-                        }
-                        mma2_commit_mc(&a_empty[ra.stage], 3);
-                        mma2_commit_mc(&b_empty[rb.stage], 3);
-                    }
-#else
                     // one issue block per stage: the probes made the mid-stage waits unnecessary, and every elected block
                     // costs its own vote, branch and register -> uniform-register moves
                     if (elect_one()) {
@@ -563,7 +531,6 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                     PMARK(1);
                     if (!ok_b) TWAIT(&b_full[nb.stage], nb.phase, 0x109 | ((s + 1) << 20));
                     PMARK(2);
-#endif
                     __syncwarp();
                     ra = na;
                     rb = nb;
@@ -599,27 +566,6 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                         Ring nb = rb;
                         nb.advance();
                         const uint32_t ok_b = ks + 2 < g.ksteps2 ? mbar_try(&b_full[nb.stage], nb.phase) : 1u;
-#ifdef TCP_TWOBLOCKS
-                        if (elect_one() && !DBG(4)) {
-                            mma2_ss(dcol, uhi, bd, IDESC, ks != 0);
-                            mma2_ss(dcol, ulo, bd, IDESC, 1);
-                            mma2_ss(dcol, uhi, bd + ((4 * KCH_BH) >> 4), IDESC, 1);
-                        }
-                        __syncwarp();
-                        PMARK(5);
-                        if (!ok_b) TWAIT(&b_full[nb.stage], nb.phase, 0x10d);
-                        __syncwarp();
-                        PMARK(2);
-                        if (elect_one()) {
-                            if (ks + 1 < g.ksteps2 && !DBG(4)) {
-                                const uint64_t uhi1 = uhi + ((2 * KCH_U) >> 4), ulo1 = ulo + ((2 * KCH_U) >> 4);
-                                mma2_ss(dcol, uhi1, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
-                                mma2_ss(dcol, ulo1, bd + ((2 * KCH_BH) >> 4), IDESC, 1);
-                                mma2_ss(dcol, uhi1, bd + ((6 * KCH_BH) >> 4), IDESC, 1);
-                            }
-                            mma2_commit_mc(&b_empty[rb.stage], 3);
-                        }
-#else
                         if (elect_one()) {
                             if (!DBG(4)) {
                                 mma2_ss(dcol, uhi, bd, IDESC, ks != 0);
@@ -638,7 +584,6 @@ score_tcp_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constan
                         PMARK(5);
                         if (!ok_b) TWAIT(&b_full[nb.stage], nb.phase, 0x10d);
                         PMARK(2);
-#endif
                         __syncwarp();
                         rb = nb;
                     }
