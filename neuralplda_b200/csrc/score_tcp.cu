@@ -2,14 +2,16 @@
 // (models.py:378-382 -> :366-376) for x1, x2 of shape [N, 512], the layout BASELINE configs[1] is quoted on.
 //
 // Same arithmetic as score_tc.cu's MODE 0 ("bf16x3": every fp32 operand split x = hi + lo into two bf16 halves, products
-// as hi*hi + lo*hi + hi*lo with fp32 accumulation in tensor memory, any fp32 range), same tile and epilogue.  What
-// changes is who shares what: score_tc.cu runs one CTA per SM and every CTA streams the whole weight image (484 KB per
-// 64-pair tile) through a 3-stage ring -- with 64 KB of x in flight next to it the ring depths, not the tensor pipe,
-// pace that kernel (the MMA warp waits 15 % of its time for converted operands and 19 % for weights).  Here two CTAs of
-// a cluster (the two SMs of a TPC) execute M = 256 MMAs (tcgen05.mma.cta_group::2): each CTA converts its own 128 rows
-// into ITS tensor memory and holds HALF of the 176 weight rows, so
-//   * the weight stream L2 -> shared memory and the tensor cores' operand reads of it are halved,
-//   * a weight stage is 11 KB instead of 22.5 KB: five of them fit next to four 16 KB x stages where three did.
+// as hi*hi + lo*hi + hi*lo with fp32 accumulation in tensor memory, any fp32 range), same tile and epilogue: the scores
+// are bit-identical.  What changes is who shares what.  score_tc.cu runs one CTA per SM and every CTA streams the whole
+// weight image (484 KB per 64-pair tile).  Here two CTAs of a cluster (the two SMs of a TPC) execute M = 256 MMAs
+// (tcgen05.mma.cta_group::2): each CTA converts its own 128 rows into ITS tensor memory and holds HALF of the 176 weight
+// rows, so
+//   * the weight stream L2 -> shared memory (7.5 -> 3.75 GB per 1 M pairs) and the tensor cores' operand reads of it are
+//     halved,
+//   * a weight stage is 11 KB instead of 22.5 KB: five of them fit next to four 16 KB x stages where three did,
+//   * the MMA warp of one CTA issues for both: half as many issue blocks, waits and commits per pair scored.
+// Measured: 1.12-1.20 ms per 1 M pairs against 1.27-1.36 ms for the one-CTA kernel on the same boxes.
 // Roles per CTA (864 threads): X loader (TMA boxes of fp32 x into a swizzled ring, local barriers), 2 x 8 converter
 // warps (shared memory -> registers -> bf16 hi/lo -> tcgen05.st into a 5-stage A ring in tensor memory; they arrive on
 // the LEADER's a_full barriers through the cluster's shared-memory window), B loader (this CTA's half of every weight
