@@ -9,8 +9,7 @@
 // rows, so
 //   * the weight stream L2 -> shared memory (7.5 -> 3.75 GB per 1 M pairs) and the tensor cores' operand reads of it are
 //     halved,
-//   * a weight stage is 11 KB instead of 22.5 KB: five of them fit next to four 16 KB x stages where three did,
-//   * the MMA warp of one CTA issues for both: half as many issue blocks, waits and commits per pair scored.
+//   * a weight stage is 11 KB instead of 22.5 KB: five of them fit next to four 16 KB x stages where three did.
 // Measured: 1.12-1.20 ms per 1 M pairs against 1.27-1.36 ms for the one-CTA kernel on the same boxes.
 // Roles per CTA (864 threads): X loader (TMA boxes of fp32 x into a swizzled ring, local barriers), 2 x 8 converter
 // warps (shared memory -> registers -> bf16 hi/lo -> tcgen05.st into a 5-stage A ring in tensor memory; they arrive on
